@@ -1,0 +1,3 @@
+class LearningRateMonitor:
+    def __init__(self, *a, **k):
+        raise NotImplementedError("stub")

@@ -1,0 +1,3 @@
+class WandbLogger:
+    def __init__(self, *a, **k):
+        raise NotImplementedError("stub")
