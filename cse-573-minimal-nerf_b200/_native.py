@@ -1,0 +1,98 @@
+"""ctypes binding of libnerf_b200.so (include/nerf_b200.h).
+
+There is no CPU implementation behind this module: loading fails loudly when the library has not been
+built, and every wrapper rejects non-CUDA tensors.
+"""
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import torch
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libnerf_b200.so"
+ABI_VERSION = 1
+
+_c_f32p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_f32 = ctypes.c_float
+_vp = ctypes.c_void_p
+
+_PROTOTYPES = {
+    "nerf_abi_version": (ctypes.c_int, []),
+    "nerf_last_error": (ctypes.c_char_p, []),
+    "nerf_raygen": (_int, [_vp, _int, _int, _f32, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "nerf_coarse_sample": (_int, [_vp, _vp, _vp, _vp, _f32, _i64, _int, _vp, _vp, _vp]),
+    "nerf_deltas": (_int, [_vp, _i64, _int, _vp, _vp]),
+    "nerf_weights": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
+    "nerf_ray_color": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
+    "nerf_composite": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nerf_fine_sample": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "nerf_merge_sort": (_int, [_vp, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp, _vp]),
+    "nerf_positional_encoding": (_int, [_vp, _i64, _int, _int, _vp, _vp]),
+    "nerf_mlp_forward_fp32": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
+    "nerf_packed_bytes": (ctypes.c_size_t, []),
+    "nerf_pack_weights": (_int, [_vp, _vp, _vp]),
+    "nerf_mlp_forward_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
+    "nerf_mlp_forward_tc_points": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu for sm_100a into libnerf_b200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", str(HERE / "csrc"), "-j8"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("building libnerf_b200.so failed (see output above)")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library.  Raises if it is missing - there is deliberately no fallback."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the NeRF hot path has no CPU or PyTorch fallback)")
+        handle = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(handle, name)            # AttributeError if the header and the library disagree
+            fn.restype, fn.argtypes = res, args
+        if handle.nerf_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"libnerf_b200.so ABI {handle.nerf_abi_version()} != expected {ABI_VERSION}")
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return list(_PROTOTYPES)
+
+
+def check(code, what):
+    if code != 0:
+        raise RuntimeError(f"{what} failed ({code}): {lib().nerf_last_error().decode()}")
+
+
+def dev(t, name, dtype=torch.float32):
+    """Validate a tensor argument: CUDA, expected dtype, contiguous.  Returns the (possibly re-laid-out) tensor."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (this path has no CPU implementation), got device {t.device}")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,40 @@
+// common.cu - error state and device queries.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace nerf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return NERF_E_CUDA;
+    }
+    return 0;
+}
+
+int num_sms() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return cached > 0 ? cached : 148;
+}
+
+}  // namespace nerf
+
+extern "C" int nerf_abi_version(void) { return NERF_ABI_VERSION; }
+extern "C" const char* nerf_last_error(void) { return nerf::g_err; }

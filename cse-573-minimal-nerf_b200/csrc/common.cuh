@@ -1,0 +1,32 @@
+// common.cuh - shared host/device helpers for libnerf_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/nerf_b200.h"
+
+namespace nerf {
+
+// thread-local error text returned by nerf_last_error()
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);     // cudaGetLastError() -> 0 / NERF_E_CUDA
+int num_sms();                           // SM count of the current device (cached)
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+#define NERF_REQUIRE(cond, ...)                     \
+    do {                                            \
+        if (!(cond)) {                              \
+            nerf::set_error(__VA_ARGS__);           \
+            return NERF_E_ARG;                      \
+        }                                           \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+}  // namespace nerf

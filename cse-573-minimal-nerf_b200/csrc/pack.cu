@@ -1,0 +1,55 @@
+// pack.cu - K5: fp32 nn.Linear parameters (state_dict order) -> the bf16 swizzled stage image + fp32 biases
+// that mlp_tc.cu streams with bulk copies (layout in pack_layout.cuh).
+#include "common.cuh"
+#include "pack_layout.cuh"
+#include "umma.cuh"
+
+namespace nerf {
+
+__constant__ pk::Layout c_pack_layout = pk::kLayout;
+
+struct PackParams { const float* p[20]; };
+
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(PackParams P, uint8_t* __restrict__ packed) {
+    const int s = blockIdx.x;
+    if (s < pk::kStages) {
+        const pk::Stage st = c_pack_layout.st[s];
+        const float* W = P.p[2 * st.param];
+        uint8_t* tile = packed + st.offset;
+        for (int e = threadIdx.x; e < st.rows * 64; e += blockDim.x) {
+            const int r = e >> 6, k = e & 63;
+            float v = 0.f;
+            if (r < st.valid_rows && k < st.kvalid) v = W[(size_t)(st.n0 + r) * st.in_features + st.k0 + k];
+            *(__nv_bfloat16*)(tile + umma::sw128_offset(r, k)) = __float2bfloat16_rn(v);
+        }
+    } else {
+        float* b = (float*)(packed + c_pack_layout.bias_offset);
+        for (int i = threadIdx.x; i < pk::kBiasFloats; i += blockDim.x) {
+            float v = 0.f;
+            if (i < 1792) v = P.p[2 * (i >> 8) + 1][i & 255];                       // mlp.0 .. feature_fn.4
+            else if (i < 1920) v = P.p[17][i - 1792];                               // rgb_fn.0
+            else if (i == pk::kBiasSigma) v = P.p[15][0];                           // density_fn.0
+            else if (i >= pk::kBiasRgb && i < pk::kBiasRgb + 3) v = P.p[19][i - pk::kBiasRgb];   // rgb_fn.2
+            b[i] = v;
+        }
+    }
+}
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" size_t nerf_packed_bytes(void) { return pk::kLayout.total_bytes; }
+
+extern "C" int nerf_pack_weights(const float* const* params20_host, void* packed, void* stream) {
+    NERF_REQUIRE(params20_host && packed, "nerf_pack_weights: null pointer");
+    NERF_REQUIRE(((uintptr_t)packed & 127) == 0, "nerf_pack_weights: packed buffer must be 128-byte aligned");
+    PackParams P;
+    for (int i = 0; i < 20; ++i) {
+        NERF_REQUIRE(params20_host[i], "nerf_pack_weights: params20_host[%d] is NULL", i);
+        P.p[i] = params20_host[i];
+    }
+    pack_weights_kernel<<<pk::kStages + 1, 256, 0, (cudaStream_t)stream>>>(P, (uint8_t*)packed);
+    return check_launch("nerf_pack_weights");
+}

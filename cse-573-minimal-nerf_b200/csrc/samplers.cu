@@ -1,0 +1,367 @@
+// samplers.cu - the HBM-bound kernels of the NeRF hot path: ray generation, stratified sampling,
+// compositing, inverse-CDF fine sampling and the per-ray merge sort.
+//
+// Arithmetic contract: the reference runs these as eager fp32 torch ops on CPU, i.e.
+// separately rounded multiplies/adds, true divisions and *sequential* running sums.  Every operation that
+// feeds a sample depth or an index is therefore spelled with __f{add,sub,mul,div}_rn so nvcc cannot
+// contract it into an FMA, and running sums are taken in index order.  Given the same uniforms the
+// depths, points and bin indices are bit-identical to the oracle.
+//
+// Mapping: one warp per ray for everything that needs a running sum, a search or a sort (coalesced
+// 128-byte row loads, the serial chain broadcast through shuffles), one thread per element otherwise.
+#include "common.cuh"
+
+namespace nerf {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * kWarp;
+
+// ------------------------------------------------------------------------------------------ K0 raygen
+struct Pose { float r[3][3]; float t[3]; };
+
+__global__ void __launch_bounds__(256)
+raygen_kernel(Pose pose, int H, int W, float half_w, float half_h, float focal,
+              const int64_t* __restrict__ xs, const int64_t* __restrict__ ys, int64_t n,
+              float* __restrict__ o, float* __restrict__ d) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float col, row;
+        if (xs) { col = (float)xs[i]; row = (float)ys[i]; }
+        else    { col = (float)(i % W); row = (float)(i / W); }
+        // dataloader.py:39: [(i - W/2)/focal, -(j - H/2)/focal, -1], true fp32 divisions
+        const float d0 = __fdiv_rn(__fsub_rn(col, half_w), focal);
+        const float d1 = -__fdiv_rn(__fsub_rn(row, half_h), focal);
+        const float d2 = -1.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // dataloader.py:40: sum_j dirs_j * c2w[k,j], left to right
+            const float s = __fadd_rn(__fadd_rn(__fmul_rn(d0, pose.r[k][0]), __fmul_rn(d1, pose.r[k][1])),
+                                      __fmul_rn(d2, pose.r[k][2]));
+            d[i * 3 + k] = s;
+            o[i * 3 + k] = pose.t[k];
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------- K1 coarse sampling
+__global__ void __launch_bounds__(256)
+coarse_sample_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ u,
+                     const float* __restrict__ t_base, float step, int64_t total, int C,
+                     float* __restrict__ samples, float* __restrict__ ts) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = e / C;
+        const int i = (int)(e - n * C);
+        // nerf_helpers.py:52-53: ts = arange + rand * step
+        const float t = __fadd_rn(__ldg(t_base + i), __fmul_rn(u[e], step));
+        ts[e] = t;
+        if (samples) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)   // nerf_helpers.py:55: d * t + o
+                samples[e * 3 + k] = __fadd_rn(__fmul_rn(__ldg(d + n * 3 + k), t), __ldg(o + n * 3 + k));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2 pieces
+__global__ void __launch_bounds__(256)
+deltas_kernel(const float* __restrict__ ts, int64_t total, int S, float* __restrict__ deltas) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % S);
+        deltas[e] = (i == S - 1) ? 1e10f : __fsub_rn(ts[e + 1], ts[e]);   // nerf_helpers.py:71-72
+    }
+}
+
+// Sequential exclusive running sum of x over one ray, 32 elements at a time: lane k holds x[base+k]; the
+// chain s += x_k runs identically in every lane (values broadcast by shuffle), lane k keeps s before x_k.
+__device__ __forceinline__ float chunk_exclusive_scan(float x, float& running, int lane) {
+    float mine = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWarp; ++k) {
+        const float v = __shfl_sync(kFull, x, k);
+        if (lane == k) mine = running;
+        running = __fadd_rn(running, v);
+    }
+    return mine;
+}
+
+// One warp per ray.  kind 0: weights from (sigma, deltas) [nerf_weights]; kind 1: full composite from
+// (sigma, rgb, ts).
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+composite_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ ts_or_deltas,
+                 int64_t N, int S, float* __restrict__ deltas_out, float* __restrict__ weights_out,
+                 float* __restrict__ ray_rgb, float* __restrict__ depth, float* __restrict__ acc,
+                 float* __restrict__ stats2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * kWarpsPerBlock;
+    float st_sq = 0.f, st_nz = 0.f;
+    for (int64_t n = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); n < N; n += warps) {
+        const float* sg = sigma + n * S;
+        const float* tp = ts_or_deltas + n * S;
+        float running = 0.f;       // sum_{j<i} -sigma_j delta_j, nerf_helpers.py:86-89
+        float cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f;
+        for (int base = 0; base < S; base += kWarp) {
+            const int i = base + lane;
+            const bool in = i < S;
+            const float s = in ? sg[i] : 0.f;
+            float t = 0.f, dl = 0.f;
+            if (KIND == 1) {
+                t = in ? tp[i] : 0.f;
+                float tn = __shfl_down_sync(kFull, t, 1);
+                if (lane == 31 && i + 1 < S) tn = tp[i + 1];
+                dl = (i == S - 1) ? 1e10f : __fsub_rn(tn, t);             // nerf_helpers.py:71-72
+            } else {
+                dl = in ? tp[i] : 0.f;
+            }
+            const float x = in ? __fmul_rn(__fmul_rn(-1.0f, s), dl) : 0.f;   // -1 * density * deltas
+            const float excl = chunk_exclusive_scan(x, running, lane);
+            if (in) {
+                const float trans = expf(excl);                               // nerf_helpers.py:89
+                const float w = __fmul_rn(__fsub_rn(1.0f, expf(x)), trans);   // nerf_helpers.py:90
+                if (weights_out) weights_out[n * S + i] = w;
+                if (KIND == 1) {
+                    if (deltas_out) deltas_out[n * S + i] = dl;
+                    const float* c = rgb + (n * S + i) * 3;
+                    cr = fmaf(w, c[0], cr); cg = fmaf(w, c[1], cg); cb = fmaf(w, c[2], cb);
+                    dsum = fmaf(w, t, dsum); asum += w;
+                    st_sq = fmaf(s, s, st_sq); st_nz += (s != 0.f) ? 1.f : 0.f;
+                }
+            }
+        }
+        if (KIND == 1) {
+            cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+            dsum = warp_sum(dsum); asum = warp_sum(asum);
+            if (lane == 0) {
+                if (ray_rgb) { ray_rgb[n * 3 + 0] = cr; ray_rgb[n * 3 + 1] = cg; ray_rgb[n * 3 + 2] = cb; }
+                if (depth) depth[n] = dsum;
+                if (acc) acc[n] = asum;
+            }
+        }
+    }
+    if (KIND == 1 && stats2) {
+        st_sq = warp_sum(st_sq); st_nz = warp_sum(st_nz);
+        __shared__ float red[2][kWarpsPerBlock];
+        if (lane == 0) { red[0][threadIdx.x >> 5] = st_sq; red[1][threadIdx.x >> 5] = st_nz; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, b = 0.f;
+            for (int k = 0; k < kWarpsPerBlock; ++k) { a += red[0][k]; b += red[1][k]; }
+            atomicAdd(stats2 + 0, a);
+            atomicAdd(stats2 + 1, b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+ray_color_kernel(const float* __restrict__ w, const float* __restrict__ rgb, int64_t N, int S, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t n = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); n < N; n += warps) {
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        for (int i = lane; i < S; i += kWarp) {
+            const float wi = w[n * S + i];
+            const float* c = rgb + (n * S + i) * 3;
+            cr = fmaf(wi, c[0], cr); cg = fmaf(wi, c[1], cg); cb = fmaf(wi, c[2], cb);
+        }
+        cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+        if (lane == 0) { out[n * 3 + 0] = cr; out[n * 3 + 1] = cg; out[n * 3 + 2] = cb; }
+    }
+}
+
+// ----------------------------------------------------------------------------------- K3 fine sampling
+// One warp per ray.  Dynamic shared memory per warp: cdf[C] then bounds[C+2].
+__global__ void __launch_bounds__(kThreads)
+fine_sample_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ w,
+                   const float* __restrict__ ts, const float* __restrict__ eps, const float* __restrict__ u,
+                   const float* __restrict__ q_base, int64_t N, int C, int F, float near_, float far_,
+                   float* __restrict__ fine_samples, float* __restrict__ fine_ts, int64_t* __restrict__ idx_out) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* cdf = smem + (size_t)wib * (2 * C + 2);
+    float* bounds = cdf + C;
+    const int64_t warps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const float Ff = (float)F;
+    for (int64_t n = blockIdx.x * (int64_t)kWarpsPerBlock + wib; n < N; n += warps) {
+        // inclusive sequential cumsum of the weights (nerf_helpers.py:137)
+        float running = 0.f;
+        for (int base = 0; base < C; base += kWarp) {
+            const int i = base + lane;
+            const float x = (i < C) ? w[n * C + i] : 0.f;
+            const float excl = chunk_exclusive_scan(x, running, lane);
+            if (i < C) {
+                cdf[i] = __fadd_rn(excl, x);
+                bounds[i + 1] = ts[n * C + i];                                  // nerf_helpers.py:149
+            }
+        }
+        if (lane == 0) { bounds[0] = near_; bounds[C + 1] = far_; }
+        __syncwarp();
+        const float total = cdf[C - 1];
+        __syncwarp();
+        for (int i = lane; i < C; i += kWarp) cdf[i] = __fdiv_rn(cdf[i], total);   // nerf_helpers.py:138
+        __syncwarp();
+        const float e = __fdiv_rn(eps[n], Ff);                                      // nerf_helpers.py:139
+        const float ox = o[n * 3], oy = o[n * 3 + 1], oz = o[n * 3 + 2];
+        const float dx = d[n * 3], dy = d[n * 3 + 1], dz = d[n * 3 + 2];
+        for (int j = lane; j < F; j += kWarp) {
+            const float q = __fadd_rn(__ldg(q_base + j), e);                         // nerf_helpers.py:142
+            int lo = 0, hi = C;                                                       // torch.searchsorted, right=False
+            while (lo < hi) {
+                const int mid = lo + ((hi - lo) >> 1);
+                if (!(cdf[mid] >= q)) lo = mid + 1; else hi = mid;
+            }
+            const float b0 = bounds[lo], b1 = bounds[lo + 1];
+            const float t = __fadd_rn(b0, __fmul_rn(__fsub_rn(b1, b0), u[n * F + j]));   // nerf_helpers.py:154
+            fine_ts[n * F + j] = t;
+            if (idx_out) idx_out[n * F + j] = lo;
+            if (fine_samples) {                                                          // nerf_helpers.py:155
+                float* p = fine_samples + (n * F + j) * 3;
+                p[0] = __fadd_rn(ox, __fmul_rn(t, dx));
+                p[1] = __fadd_rn(oy, __fmul_rn(t, dy));
+                p[2] = __fadd_rn(oz, __fmul_rn(t, dz));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// -------------------------------------------------------------------------------------- K4 merge sort
+// One warp per ray, enumeration sort in shared memory: rank(e) = #{j : v_j < v_e or (v_j == v_e and j < e)}.
+// Dynamic shared memory per warp: vals[S] then sorted[S].
+__global__ void __launch_bounds__(kThreads)
+merge_sort_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ ts_a, int A,
+                  const float* __restrict__ ts_b, int B, int64_t N, float* __restrict__ ts_sorted,
+                  float* __restrict__ samples_sorted) {
+    extern __shared__ float smem[];
+    const int S = A + B;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* vals = smem + (size_t)wib * 2 * S;
+    float* sorted = vals + S;
+    const int64_t warps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t n = blockIdx.x * (int64_t)kWarpsPerBlock + wib; n < N; n += warps) {
+        for (int i = lane; i < A; i += kWarp) vals[i] = ts_a[n * A + i];           // nerf_model.py:117 (fine first)
+        for (int i = lane; i < B; i += kWarp) vals[A + i] = ts_b[n * B + i];
+        __syncwarp();
+        for (int e = lane; e < S; e += kWarp) {
+            const float v = vals[e];
+            int rank = 0;
+            for (int j = 0; j < S; ++j) {
+                const float x = vals[j];
+                rank += (x < v || (x == v && j < e)) ? 1 : 0;
+            }
+            sorted[rank] = v;
+        }
+        __syncwarp();
+        const float ox = o ? o[n * 3] : 0.f, oy = o ? o[n * 3 + 1] : 0.f, oz = o ? o[n * 3 + 2] : 0.f;
+        const float dx = d ? d[n * 3] : 0.f, dy = d ? d[n * 3 + 1] : 0.f, dz = d ? d[n * 3 + 2] : 0.f;
+        for (int i = lane; i < S; i += kWarp) {
+            const float t = sorted[i];
+            ts_sorted[n * S + i] = t;
+            if (samples_sorted) {
+                float* p = samples_sorted + (n * S + i) * 3;
+                p[0] = __fadd_rn(ox, __fmul_rn(t, dx));
+                p[1] = __fadd_rn(oy, __fmul_rn(t, dy));
+                p[2] = __fadd_rn(oz, __fmul_rn(t, dz));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static int grid_for(int64_t items, int per_block) {
+    int64_t blocks = (items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" int nerf_raygen(const float* c2w_host, int H, int W, float focal, const int64_t* xs, const int64_t* ys,
+                           int64_t n, float* o, float* d, void* stream) {
+    NERF_REQUIRE(c2w_host && o && d, "nerf_raygen: null pointer");
+    NERF_REQUIRE(H > 0 && W > 0 && n >= 0, "nerf_raygen: bad size H=%d W=%d n=%lld", H, W, (long long)n);
+    NERF_REQUIRE((xs == nullptr) == (ys == nullptr), "nerf_raygen: xs and ys must both be given or both be NULL");
+    NERF_REQUIRE(xs || n == (int64_t)H * W, "nerf_raygen: full-grid mode needs n == H*W");
+    if (n == 0) return 0;
+    Pose p;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) p.r[r][c] = c2w_host[r * 4 + c];
+        p.t[r] = c2w_host[r * 4 + 3];
+    }
+    raygen_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, H, W, (float)(W * .5), (float)(H * .5), focal,
+                                                                     xs, ys, n, o, d);
+    return check_launch("nerf_raygen");
+}
+
+extern "C" int nerf_coarse_sample(const float* o, const float* d, const float* u, const float* t_base, float step,
+                                  int64_t N, int C, float* samples, float* ts, void* stream) {
+    NERF_REQUIRE(o && d && u && t_base && ts, "nerf_coarse_sample: null pointer");
+    NERF_REQUIRE(N >= 0 && C > 0, "nerf_coarse_sample: bad size N=%lld C=%d", (long long)N, C);
+    if (N == 0) return 0;
+    coarse_sample_kernel<<<grid_for(N * C, 256), 256, 0, (cudaStream_t)stream>>>(o, d, u, t_base, step, N * C, C, samples, ts);
+    return check_launch("nerf_coarse_sample");
+}
+
+extern "C" int nerf_deltas(const float* ts, int64_t N, int S, float* deltas, void* stream) {
+    NERF_REQUIRE(ts && deltas, "nerf_deltas: null pointer");
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_deltas: bad size");
+    if (N == 0) return 0;
+    deltas_kernel<<<grid_for(N * S, 256), 256, 0, (cudaStream_t)stream>>>(ts, N * S, S, deltas);
+    return check_launch("nerf_deltas");
+}
+
+extern "C" int nerf_weights(const float* sigma, const float* deltas, int64_t N, int S, float* weights, void* stream) {
+    NERF_REQUIRE(sigma && deltas && weights, "nerf_weights: null pointer");
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_weights: bad size");
+    if (N == 0) return 0;
+    composite_kernel<0><<<grid_for(N, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(
+        sigma, nullptr, deltas, N, S, nullptr, weights, nullptr, nullptr, nullptr, nullptr);
+    return check_launch("nerf_weights");
+}
+
+extern "C" int nerf_ray_color(const float* weights, const float* rgb, int64_t N, int S, float* ray_rgb, void* stream) {
+    NERF_REQUIRE(weights && rgb && ray_rgb, "nerf_ray_color: null pointer");
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_ray_color: bad size");
+    if (N == 0) return 0;
+    ray_color_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(weights, rgb, N, S, ray_rgb);
+    return check_launch("nerf_ray_color");
+}
+
+extern "C" int nerf_composite(const float* sigma, const float* rgb, const float* ts, int64_t N, int S,
+                              float* deltas, float* weights, float* ray_rgb, float* depth, float* acc,
+                              float* stats2, void* stream) {
+    NERF_REQUIRE(sigma && rgb && ts, "nerf_composite: null pointer");
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_composite: bad size");
+    if (N == 0) return 0;
+    composite_kernel<1><<<grid_for(N, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(
+        sigma, rgb, ts, N, S, deltas, weights, ray_rgb, depth, acc, stats2);
+    return check_launch("nerf_composite");
+}
+
+extern "C" int nerf_fine_sample(const float* o, const float* d, const float* w, const float* ts, const float* eps,
+                                const float* u, const float* q_base, int64_t N, int C, int F, float near_, float far_,
+                                float* fine_samples, float* fine_ts, int64_t* idx, void* stream) {
+    NERF_REQUIRE(o && d && w && ts && eps && u && q_base && fine_ts, "nerf_fine_sample: null pointer");
+    NERF_REQUIRE(N >= 0 && C > 0 && F > 0 && C <= 2048, "nerf_fine_sample: bad size N=%lld C=%d F=%d", (long long)N, C, F);
+    if (N == 0) return 0;
+    const size_t smem = (size_t)kWarpsPerBlock * (2 * C + 2) * sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fine_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fine_sample_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, smem, (cudaStream_t)stream>>>(
+        o, d, w, ts, eps, u, q_base, N, C, F, near_, far_, fine_samples, fine_ts, idx);
+    return check_launch("nerf_fine_sample");
+}
+
+extern "C" int nerf_merge_sort(const float* o, const float* d, const float* ts_a, int A, const float* ts_b, int B,
+                               int64_t N, float* ts_sorted, float* samples_sorted, void* stream) {
+    NERF_REQUIRE(ts_a && ts_b && ts_sorted, "nerf_merge_sort: null pointer");
+    NERF_REQUIRE(!samples_sorted || (o && d), "nerf_merge_sort: samples_sorted needs o and d");
+    NERF_REQUIRE(N >= 0 && A >= 0 && B >= 0 && A + B > 0 && A + B <= 1024, "nerf_merge_sort: bad size A=%d B=%d", A, B);
+    if (N == 0) return 0;
+    const size_t smem = (size_t)kWarpsPerBlock * 2 * (A + B) * sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    merge_sort_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, smem, (cudaStream_t)stream>>>(
+        o, d, ts_a, A, ts_b, B, N, ts_sorted, samples_sorted);
+    return check_launch("nerf_merge_sort");
+}

@@ -1,0 +1,100 @@
+// umma_probe.cu - single-CTA known-answer probe for the tcgen05 building blocks in umma.cuh.
+// D[128,N] = A[128,K] * B[N,K]^T with A either staged in 128B-swizzled shared memory (mode 0, SS) or
+// written to TMEM with tcgen05.st (mode 1, TS), B always in swizzled shared memory.  Used by
+// tests/test_umma_probe.py to validate descriptor encodings on the device independently of the fused kernel.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace nerf {
+
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(int mode, const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, int K, int N,
+                  int d_col, float* __restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int kblocks = K / 64;
+    uint8_t* sA = smem;                                  // kblocks x [128 x 128 B]
+    uint8_t* sB = smem + (size_t)kblocks * 16384;        // kblocks x [N x 128 B]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_holder;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
+    if (warp == 0) umma::tmem_alloc(&tmem_holder, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = tmem_holder;
+
+    // stage B (and A for SS) into swizzled shared memory
+    for (int e = tid; e < N * K; e += blockDim.x) {
+        const int n = e / K, k = e % K;
+        *(__nv_bfloat16*)(sB + (size_t)(k / 64) * N * 128 + umma::sw128_offset(n, k % 64)) = B[e];
+    }
+    if (mode == 0) {
+        for (int e = tid; e < 128 * K; e += blockDim.x) {
+            const int m = e / K, k = e % K;
+            *(__nv_bfloat16*)(sA + (size_t)(k / 64) * 16384 + umma::sw128_offset(m, k % 64)) = A[e];
+        }
+    } else {
+        // thread = row; pack (k, k+1) into one 32-bit TMEM cell, columns 256 + k/2
+        for (int c0 = 0; c0 < K / 2; c0 += 16) {
+            uint32_t v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const __nv_bfloat16 lo = A[tid * K + 2 * (c0 + j)], hi = A[tid * K + 2 * (c0 + j) + 1];
+                v[j] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+            }
+            umma::tmem_st16(umma::tmem_addr(tmem, warp * 32, 256 + c0), v);
+        }
+        umma::tmem_wait_st();
+    }
+    umma::fence_proxy_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+
+    if (tid == 0) {
+        const uint32_t idesc = umma::make_idesc_bf16(128, N);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < kblocks; ++kb) {
+            const uint64_t bdesc = umma::make_desc_k_sw128(umma::smem_u32(sB + (size_t)kb * N * 128));
+            const uint64_t adesc = umma::make_desc_k_sw128(umma::smem_u32(sA + (size_t)kb * 16384));
+            for (int k = 0; k < 4; ++k) {
+                if (mode == 0) umma::mma_ss(tmem + d_col, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                else           umma::mma_ts(tmem + d_col, tmem + 256 + kb * 32 + k * 8, bdesc + 2 * k, idesc, acc);
+                acc = 1;
+            }
+        }
+        umma::mma_commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 4) {
+        uint32_t v[4];
+        umma::tmem_ld4(umma::tmem_addr(tmem, warp * 32, d_col + c0), v);
+        umma::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace nerf
+
+// Test-only entry point (declared in tests, not in include/nerf_b200.h).
+extern "C" int nerf_debug_umma(int mode, const void* A_bf16, const void* B_bf16, int K, int N, int d_col, float* D,
+                               void* stream) {
+    using namespace nerf;
+    NERF_REQUIRE(A_bf16 && B_bf16 && D, "nerf_debug_umma: null pointer");
+    NERF_REQUIRE((mode == 0 || mode == 1) && K % 64 == 0 && K >= 64 && K <= 256 && N % 16 == 0 && N >= 16 && N <= 256 &&
+                     d_col >= 0 && d_col + N <= 256,
+                 "nerf_debug_umma: bad shape");
+    const size_t smem = (size_t)(K / 64) * (16384 + (size_t)N * 128) + 1024;
+    cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, (const __nv_bfloat16*)A_bf16, (const __nv_bfloat16*)B_bf16, K, N,
+                                                            d_col, D);
+    return check_launch("nerf_debug_umma");
+}

@@ -1,0 +1,203 @@
+"""B200 drop-in for the reference's `nerf_model.py`: same classes, constructor arguments, state_dict keys,
+forward signatures and return shapes; the arithmetic runs in libnerf_b200.so.
+
+Reference counterparts (file:line): positional_encoding 19-33, normalize_coordinates 35-54,
+NeRFNetwork 56-205, NeRFModel 308-389.
+
+`precision`:
+  "bf16" (default) - the fused tcgen05 kernel: bf16 operands, fp32 accumulation in TMEM (position_dim 10,
+                     direction_dim 4 only);
+  "fp32"           - the exact-fp32 CUDA-core kernel (any encoding sizes); tight-parity mode.
+"""
+import ctypes
+import math
+import random
+from timeit import default_timer as timer
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import _native as nat
+import nerf_helpers
+from lightning_shim import LightningModule
+
+ACT_FN = nn.ReLU()
+
+
+def positional_encoding(x, dim=10):
+    """[..., C] -> [..., 2*dim*C]: per frequency i, cos(2^i pi x) for all channels then sin(2^i pi x)."""
+    t = nat.dev(x, "x")
+    c = t.shape[-1]
+    flat = t.reshape(-1, c)
+    out = torch.empty((flat.shape[0], 2 * dim * c), device=t.device, dtype=torch.float32)
+    nat.check(nat.lib().nerf_positional_encoding(nat.ptr(flat), flat.shape[0], c, dim, nat.ptr(out), nat.stream()),
+              "nerf_positional_encoding")
+    return out.reshape(*t.shape[:-1], 2 * dim * c)
+
+
+def normalize_coordinates(x, bound=math.pi):
+    """x / bound (coordinates are expected within [-bound, bound])."""
+    return x / bound
+
+
+class NeRFModel(nn.Module):
+    """One NeRF MLP: PE(x) -> 4x256 -> [+PE(x)] -> 3x256 -> sigma (ReLU) and rgb (128 -> 3, sigmoid).
+    The nn.Linear modules only hold the parameters (identical state_dict keys to the reference)."""
+
+    def __init__(self, position_dim=10, direction_dim=4, precision="bf16"):
+        super().__init__()
+        self.position_dim, self.direction_dim, self.precision = position_dim, direction_dim, precision
+        pe, de = position_dim * 2 * 3, direction_dim * 2 * 3
+        self.mlp = nn.Sequential(nn.Linear(pe, 256), ACT_FN, nn.Linear(256, 256), ACT_FN,
+                                 nn.Linear(256, 256), ACT_FN, nn.Linear(256, 256), ACT_FN)
+        self.feature_fn = nn.Sequential(nn.Linear(256 + pe, 256), ACT_FN, nn.Linear(256, 256), ACT_FN,
+                                        nn.Linear(256, 256))
+        self.density_fn = nn.Sequential(nn.Linear(256, 1), nn.ReLU())
+        self.rgb_fn = nn.Sequential(nn.Linear(256 + de, 128), ACT_FN, nn.Linear(128, 3), nn.Sigmoid())
+        self._packed = None
+        self._packed_key = None
+
+    # ---- parameter plumbing
+    def ordered_params(self):
+        """The 20 tensors in state_dict order."""
+        mods = [self.mlp[0], self.mlp[2], self.mlp[4], self.mlp[6], self.feature_fn[0], self.feature_fn[2],
+                self.feature_fn[4], self.density_fn[0], self.rgb_fn[0], self.rgb_fn[2]]
+        out = []
+        for m in mods:
+            out += [m.weight, m.bias]
+        return out
+
+    def _param_ptrs(self):
+        ps = [nat.dev(p.detach(), "parameter") for p in self.ordered_params()]
+        arr = (ctypes.c_void_p * 20)(*[p.data_ptr() for p in ps])
+        return arr, ps
+
+    def uses_tensor_cores(self):
+        return self.precision == "bf16" and self.position_dim == 10 and self.direction_dim == 4
+
+    def packed_weights(self):
+        """bf16 swizzled weight image for the tcgen05 kernel; re-packed whenever a parameter changed."""
+        params = self.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or self._packed_key != key or self._packed.device != params[0].device:
+            arr, keep = self._param_ptrs()
+            if self._packed is None or self._packed.device != params[0].device:
+                self._packed = torch.empty(nat.lib().nerf_packed_bytes(), dtype=torch.uint8, device=params[0].device)
+            nat.check(nat.lib().nerf_pack_weights(arr, nat.ptr(self._packed), nat.stream()), "nerf_pack_weights")
+            self._packed_key = key
+        return self._packed
+
+    # ---- forward
+    def forward(self, samples, direc):
+        """samples [N,S,3], direc [N,3] -> density [N,S,1], rgb [N,S,3]."""
+        x, dr = nat.dev(samples, "samples"), nat.dev(direc, "direc")
+        N, S, _ = x.shape
+        sigma = torch.empty((N, S, 1), device=x.device, dtype=torch.float32)
+        rgb = torch.empty((N, S, 3), device=x.device, dtype=torch.float32)
+        if self.uses_tensor_cores():
+            nat.check(nat.lib().nerf_mlp_forward_tc_points(nat.ptr(self.packed_weights()), nat.ptr(x), nat.ptr(dr), N, S,
+                                                           nat.ptr(sigma), nat.ptr(rgb), nat.stream()), "nerf_mlp_forward_tc")
+        else:
+            arr, keep = self._param_ptrs()
+            nat.check(nat.lib().nerf_mlp_forward_fp32(arr, self.position_dim, self.direction_dim, nat.ptr(x), nat.ptr(dr),
+                                                      N, S, nat.ptr(sigma), nat.ptr(rgb), nat.stream()), "nerf_mlp_forward_fp32")
+        return sigma, rgb
+
+    def forward_rays(self, o_rays, d_rays, ts):
+        """Same network evaluated at o + t*d for ts [N,S,1] without materialising the points."""
+        N, S = ts.shape[0], ts.shape[1]
+        sigma = torch.empty((N, S, 1), device=ts.device, dtype=torch.float32)
+        rgb = torch.empty((N, S, 3), device=ts.device, dtype=torch.float32)
+        if self.uses_tensor_cores():
+            nat.check(nat.lib().nerf_mlp_forward_tc(nat.ptr(self.packed_weights()), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(ts),
+                                                    N, S, nat.ptr(sigma), nat.ptr(rgb), nat.stream()), "nerf_mlp_forward_tc")
+            return sigma, rgb
+        pts = d_rays[:, None, :] * ts + o_rays[:, None, :]
+        return self.forward(pts.contiguous(), d_rays)
+
+
+class NeRFNetwork(LightningModule):
+    """Coarse + fine NeRF (the reference's Lightning module): forward(o_rays, d_rays) ->
+    {'fine_rgb_rays': [N,3], 'coarse_rgb_rays': [N,3]}."""
+
+    def __init__(self, position_dim=10, direction_dim=4, coarse_samples=64,
+                 fine_samples=128, near=2.0, far=6.0, precision="bf16"):
+        super().__init__()
+        self.position_dim, self.direction_dim = position_dim, direction_dim
+        self.coarse_samples, self.fine_samples = coarse_samples, fine_samples
+        self.near, self.far = near, far
+        self.coarse_network = NeRFModel(position_dim, direction_dim, precision)
+        self.fine_network = NeRFModel(position_dim, direction_dim, precision)
+        self.im_idx, self.max_idx = 0, 1
+        self.timer = timer()
+        self.last = {}                      # depth / acc / weights of the most recent forward
+
+    def forward(self, o_rays, d_rays, rand=None):
+        """rand = (u_c [N,C], eps [N,1], u_f [N,F,1]) replaces the three torch.rand draws when given."""
+        o, d = nat.dev(o_rays, "o_rays"), nat.dev(d_rays, "d_rays")
+        N, C, Fn = o.shape[0], self.coarse_samples, self.fine_samples
+        dv = o.device
+        if rand is None:        # the reference's draw order and shapes (nerf_helpers.py:52,139,154)
+            rand = (torch.rand((N, C), device=dv), torch.rand((N, 1), device=dv), torch.rand((N, Fn, 1), device=dv))
+        u_c, eps, u_f = rand
+        c_ts = self._coarse_ts(o, d, u_c)
+        c_sigma, c_rgb = self.coarse_network.forward_rays(o, d, c_ts)
+        c = nerf_helpers.composite(c_sigma, c_rgb, c_ts)
+        self.log('coarse_density_norms', torch.sqrt(c["stats"][0]), batch_size=1)
+        self.log('coarse_density_non_zeros', c["stats"][1], batch_size=1)
+        # near / far are NOT forwarded upstream (nerf_model.py:114-115): the sampler's 2.0 / 6.0 defaults apply
+        _, f_ts = nerf_helpers.inverse_transform_sampling(o, d, c["weights"], c_ts, Fn, rand=(eps, u_f))
+        _, ts = nerf_helpers.merge_samples(o, d, f_ts, c_ts, want_points=False)
+        f_sigma, f_rgb = self.fine_network.forward_rays(o, d, ts)
+        f = nerf_helpers.composite(f_sigma, f_rgb, ts, want_weights=False)
+        self.log('fine_density_norms', torch.sqrt(f["stats"][0]), batch_size=1)
+        self.log('fine_density_non_zeros', f["stats"][1], batch_size=1)
+        self.last = {"depth": f["depth"], "acc": f["acc"], "ts": ts, "coarse_ts": c_ts, "coarse_weights": c["weights"],
+                     "coarse_sigma": c_sigma, "fine_sigma": f_sigma, "coarse_rgb": c_rgb, "fine_rgb": f_rgb}
+        return {'fine_rgb_rays': f["rgb"], 'coarse_rgb_rays': c["rgb"]}
+
+    def _coarse_ts(self, o, d, u_c):
+        N, C = u_c.shape
+        t_base, step = nerf_helpers._strata(self.near, self.far, C, o.device)
+        ts = torch.empty((N, C, 1), device=o.device, dtype=torch.float32)
+        nat.check(nat.lib().nerf_coarse_sample(nat.ptr(o), nat.ptr(d), nat.ptr(nat.dev(u_c, "u_c")), nat.ptr(t_base), step,
+                                               N, C, None, nat.ptr(ts), nat.stream()), "nerf_coarse_sample")
+        return ts
+
+    def configure_optimizers(self):
+        start_lr, end_lr, num_epochs = 5e-4, 5e-5, 1200
+        gamma = (end_lr / start_lr) ** (1 / num_epochs)
+        optimizer = torch.optim.Adam(self.parameters(), lr=start_lr)
+        lr_decay = torch.optim.lr_scheduler.ExponentialLR(optimizer=optimizer, gamma=gamma)
+        return {'optimizer': optimizer, 'lr_scheduler': lr_decay}
+
+    def _step(self, batch, prefix):
+        nerf_helpers.fix_batchify(batch)
+        o_rays, d_rays, rgb = batch['origin'], batch['direc'], batch['rgb']
+        pred = self.forward(o_rays, d_rays)
+        N = pred['fine_rgb_rays'].shape[0]
+        coarse_loss = F.mse_loss(pred['coarse_rgb_rays'], rgb)
+        fine_loss = F.mse_loss(pred['fine_rgb_rays'], rgb)
+        loss = coarse_loss + fine_loss
+        self.log(f'{prefix}_loss', loss, batch_size=N)
+        self.log(f'{prefix}_fine_loss', fine_loss, batch_size=N)
+        self.log(f'{prefix}_coarse_loss', coarse_loss, batch_size=N)
+        return loss, N
+
+    def training_step(self, train_batch, batch_idx):
+        loss, N = self._step(train_batch, 'train')
+        self.log('train iteration speed', timer() - self.timer, batch_size=N)
+        self.timer = timer()
+        return loss
+
+    def validation_step(self, val_batch, batch_idx):
+        self.max_idx = max(self.max_idx, batch_idx)
+        if batch_idx == 0:
+            self.im_idx = random.randint(0, self.max_idx)
+        loss, N = self._step(val_batch, 'val')
+        if batch_idx == self.im_idx and 'all_origin' in val_batch:
+            im = nerf_helpers.view_reconstruction(self, val_batch['all_origin'], val_batch['all_direc'], N=N)
+            if self.logger is not None and hasattr(self.logger, 'log_image'):
+                self.logger.log_image(key='recon', images=[im], caption=[f'val/{self.im_idx}.png'])
+        return loss

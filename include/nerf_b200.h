@@ -1,0 +1,114 @@
+/* nerf_b200.h - C ABI of libnerf_b200.so: the sm_100a NeRF render-and-train hot path.
+ *
+ * The reference (NakuraMino/CSE-573-Minimal-NeRF) is pure Python/PyTorch and has no FFI layer; its
+ * boundary is the Python call surface of nerf_helpers.py / nerf_model.py / dataloader.py.  Each entry
+ * point below replaces the *inside* of one of those functions (file:line cited per function) and is
+ * what the Python host modules in cse-573-minimal-nerf_b200/ bind through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (or the stated integer type) owned by the
+ *     caller, except where the name ends in `_host`;
+ *   - nothing is allocated or freed here except lazily created per-device function attributes;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy stream);
+ *   - return value 0 = launched, negative = rejected (NERF_E_*); text via nerf_last_error() (thread-local);
+ *   - N = rays, C = coarse samples per ray, F = fine samples per ray, S = samples per ray of one network.
+ *   - there is no CPU implementation behind any of these: without a CUDA device they fail.
+ */
+#ifndef NERF_B200_H_
+#define NERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERF_ABI_VERSION 1
+
+#define NERF_E_ARG    (-1)   /* null pointer / bad size / unsupported shape */
+#define NERF_E_CUDA   (-2)   /* CUDA runtime error at launch */
+#define NERF_E_DEVICE (-3)   /* device is not sm_100 */
+
+int nerf_abi_version(void);
+const char* nerf_last_error(void);
+
+/* ---- H0: rays.  dataloader.py:36-43 (get_rays), :150-152 (pixel gather).
+ * c2w_host: 12 or 16 floats on the HOST, row-major rows of the 4x4 camera-to-world matrix.
+ * xs, ys: [n] int64 device arrays of pixel column / row, or both NULL for the full H*W grid in
+ * row-major order (then n must be H*W).  o, d: [n,3].  d is NOT normalised (as upstream). */
+int nerf_raygen(const float* c2w_host, int H, int W, float focal, const int64_t* xs, const int64_t* ys,
+                int64_t n, float* o, float* d, void* stream);
+
+/* ---- H1: stratified depths and points.  nerf_helpers.py:28-56.
+ * u: [N,C] uniforms in [0,1).  t_base: [C] strata origins (the reference's torch.arange(near, far, step),
+ * evaluated by the host with torch so that its rounding is inherited).  ts[n,i] = t_base[i] + u*step,
+ * samples = d*t + o (separate multiply and add).  samples may be NULL. */
+int nerf_coarse_sample(const float* o, const float* d, const float* u, const float* t_base, float step,
+                       int64_t N, int C, float* samples, float* ts, void* stream);
+
+/* ---- H2: deltas.  nerf_helpers.py:58-73.  ts, deltas: [N,S]; deltas[:, S-1] = 1e10. */
+int nerf_deltas(const float* ts, int64_t N, int S, float* deltas, void* stream);
+
+/* ---- H3: unnormalised weights.  nerf_helpers.py:75-91.  sigma, deltas, weights: [N,S].
+ * The exclusive running sum of -sigma*delta is taken sequentially in fp32 (CPU torch order). */
+int nerf_weights(const float* sigma, const float* deltas, int64_t N, int S, float* weights, void* stream);
+
+/* ---- H4: ray colour.  nerf_helpers.py:93-104.  weights [N,S], rgb [N,S,3] -> ray_rgb [N,3]. */
+int nerf_ray_color(const float* weights, const float* rgb, int64_t N, int S, float* ray_rgb, void* stream);
+
+/* ---- H2+H3+H4 in one pass (what NeRFNetwork.forward does at nerf_model.py:109-111 and :128-130).
+ * sigma [N,S], rgb [N,S,3], ts [N,S].  Every output may be NULL: deltas [N,S], weights [N,S],
+ * ray_rgb [N,3], depth [N] (sum w*t), acc [N] (sum w).  stats2 (nullable, [2], ACCUMULATED with atomics):
+ * sum sigma^2 and count(sigma != 0) - the two density statistics logged at nerf_model.py:105-106. */
+int nerf_composite(const float* sigma, const float* rgb, const float* ts, int64_t N, int S,
+                   float* deltas, float* weights, float* ray_rgb, float* depth, float* acc,
+                   float* stats2, void* stream);
+
+/* ---- H5: inverse-CDF fine sampling.  nerf_helpers.py:106-156.
+ * w, ts: [N,C] coarse weights and depths.  eps: [N] and u: [N,F] raw uniforms.  q_base: [F] query grid
+ * (the reference's torch.arange(0, 1, 1/F), evaluated by the host).  cdf = sequential fp32 cumsum / last;
+ * an all-zero ray has a NaN cdf and every query falls in the last bin, as upstream.
+ * fine_samples [N,F,3] (nullable), fine_ts [N,F], idx [N,F] int64 lower-bound indices (nullable). */
+int nerf_fine_sample(const float* o, const float* d, const float* w, const float* ts, const float* eps,
+                     const float* u, const float* q_base, int64_t N, int C, int F, float near_, float far_,
+                     float* fine_samples, float* fine_ts, int64_t* idx, void* stream);
+
+/* ---- H6: merge + sort.  nerf_model.py:116-120.  ts_a [N,A] (fine) and ts_b [N,B] (coarse) are
+ * concatenated, sorted ascending per ray; samples_sorted [N,A+B,3] = o + t*d (nullable). A+B <= 1024. */
+int nerf_merge_sort(const float* o, const float* d, const float* ts_a, int A, const float* ts_b, int B,
+                    int64_t N, float* ts_sorted, float* samples_sorted, void* stream);
+
+/* ---- H7: positional encoding.  nerf_model.py:19-33.  x [n,c] -> out [n, 2*L*c];
+ * per frequency i: cos(2^i pi x) for the c channels, then sin(2^i pi x). */
+int nerf_positional_encoding(const float* x, int64_t n, int c, int L, float* out, void* stream);
+
+/* ---- H8: one NeRFModel forward.  nerf_model.py:362-389.
+ * params20_host: HOST array of 20 device pointers in state_dict order
+ *   (mlp.0.weight, mlp.0.bias, mlp.2.*, mlp.4.*, mlp.6.*, feature_fn.0.*, feature_fn.2.*, feature_fn.4.*,
+ *    density_fn.0.*, rgb_fn.0.*, rgb_fn.2.*), fp32, nn.Linear layout [out,in].
+ * samples [N,S,3], direc [N,3] -> sigma [N,S], rgb [N,S,3].
+ * This is the exact-fp32 CUDA-core form (any position_dim/direction_dim, any N,S); the tensor-core form is
+ * nerf_mlp_forward_tc below. */
+int nerf_mlp_forward_fp32(const float* const* params20_host, int position_dim, int direction_dim,
+                          const float* samples, const float* direc, int64_t N, int S,
+                          float* sigma, float* rgb, void* stream);
+
+/* ---- K5: pack one network's weights for the tcgen05 kernels (bf16, K-major, 128B-swizzled UMMA tiles,
+ * biases fp32).  position_dim must be 10 and direction_dim 4 (the only shape the tensor-core kernel is
+ * specialised for).  `packed` holds nerf_packed_bytes() bytes. */
+size_t nerf_packed_bytes(void);
+int nerf_pack_weights(const float* const* params20_host, void* packed, void* stream);
+
+/* ---- K8: NeRFModel forward on the 5th-gen tensor cores (bf16 operands, fp32 accumulation in TMEM).
+ * Samples are given as rays + depths: sample (n,s) sits at o[n] + ts[n,s]*d[n].  sigma [N,S], rgb [N,S,3]. */
+int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, const float* ts,
+                        int64_t N, int S, float* sigma, float* rgb, void* stream);
+/* Same kernel with explicit sample points [N,S,3] (the NeRFModel.forward(samples, direc) call surface). */
+int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
+                               int64_t N, int S, float* sigma, float* rgb, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H_ */

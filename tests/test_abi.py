@@ -1,0 +1,72 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/nerf_b200.h declares; the host modules keep the reference's call surface; no CPU fallback exists."""
+import ctypes
+import inspect
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import _native
+    if not _native.LIB_PATH.exists():
+        _native.build()
+    return _native.lib()
+
+
+def test_header_symbols_exported(lib):
+    header = (ROOT / "include" / "nerf_b200.h").read_text()
+    declared = set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 16
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/nerf_b200.h but not exported"
+    import _native
+    assert declared == set(_native.exported_symbols())
+    assert lib.nerf_abi_version() == 1
+    assert lib.nerf_packed_bytes() == 57 * 16384 + 6 * 2048 + 1928 * 4
+
+
+def test_argument_validation_without_gpu(lib):
+    # null pointers are rejected before any CUDA call, with a message
+    assert lib.nerf_deltas(None, 4, 4, None, None) == -1
+    assert b"null pointer" in lib.nerf_last_error()
+    assert lib.nerf_merge_sort(None, None, None, 1, None, 1, 1, None, None, None) == -1
+
+
+def test_no_cpu_fallback():
+    import nerf_helpers
+    import nerf_model
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        nerf_helpers.generate_deltas(torch.zeros(1, 4, 1))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        nerf_model.NeRFModel()(torch.zeros(4, 4, 3), torch.zeros(4, 3))
+    src = "".join(inspect.getsource(m) for m in (nerf_helpers, nerf_model))
+    assert "oracle" not in src
+
+
+def test_call_surface_matches_reference():
+    """Names, positional parameters and defaults of the reference's public functions."""
+    import dataloader
+    import nerf_helpers as h
+    import nerf_model as m
+
+    def params(fn):
+        return [(k, v.default) for k, v in inspect.signature(fn).parameters.items()]
+    assert params(h.generate_coarse_samples)[:5] == [("o_rays", inspect._empty), ("d_rays", inspect._empty),
+                                                      ("num_samples", inspect._empty), ("near", 2.0), ("far", 6.0)]
+    assert [k for k, _ in params(h.inverse_transform_sampling)][:7] == ["o_rays", "d_rays", "weights", "ts", "num_samples", "near", "far"]
+    assert [k for k, _ in params(h.view_reconstruction)] == ["model", "all_o_rays", "all_d_rays", "N"]
+    assert params(h.generate_360_view_synthesis)[3:] == [("height", 800), ("width", 800), ("radius", 4.0),
+                                                         ("cam_angle_x", 0.6911112070083618), ("N", 4096), ("num_poses", 40)]
+    assert [k for k, _ in params(dataloader.get_rays)][:4] == ["H", "W", "focal", "c2w"]
+    assert params(m.NeRFNetwork.__init__)[1:7] == [("position_dim", 10), ("direction_dim", 4), ("coarse_samples", 64),
+                                                   ("fine_samples", 128), ("near", 2.0), ("far", 6.0)]
+    import synthetic
+    net = m.NeRFNetwork()
+    assert list(net.state_dict().keys()) == synthetic.state_dict_keys()
+    assert sum(p.numel() for p in net.parameters()) == 924680

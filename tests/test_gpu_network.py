@@ -1,0 +1,108 @@
+"""GPU parity of NeRFNetwork.forward (coarse + fine, nerf_model.py:89-132) and of the 100x100 render
+(BASELINE.json configs[0]) against the golden vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+import synthetic
+from oracle import nerf_oracle as O
+from util import T, bits_equal, rand_triple
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def make_net(seed, kind, precision):
+    import nerf_model
+    net = nerf_model.NeRFNetwork(precision=precision)
+    net.load_state_dict(synthetic.make_state_dict(seed, kind))
+    return net.to(DEV)
+
+
+@pytest.mark.parametrize("kind,seed", [("init", 3), ("dense", 4)])
+def test_forward_fp32_matches_reference(golden, kind, seed):
+    """fp32 mode: sorted depths bit-exact where the coarse weights agree, colours to 2e-5."""
+    g = golden["network"]
+    net = make_net(seed, kind, "fp32")
+    o, d = T(g["o"], DEV), T(g["d"], DEV)
+    out = net.forward(o, d, rand=rand_triple(500 + seed * 10, 64, device=DEV))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(net.last["coarse_sigma"].cpu(), T(g[f"c_sigma_{kind}"]), atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(out["coarse_rgb_rays"].cpu(), T(g[f"coarse_rgb_rays_{kind}"]), atol=2e-5, rtol=1e-4)
+    if kind == "dense":
+        # weights differ from the CPU's by ~1e-7, so a handful of bin decisions may flip; nearly all depths are identical
+        same = (net.last["ts"].cpu() == T(g[f"sorted_ts_{kind}"])).float().mean().item()
+        assert same > 0.97, same
+        torch.testing.assert_close(out["fine_rgb_rays"].cpu(), T(g[f"fine_rgb_rays_{kind}"]), atol=5e-4, rtol=0)
+    stats = torch.stack([net.logged[k].cpu() for k in ("coarse_density_norms", "coarse_density_non_zeros")])
+    torch.testing.assert_close(stats, T(g[f"stat_{kind}"]).float()[:2], rtol=1e-3, atol=1.0)
+
+
+def test_fine_path_bit_exact_given_reference_weights(golden):
+    """Feed the oracle's own coarse weights: indices, fine depths and the sorted depths must be bit-identical."""
+    import nerf_helpers as h
+    g = golden["network"]
+    sd = synthetic.make_state_dict(4, "dense")
+    o, d = T(g["o"]), T(g["d"])
+    u_c, eps, u_f = rand_triple(540, 64)
+    ref = O.network_forward(sd, o, d, u_c, eps, u_f, full=True)
+    assert bits_equal(ref["ts"], g["sorted_ts_dense"])
+    _, fts, idx = h.inverse_transform_sampling(o.to(DEV), d.to(DEV), ref["coarse_weights"].to(DEV), ref["coarse_ts"].to(DEV), 128,
+                                               rand=(eps.to(DEV), u_f.to(DEV)), return_idx=True)
+    assert bits_equal(idx, g["idx_dense"]) and bits_equal(fts, ref["fine_ts"])
+    pts, ts = h.merge_samples(o.to(DEV), d.to(DEV), fts, ref["coarse_ts"].to(DEV))
+    assert bits_equal(ts, g["sorted_ts_dense"]) and bits_equal(pts, g["f_in_pts_dense"])
+
+
+def test_forward_bf16_dense(golden):
+    """Tensor-core path, dense weights: rgb within bf16 tolerance of the reference; PSNR-vs-oracle reported."""
+    g = golden["network"]
+    net = make_net(4, "dense", "bf16")
+    o, d = T(g["o"], DEV), T(g["d"], DEV)
+    out = net.forward(o, d, rand=rand_triple(540, 64, device=DEV))
+    torch.cuda.synchronize()
+    for key in ("coarse_rgb_rays", "fine_rgb_rays"):
+        diff = (out[key].cpu() - T(g[f"{key}_dense"])).abs()
+        psnr = 10 * np.log10(1.0 / max(float((diff ** 2).mean()), 1e-20))
+        print(f"{key}: max {diff.max():.3e} mean {diff.mean():.3e} PSNR-vs-reference {psnr:.1f} dB")
+        assert diff.mean() < 1e-3 and diff.max() < 8e-3 and psnr > 50.0
+    assert out["fine_rgb_rays"].shape == (64, 3)
+    assert net.last["depth"].shape == (64,) and (net.last["acc"] <= 1 + 1e-5).all()
+
+
+def test_forward_bf16_random_init_statistical(golden):
+    """Random-init weights sit on the sigma ReLU knife-edge at the 1e10-wide last interval: judged
+    by the mean and the fraction of rays beyond tolerance, never by max-abs."""
+    g = golden["network"]
+    net = make_net(3, "init", "bf16")
+    out = net.forward(T(g["o"], DEV), T(g["d"], DEV), rand=rand_triple(530, 64, device=DEV))
+    diff = (out["coarse_rgb_rays"].cpu() - T(g["coarse_rgb_rays_init"])).abs().max(dim=1).values
+    print(f"coarse: mean {diff.mean():.3e} frac>0.02 {(diff > 0.02).float().mean():.3f}")
+    assert diff.mean() < 0.08 and (diff > 0.02).float().mean() < 0.5
+
+
+def test_render_100x100(golden):
+    """BASELINE configs[0] on the device: view_reconstruction, chunk 4096, dense checkpoint, both precisions."""
+    import dataloader
+    import nerf_helpers as h
+    g = golden["render100"]
+    o, d = dataloader.get_rays(100, 100, float(g["focal"]), T(g["c2w"]))
+    real_rand = torch.rand
+    for precision, min_psnr in (("fp32", 45.0), ("bf16", 40.0)):
+        net = make_net(5, "dense", precision)
+        state = {"k": 0}
+
+        def fake_rand(shape, device=None, **kw):
+            out = T(synthetic.uniforms(600 + state["k"], tuple(shape)), DEV)
+            state["k"] += 1
+            return out
+        torch.rand = fake_rand
+        try:
+            im = h.view_reconstruction(net, o, d, N=4096)
+        finally:
+            torch.rand = real_rand
+        assert im.shape == (100, 100, 3) and im.dtype == np.uint8
+        psnr = O.psnr_uint8(im, g["image"])
+        diff = np.abs(im.astype(np.int32) - g["image"].astype(np.int32))
+        print(f"{precision}: PSNR vs reference frame {psnr:.2f} dB, max |d| {diff.max()}, frac != {(diff > 0).mean():.4f}")
+        assert psnr > min_psnr

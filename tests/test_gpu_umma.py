@@ -1,0 +1,27 @@
+"""GPU known-answer probe of the tcgen05 building blocks (umma.cuh): one-CTA GEMMs with A in swizzled shared
+memory (SS) or in TMEM (TS) against torch.matmul on the same bf16 inputs."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("K,N,d_col", [(64, 128, 0), (256, 128, 128), (256, 16, 128), (128, 256, 0), (64, 144, 0)])
+def test_umma_probe(mode, K, N, d_col):
+    import _native as nat
+    fn = nat.lib().nerf_debug_umma
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                   ctypes.c_void_p]
+    g = torch.Generator(device="cuda").manual_seed(1234 + K + N)
+    A = (torch.randn(128, K, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
+    B = (torch.randn(N, K, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
+    D = torch.full((128, N), float("nan"), device="cuda")
+    nat.check(fn(mode, nat.ptr(A), nat.ptr(B), K, N, d_col, nat.ptr(D), nat.stream()), "nerf_debug_umma")
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().T
+    err = (D - ref).abs().max().item()
+    assert err < 1e-2 * max(1.0, ref.abs().max().item() / 16), f"mode {mode} K {K} N {N}: max err {err}"
