@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py - rays/s of the NeRF render hot path on B200 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--hw 800]
+
+One "step" = one H x W novel-view frame (default 800x800 = 640 000 rays) pushed through NeRFNetwork.forward in
+chunks of 4096 rays: stratified sampling -> coarse MLP -> compositing -> inverse-CDF sampling -> merge sort ->
+fine MLP -> compositing (64 coarse + 128 fine samples per ray), weights from a synthetic checkpoint in the
+reference's format (the shipped lego checkpoint is not available offline).
+
+  value     device-resident rays, CUDA-event time per step (L2 flushed between steps), max over ranks
+  e2e       same frame through the public view_reconstruction-style path with HOST buffers: pinned rays H2D,
+            render, uint8 conversion, image D2H (and the per-frame gather at N > 1) inside the timed region
+  roofline  fused tcgen05 MLP kernel: algorithmic FLOPs / CUDA-event time of its launches inside the timed region
+  cpu_baseline  the CPU oracle (port of the reference) on this box's host cores, bounded sample (N=1 only)
+
+`--impl reference` times the reference's CPU path (oracle port; the Python reference cannot travel to the GPU
+box) with all host threads on the same metric.  Multi-GPU (torchrun): weak scaling, one frame of the orbit per
+rank per step, no data-path collective; the only exchange is the final image gather in the e2e arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "cse-573-minimal-nerf_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+FLOP_PER_SAMPLE = 2 * 460416          # true (unpadded) MACs of one NeRFModel forward x 2
+CAM_ANGLE_X = 0.6911112070083618
+COARSE, FINE, CHUNK = 64, 128, 4096
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        p = json.loads(f.read_text())
+        return {"tflops_burst": p["bf16_tflops"], "tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def frame_setup(H, W, pose_index):
+    import synthetic
+    from oracle import nerf_oracle as O      # pose + focal helpers only (host-side scalars)
+    focal = O.focal_from_fov(W, CAM_ANGLE_X)
+    angle = float(np.linspace(-180, 180, 41)[:-1][pose_index % 40])
+    return synthetic.orbit_pose(angle, -30.0, 4.0), focal
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU oracle (port of the reference's forward) with all host threads."""
+    if rank != 0:
+        return
+    import synthetic
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    sd = synthetic.make_state_dict(5, "dense")
+    c2w, focal = frame_setup(args.hw, args.hw, 0)
+    o, d = O.get_rays(args.hw, args.hw, focal, c2w)
+    o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+    n = min(CHUNK, o.shape[0])                         # bounded sample: one 4096-ray chunk per step
+
+    def step(k):
+        lo = (k * n) % max(o.shape[0] - n + 1, 1)
+        rand = (torch.rand(n, COARSE), torch.rand(n, 1), torch.rand(n, FINE, 1))
+        with torch.no_grad():
+            O.network_forward(sd, o[lo:lo + n], d[lo:lo + n], *rand)
+    for k in range(args.warmup):
+        step(k)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = n / dt
+    sample = f"one {n}-ray chunk of the {args.hw}x{args.hw} frame per step (no_grad), CPU oracle port of the reference"
+    print(json.dumps({
+        "impl": "reference", "metric": "rays/sec render (device-timed)", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args):
+    return {"workload": f"render {args.hw}x{args.hw} lego-360 orbit frame, 64 coarse + 128 fine samples/ray, ray chunk 4096, "
+                        "synthetic checkpoint in the reference's PL format (dense weight set, seed 5)",
+            "H": args.hw, "W": args.hw, "chunk": CHUNK, "coarse": COARSE, "fine": FINE,
+            "l2": "256 MB L2 flush between timed steps; per-step uniforms (0.49 GB) exceed the 126 MB L2"}
+
+
+def cpu_baseline(args):
+    import synthetic
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    sd = synthetic.make_state_dict(5, "dense")
+    c2w, focal = frame_setup(args.hw, args.hw, 0)
+    o, d = O.get_rays(args.hw, args.hw, focal, c2w)
+    o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+    n = min(CHUNK, o.shape[0])
+    chunks = 3
+    t_best = []
+    with torch.no_grad():
+        for k in range(chunks):
+            lo = (k * 7919 * n) % max(o.shape[0] - n + 1, 1)
+            rand = (torch.rand(n, COARSE), torch.rand(n, 1), torch.rand(n, FINE, 1))
+            t0 = time.perf_counter()
+            O.network_forward(sd, o[lo:lo + n], d[lo:lo + n], *rand)
+            t_best.append(time.perf_counter() - t0)
+    dt = float(np.mean(t_best[1:]))                     # first chunk is warm-up
+    return {"value": n / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{chunks - 1} timed 4096-ray chunks (+1 warm-up) of the same frame through the CPU oracle, no_grad, "
+                      f"{os.cpu_count()} threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--hw", type=int, default=800, help="frame height = width")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import _native as nat
+    import dataloader
+    import nerf_model
+    import synthetic
+
+    net = nerf_model.NeRFNetwork()
+    net.load_state_dict(synthetic.make_state_dict(5, "dense"))
+    net = net.to(dev)
+    H = W = args.hw
+    nrays = H * W
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = torch.empty((nrays, 3), device=dev, dtype=torch.float32)
+    host_o = torch.empty((nrays, 3), dtype=torch.float32).pin_memory()
+    host_d = torch.empty((nrays, 3), dtype=torch.float32).pin_memory()
+    host_im = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+    gathered = torch.empty((world, H, W, 3), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def rays_for(step):
+        c2w, focal = frame_setup(H, W, step * world + rank)
+        o, d = dataloader.get_rays(H, W, focal, c2w, device=dev)
+        return o.reshape(nrays, 3), d.reshape(nrays, 3)
+
+    def render(o, d):
+        with torch.no_grad():
+            for i in range(0, nrays, CHUNK):
+                out[i:i + CHUNK] = net.forward(o[i:i + CHUNK], d[i:i + CHUNK])["fine_rgb_rays"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident arm ("value")
+    o, d = rays_for(0)
+    for _ in range(args.warmup):
+        render(o, d)
+    barrier()
+    nat.launches = 0
+    nat.kernel_events = []
+    step_ms = []
+    with ClockSampler(local_rank) as clocks:
+        for k in range(args.steps):
+            o, d = rays_for(k)
+            flush.fill_(k & 0xFF)
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            render(o, d)
+            t1.record()
+            barrier()
+            step_ms.append(t0.elapsed_time(t1))
+    launches = nat.launches
+    events, nat.kernel_events = nat.kernel_events, None
+    ms = torch.tensor([float(np.mean(step_ms))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item())
+    value = nrays * world / (ms_per_step * 1e-3)
+
+    mlp_ms = sum(a.elapsed_time(b) for _, _, a, b in events)
+    mlp_samples = sum(u for _, u, _, _ in events)
+    pk = peaks()
+    achieved = mlp_samples * FLOP_PER_SAMPLE / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    traffic = None
+    tf = ROOT / "profiles" / "mlp_tc_traffic.json"
+    if tf.exists():
+        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "mlp_tc_kernel", "achieved": achieved, "peak": pk["tflops_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+                "peak_source": f"{pk['source']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); "
+                               f"burst {pk['tflops_burst']}",
+                "frac_of_burst": achieved / pk["tflops_burst"], "launches_timed": len(events),
+                "kernel_share_of_step": mlp_ms / (sum(step_ms) or 1.0),
+                "flop_per_sample": FLOP_PER_SAMPLE}
+
+    # ------------------------------------------------------------------ end-to-end arm (host buffers)
+    def e2e_step(k):
+        o, d = rays_for(k)                    # stands in for the reference's CPU get_rays: produce host rays first
+        host_o.copy_(o); host_d.copy_(d)
+        torch.cuda.synchronize()
+        flush.fill_(k & 0xFF)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        od = host_o.to(dev, non_blocking=True)           # nerf_helpers.py:184: o_rays.to(device), d_rays.to(device)
+        dd = host_d.to(dev, non_blocking=True)
+        render(od, dd)
+        im = (out * 255).clamp_(0, 255).to(torch.uint8).reshape(H, W, 3)     # nerf_helpers.py:207-210
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, im)
+        host_im.copy_(im, non_blocking=True)
+        t1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        barrier()
+        return t0.elapsed_time(t1), wall * 1e3
+    e2e_step(0)
+    e2e = [e2e_step(k) for k in range(args.steps)]
+    e_ms = torch.tensor([float(np.mean([max(a, b) for a, b in e2e]))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = nrays * world / (float(e_ms.item()) * 1e-3)
+
+    if rank == 0:
+        line = {
+            "metric": "rays/sec render (device-timed)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(host_o.numel() * 4 * 2),
+                    "d2h_bytes_per_step": int(host_im.numel()), "ms_per_step": float(e_ms.item())},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

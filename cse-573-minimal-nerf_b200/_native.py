@@ -74,9 +74,35 @@ def exported_symbols():
     return list(_PROTOTYPES)
 
 
+launches = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+kernel_events = None  # when a list: (name, start_event, end_event) appended around each timed tensor-core launch
+
+
 def check(code, what):
+    global launches
     if code != 0:
         raise RuntimeError(f"{what} failed ({code}): {lib().nerf_last_error().decode()}")
+    launches += 1
+
+
+class timed_kernel:
+    """Brackets one kernel launch with CUDA events on the current stream when `kernel_events` is a list."""
+
+    def __init__(self, name, units):
+        self.name, self.units = name, units
+
+    def __enter__(self):
+        if kernel_events is not None:
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t1 = torch.cuda.Event(enable_timing=True)
+            self.t0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if kernel_events is not None:
+            self.t1.record()
+            kernel_events.append((self.name, self.units, self.t0, self.t1))
+        return False
 
 
 def dev(t, name, dtype=torch.float32):

@@ -137,10 +137,10 @@ extern "C" int nerf_positional_encoding(const float* x, int64_t n, int c, int L,
 extern "C" int nerf_mlp_forward_fp32(const float* const* params20_host, int position_dim, int direction_dim,
                                      const float* samples, const float* direc, int64_t N, int S,
                                      float* sigma, float* rgb, void* stream) {
-    NERF_REQUIRE(params20_host && samples && direc && sigma && rgb, "nerf_mlp_forward_fp32: null pointer");
     NERF_REQUIRE(N >= 0 && S > 0 && position_dim > 0 && direction_dim > 0 && position_dim <= 32 && direction_dim <= 32,
                  "nerf_mlp_forward_fp32: bad size");
     if (N == 0) return 0;
+    NERF_REQUIRE(params20_host && samples && direc && sigma && rgb, "nerf_mlp_forward_fp32: null pointer");
     NetParams P;
     for (int i = 0; i < 20; ++i) {
         NERF_REQUIRE(params20_host[i], "nerf_mlp_forward_fp32: params20_host[%d] is NULL", i);

@@ -370,11 +370,11 @@ using namespace nerf;
 
 static int launch_mlp_tc(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
                          int64_t N, int S, float* sigma, float* rgb, void* stream) {
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_forward_tc: bad size N=%lld S=%d", (long long)N, S);
+    if (N == 0) return 0;
     NERF_REQUIRE(packed && d && sigma && rgb, "nerf_mlp_forward_tc: null pointer");
     NERF_REQUIRE(samples || (o && ts), "nerf_mlp_forward_tc: need either samples or (o, ts)");
     NERF_REQUIRE(((uintptr_t)packed & 127) == 0, "nerf_mlp_forward_tc: packed buffer must be 128-byte aligned");
-    NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_forward_tc: bad size N=%lld S=%d", (long long)N, S);
-    if (N == 0) return 0;
     static thread_local bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);

@@ -297,34 +297,34 @@ extern "C" int nerf_raygen(const float* c2w_host, int H, int W, float focal, con
 
 extern "C" int nerf_coarse_sample(const float* o, const float* d, const float* u, const float* t_base, float step,
                                   int64_t N, int C, float* samples, float* ts, void* stream) {
-    NERF_REQUIRE(o && d && u && t_base && ts, "nerf_coarse_sample: null pointer");
     NERF_REQUIRE(N >= 0 && C > 0, "nerf_coarse_sample: bad size N=%lld C=%d", (long long)N, C);
     if (N == 0) return 0;
+    NERF_REQUIRE(o && d && u && t_base && ts, "nerf_coarse_sample: null pointer");
     coarse_sample_kernel<<<grid_for(N * C, 256), 256, 0, (cudaStream_t)stream>>>(o, d, u, t_base, step, N * C, C, samples, ts);
     return check_launch("nerf_coarse_sample");
 }
 
 extern "C" int nerf_deltas(const float* ts, int64_t N, int S, float* deltas, void* stream) {
-    NERF_REQUIRE(ts && deltas, "nerf_deltas: null pointer");
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_deltas: bad size");
     if (N == 0) return 0;
+    NERF_REQUIRE(ts && deltas, "nerf_deltas: null pointer");
     deltas_kernel<<<grid_for(N * S, 256), 256, 0, (cudaStream_t)stream>>>(ts, N * S, S, deltas);
     return check_launch("nerf_deltas");
 }
 
 extern "C" int nerf_weights(const float* sigma, const float* deltas, int64_t N, int S, float* weights, void* stream) {
-    NERF_REQUIRE(sigma && deltas && weights, "nerf_weights: null pointer");
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_weights: bad size");
     if (N == 0) return 0;
+    NERF_REQUIRE(sigma && deltas && weights, "nerf_weights: null pointer");
     composite_kernel<0><<<grid_for(N, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(
         sigma, nullptr, deltas, N, S, nullptr, weights, nullptr, nullptr, nullptr, nullptr);
     return check_launch("nerf_weights");
 }
 
 extern "C" int nerf_ray_color(const float* weights, const float* rgb, int64_t N, int S, float* ray_rgb, void* stream) {
-    NERF_REQUIRE(weights && rgb && ray_rgb, "nerf_ray_color: null pointer");
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_ray_color: bad size");
     if (N == 0) return 0;
+    NERF_REQUIRE(weights && rgb && ray_rgb, "nerf_ray_color: null pointer");
     ray_color_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(weights, rgb, N, S, ray_rgb);
     return check_launch("nerf_ray_color");
 }
@@ -332,9 +332,9 @@ extern "C" int nerf_ray_color(const float* weights, const float* rgb, int64_t N,
 extern "C" int nerf_composite(const float* sigma, const float* rgb, const float* ts, int64_t N, int S,
                               float* deltas, float* weights, float* ray_rgb, float* depth, float* acc,
                               float* stats2, void* stream) {
-    NERF_REQUIRE(sigma && rgb && ts, "nerf_composite: null pointer");
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_composite: bad size");
     if (N == 0) return 0;
+    NERF_REQUIRE(sigma && rgb && ts, "nerf_composite: null pointer");
     composite_kernel<1><<<grid_for(N, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(
         sigma, rgb, ts, N, S, deltas, weights, ray_rgb, depth, acc, stats2);
     return check_launch("nerf_composite");
@@ -343,9 +343,9 @@ extern "C" int nerf_composite(const float* sigma, const float* rgb, const float*
 extern "C" int nerf_fine_sample(const float* o, const float* d, const float* w, const float* ts, const float* eps,
                                 const float* u, const float* q_base, int64_t N, int C, int F, float near_, float far_,
                                 float* fine_samples, float* fine_ts, int64_t* idx, void* stream) {
-    NERF_REQUIRE(o && d && w && ts && eps && u && q_base && fine_ts, "nerf_fine_sample: null pointer");
     NERF_REQUIRE(N >= 0 && C > 0 && F > 0 && C <= 2048, "nerf_fine_sample: bad size N=%lld C=%d F=%d", (long long)N, C, F);
     if (N == 0) return 0;
+    NERF_REQUIRE(o && d && w && ts && eps && u && q_base && fine_ts, "nerf_fine_sample: null pointer");
     const size_t smem = (size_t)kWarpsPerBlock * (2 * C + 2) * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(fine_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     fine_sample_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, smem, (cudaStream_t)stream>>>(
@@ -355,10 +355,10 @@ extern "C" int nerf_fine_sample(const float* o, const float* d, const float* w, 
 
 extern "C" int nerf_merge_sort(const float* o, const float* d, const float* ts_a, int A, const float* ts_b, int B,
                                int64_t N, float* ts_sorted, float* samples_sorted, void* stream) {
-    NERF_REQUIRE(ts_a && ts_b && ts_sorted, "nerf_merge_sort: null pointer");
-    NERF_REQUIRE(!samples_sorted || (o && d), "nerf_merge_sort: samples_sorted needs o and d");
     NERF_REQUIRE(N >= 0 && A >= 0 && B >= 0 && A + B > 0 && A + B <= 1024, "nerf_merge_sort: bad size A=%d B=%d", A, B);
     if (N == 0) return 0;
+    NERF_REQUIRE(ts_a && ts_b && ts_sorted, "nerf_merge_sort: null pointer");
+    NERF_REQUIRE(!samples_sorted || (o && d), "nerf_merge_sort: samples_sorted needs o and d");
     const size_t smem = (size_t)kWarpsPerBlock * 2 * (A + B) * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     merge_sort_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, smem, (cudaStream_t)stream>>>(

@@ -110,8 +110,10 @@ class NeRFModel(nn.Module):
         sigma = torch.empty((N, S, 1), device=ts.device, dtype=torch.float32)
         rgb = torch.empty((N, S, 3), device=ts.device, dtype=torch.float32)
         if self.uses_tensor_cores():
-            nat.check(nat.lib().nerf_mlp_forward_tc(nat.ptr(self.packed_weights()), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(ts),
-                                                    N, S, nat.ptr(sigma), nat.ptr(rgb), nat.stream()), "nerf_mlp_forward_tc")
+            packed = self.packed_weights()
+            with nat.timed_kernel("mlp_tc_kernel", N * S):
+                nat.check(nat.lib().nerf_mlp_forward_tc(nat.ptr(packed), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(ts),
+                                                        N, S, nat.ptr(sigma), nat.ptr(rgb), nat.stream()), "nerf_mlp_forward_tc")
             return sigma, rgb
         pts = d_rays[:, None, :] * ts + o_rays[:, None, :]
         return self.forward(pts.contiguous(), d_rays)

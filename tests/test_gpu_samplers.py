@@ -76,7 +76,8 @@ def test_compositing(golden, mods):
         sgc = T(g[f"sigma_{S}"])
         torch.testing.assert_close(c["stats"].cpu(), torch.stack([(sgc ** 2).sum(), (sgc != 0).sum().float()]), rtol=1e-5, atol=0)
         # all-zero density rays render black with zero opacity
-        assert (c["rgb"][::5] == 0).all() and (c["acc"][::5] == 0).all()
+        empty = (sg == 0).all(dim=1)[:, 0]
+        assert empty.sum() >= 8 and (c["rgb"][empty] == 0).all() and (c["acc"][empty] == 0).all()
 
 
 def test_compositing_reference_kats(mods):
