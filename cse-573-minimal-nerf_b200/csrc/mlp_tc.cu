@@ -20,92 +20,40 @@
 //
 // Step / barrier protocol: steps are numbered globally (gs); step gs uses D region gs&1 and the barrier pair
 // dfull[gs&1] (MMA -> epilogue, tcgen05.commit) / edone[gs&1] (epilogue -> MMA, 256 arrivals).
-#include "common.cuh"
-#include "pack_layout.cuh"
-#include "umma.cuh"
+#include <stdlib.h>
+#include "mlp_tc_common.cuh"
 
 namespace nerf {
 
 namespace tc {
 constexpr int kTileM = 128;
-constexpr int kSlots = 11;
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
+constexpr int kSlots = 9;
+constexpr int kThreads = 512;          // warp 0 producer, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue, 12-15 PE
+constexpr int kEpiWarps = 8;
+constexpr int kPEWarps = 4;
 constexpr uint32_t kColD = 0, kColA0 = 256, kColA1 = 384;
 
 // shared-memory map (bytes from a 1024-aligned base)
-constexpr uint32_t kOffPE = 0;
-constexpr uint32_t kOffPEDir = 16384;
-constexpr uint32_t kOffRing = 32768;
+constexpr uint32_t kOffPE = 0;             // 2 x [128 x 64] bf16 PE(x) tiles (double buffered across tiles)
+constexpr uint32_t kOffPEDir = 32768;      // 2 x [128 x 64] bf16 PE(dir) tiles
+constexpr uint32_t kOffRing = 65536;
 constexpr uint32_t kOffBias = kOffRing + kSlots * 16384;
 constexpr uint32_t kOffBars = kOffBias + ((pk::kBiasFloats * 4 + 15) / 16) * 16;
-constexpr uint32_t kNumBars = 2 * kSlots + 5;
+constexpr uint32_t kNumBars = 2 * kSlots + 8;
 constexpr uint32_t kOffTmemHolder = kOffBars + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemHolder + 16 + 1024;   // + alignment slack
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-constexpr float kPiF = 3.14159274101257324f;
-constexpr float kInv2Pi = 0.15915494309189535f;
-constexpr float k2PiHi = 6.28318548202514648f;
-constexpr float k2PiLo = -1.7484555e-7f;
 }  // namespace tc
 
-struct StageRef { uint32_t offset, bytes; };
-struct StageTable { StageRef s[pk::kStages]; };
-constexpr StageTable make_stage_table() {
-    StageTable t{};
-    for (int i = 0; i < pk::kStages; ++i) {
-        t.s[i].offset = pk::kLayout.st[i].offset;
-        t.s[i].bytes = (uint32_t)pk::kLayout.st[i].rows * 128u;
-    }
-    return t;
-}
-__constant__ StageTable c_stages = make_stage_table();
-
-// cos / sin of a = fl32(2^i pi) * x for |a| up to a few thousand: Cody-Waite reduction by 2 pi in two FMAs,
-// then the MUFU approximations on [-pi, pi] (abs error ~1e-6, far below bf16 resolution).
-__device__ __forceinline__ void fast_sincos(float a, float& s, float& c) {
-    const float k = rintf(a * tc::kInv2Pi);
-    float r = fmaf(-k, tc::k2PiHi, a);
-    r = fmaf(-k, tc::k2PiLo, r);
-    s = __sinf(r);
-    c = __cosf(r);
-}
-
-// Row `r` of a [128 x 64] bf16 K-major 128B-swizzled tile <- 32 packed registers (64 bf16).
-__device__ __forceinline__ void store_row_sw128(uint8_t* tile, int r, const uint32_t (&v)[32]) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        uint4 q = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-        *(uint4*)(tile + r * 128 + ((c ^ (r & 7)) << 4)) = q;
-    }
-}
-
-template <int L>
-__device__ __forceinline__ void encode_row(const float (&x)[3], uint32_t (&v)[32]) {
-    // per frequency: [cos x, cos y, cos z, sin x, sin y, sin z] (nerf_model.py:29-31) -> 3 packed registers
-#pragma unroll
-    for (int i = 0; i < L; ++i) {
-        const float f = tc::kPiF * (float)(1 << i);
-        float s[3], c[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) fast_sincos(__fmul_rn(f, x[k]), s[k], c[k]);
-        v[3 * i + 0] = umma::pack_bf16(c[0], c[1]);
-        v[3 * i + 1] = umma::pack_bf16(c[2], s[0]);
-        v[3 * i + 2] = umma::pack_bf16(s[1], s[2]);
-    }
-#pragma unroll
-    for (int j = 3 * L; j < 32; ++j) v[j] = 0u;
-}
-
+template <bool PROFILE>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_rays, const float* __restrict__ d_rays,
               const float* __restrict__ ts, const float* __restrict__ samples, int64_t total, int S,
-              float* __restrict__ sigma_out, float* __restrict__ rgb_out) {
+              float* __restrict__ sigma_out, float* __restrict__ rgb_out, long long* __restrict__ dbg) {
+    long long prof[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sPE = smem + tc::kOffPE;
-    uint8_t* sPEDir = smem + tc::kOffPEDir;
     uint8_t* sRing = smem + tc::kOffRing;
     float* sBias = (float*)(smem + tc::kOffBias);
     uint64_t* bars = (uint64_t*)(smem + tc::kOffBars);
@@ -113,7 +61,8 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
     uint64_t* empty = bars + tc::kSlots;
     uint64_t* dfull = bars + 2 * tc::kSlots;
     uint64_t* edone = dfull + 2;
-    uint64_t* pe_ready = edone + 2;
+    uint64_t* pe_full = edone + 2;
+    uint64_t* pe_empty = pe_full + 2;
     uint32_t* tmem_holder = (uint32_t*)(smem + tc::kOffTmemHolder);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -121,9 +70,12 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
 
     if (tid == 0) {
         for (int i = 0; i < tc::kSlots; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
-        umma::mbar_init(&dfull[0], 1); umma::mbar_init(&dfull[1], 1);
-        umma::mbar_init(&edone[0], tc::kEpiThreads); umma::mbar_init(&edone[1], tc::kEpiThreads);
-        umma::mbar_init(pe_ready, tc::kEpiThreads);
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&dfull[i], 1);
+            umma::mbar_init(&edone[i], tc::kEpiWarps);
+            umma::mbar_init(&pe_full[i], tc::kPEWarps);
+            umma::mbar_init(&pe_empty[i], 1);
+        }
         umma::fence_mbar_init();
     }
     if (warp == 2) umma::tmem_alloc(tmem_holder, 512);
@@ -137,195 +89,236 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
     const uint32_t tmem = *tmem_holder;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ weight producer
-        if (lane == 0) {
-            uint32_t cnt = 0;
-            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int s = 0; s < pk::kStages; ++s, ++cnt) {
-                    const uint32_t slot = cnt % tc::kSlots, ph = (cnt / tc::kSlots) & 1;
-                    umma::mbar_wait(&empty[slot], ph ^ 1);
+        // ------------------------------------------------------------------ weight producer (warp-uniform, one lane issues)
+        const bool leader = umma::elect_one();
+        uint32_t cnt = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int s = 0; s < pk::kStages; ++s, ++cnt) {
+                const uint32_t slot = cnt % tc::kSlots, ph = (cnt / tc::kSlots) & 1;
+                NERF_PROF_BEGIN(tw)
+                umma::mbar_wait(&empty[slot], ph ^ 1);
+                NERF_PROF_END(tw, 4)
+                if (leader) {
                     const StageRef st = c_stages.s[s];
                     umma::mbar_arrive_expect_tx(&full[slot], st.bytes);
                     umma::bulk_g2s(sRing + slot * 16384, packed + st.offset, st.bytes, &full[slot]);
                 }
+                __syncwarp();
             }
         }
+        if (PROFILE && lane == 0) dbg[blockIdx.x * 16 + 4] = prof[4];
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t kI128 = umma::make_idesc_bf16(128, 128);
-            constexpr uint32_t kI16 = umma::make_idesc_bf16(128, 16);
-            const uint64_t descPE = umma::make_desc_k_sw128(umma::smem_u32(sPE));
-            const uint64_t descPEDir = umma::make_desc_k_sw128(umma::smem_u32(sPEDir));
-            uint32_t cnt = 0;         // weight stages consumed
-            int64_t gs = 0;           // global step index
-            int64_t e_waited = 0;     // epilogue steps already observed
-            uint32_t tile_iter = 0;
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
+        const bool leader = umma::elect_one();
+        constexpr uint32_t kI128 = umma::make_idesc_bf16(128, 128);
+        constexpr uint32_t kI16 = umma::make_idesc_bf16(128, 16);
+        uint32_t cnt = 0;         // weight stages consumed
+        int64_t gs = 0;           // global step index
+        int64_t e_waited = 0;     // epilogue steps already observed
+        uint32_t tile_iter = 0;
+        NERF_PROF_BEGIN(t_mma_total)
 
-            auto ensure_e = [&](int64_t k) {       // epilogue of global step k (and all before it) is done
-                while (e_waited <= k) {
-                    umma::mbar_wait(&edone[e_waited & 1], (uint32_t)((e_waited >> 1) & 1));
-                    ++e_waited;
-                }
-                umma::tc_fence_after();
-            };
-            // one K=64 weight stage: nk16 K=16 slices; A from TMEM columns (a_col >= 0) or from a smem tile
-            auto kblock = [&](uint32_t d_col, int a_col, uint64_t a_desc, uint32_t idesc, int nk16, uint32_t& acc) {
-                const uint32_t slot = cnt % tc::kSlots, ph = (cnt / tc::kSlots) & 1;
-                umma::mbar_wait(&full[slot], ph);
-                umma::tc_fence_after();
+        auto ensure_e = [&](int64_t k) {       // epilogue of global step k (and all before it) is done
+            NERF_PROF_BEGIN(tw)
+            while (e_waited <= k) {
+                umma::mbar_wait(&edone[e_waited & 1], (uint32_t)((e_waited >> 1) & 1));
+                ++e_waited;
+            }
+            NERF_PROF_END(tw, 2)
+            umma::tc_fence_after();
+        };
+        // one K=64 weight stage: nk16 K=16 slices; A from TMEM columns (a_col >= 0) or from a smem tile
+        auto kblock = [&](uint32_t d_col, int a_col, uint64_t a_desc, uint32_t idesc, int nk16, uint32_t& acc) {
+            const uint32_t slot = cnt % tc::kSlots, ph = (cnt / tc::kSlots) & 1;
+            NERF_PROF_BEGIN(tw)
+            umma::mbar_wait(&full[slot], ph);
+            NERF_PROF_END(tw, 1)
+            umma::tc_fence_after();
+            if (leader) {
                 const uint64_t bdesc = umma::make_desc_k_sw128(umma::smem_u32(sRing + slot * 16384));
+#pragma unroll 4
                 for (int k = 0; k < nk16; ++k) {
-                    if (a_col >= 0) umma::mma_ts(tmem + d_col, tmem + (uint32_t)a_col + 8u * k, bdesc + 2u * k, idesc, acc);
-                    else            umma::mma_ss(tmem + d_col, a_desc + 2u * k, bdesc + 2u * k, idesc, acc);
-                    acc = 1;
+                    if (a_col >= 0) umma::mma_ts(tmem + d_col, tmem + (uint32_t)a_col + 8u * k, bdesc + 2u * k, idesc, acc | (uint32_t)k);
+                    else            umma::mma_ss(tmem + d_col, a_desc + 2u * k, bdesc + 2u * k, idesc, acc | (uint32_t)k);
                 }
                 umma::mma_commit(&empty[slot]);
-                ++cnt;
-            };
-            // a hidden layer read from A buffer `a_base` (K = 256), optionally preceded by a smem K block
-            auto layer = [&](int a_base, bool pe_first) {
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
-                    uint32_t acc = 0;
-                    ensure_e(gs - 2);
-                    if (pe_first) kblock(d_col, -1, descPE, kI128, 4, acc);
-                    kblock(d_col, a_base + 0, 0, kI128, 4, acc);
-                    kblock(d_col, a_base + 32, 0, kI128, 4, acc);
-                    if (h == 0) ensure_e(gs - 1);
-                    kblock(d_col, a_base + 64, 0, kI128, 4, acc);
-                    kblock(d_col, a_base + 96, 0, kI128, 4, acc);
-                    umma::mma_commit(&dfull[gs & 1]);
-                    ++gs;
-                }
-            };
+            }
+            __syncwarp();
+            acc = 1;
+            ++cnt;
+        };
+        // a hidden layer read from A buffer `a_base` (K = 256), optionally preceded by the PE(x) K block
+        auto layer = [&](int a_base, bool pe_first, uint64_t descPE) {
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
+                uint32_t acc = 0;
+                ensure_e(gs - 2);
+                if (pe_first) kblock(d_col, -1, descPE, kI128, 4, acc);
+                kblock(d_col, a_base + 0, 0, kI128, 4, acc);
+                kblock(d_col, a_base + 32, 0, kI128, 4, acc);
+                if (h == 0) ensure_e(gs - 1);
+                kblock(d_col, a_base + 64, 0, kI128, 4, acc);
+                kblock(d_col, a_base + 96, 0, kI128, 4, acc);
+                if (leader) umma::mma_commit(&dfull[gs & 1]);
+                __syncwarp();
+                ++gs;
+            }
+        };
 
-            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
-                umma::mbar_wait(pe_ready, tile_iter & 1);
-                umma::tc_fence_after();
-                for (int h = 0; h < 2; ++h) {                                   // mlp.0: A = PE(x) tile
-                    uint32_t acc = 0;
-                    ensure_e(gs - 2);
-                    kblock(tc::kColD + 128u * (uint32_t)(gs & 1), -1, descPE, kI128, 4, acc);
-                    umma::mma_commit(&dfull[gs & 1]);
-                    ++gs;
-                }
-                layer(tc::kColA0, false);     // mlp.2        reads A0 (epilogue writes A1)
-                layer(tc::kColA1, false);     // mlp.4        reads A1
-                layer(tc::kColA0, false);     // mlp.6        reads A0
-                layer(tc::kColA1, true);      // feature_fn.0 reads PE(x) + A1
-                layer(tc::kColA0, false);     // feature_fn.2 reads A0
-                layer(tc::kColA1, false);     // feature_fn.4 reads A1, feat -> A0
-                {                             // rgb_fn.0: PE(dir) + feat (A0) -> D region, r -> A1[0:64]
-                    const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
-                    uint32_t acc = 0;
-                    ensure_e(gs - 2);
-                    kblock(d_col, -1, descPEDir, kI128, 2, acc);
-                    kblock(d_col, tc::kColA0 + 0, 0, kI128, 4, acc);
-                    kblock(d_col, tc::kColA0 + 32, 0, kI128, 4, acc);
-                    ensure_e(gs - 1);
-                    kblock(d_col, tc::kColA0 + 64, 0, kI128, 4, acc);
-                    kblock(d_col, tc::kColA0 + 96, 0, kI128, 4, acc);
-                    umma::mma_commit(&dfull[gs & 1]);
-                    ++gs;
-                }
-                {                             // density_fn.0: feat (A0) -> 16 columns
-                    const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
-                    uint32_t acc = 0;
-                    ensure_e(gs - 2);
-                    for (int kb = 0; kb < 4; ++kb) kblock(d_col, tc::kColA0 + 32 * kb, 0, kI16, 4, acc);
-                    umma::mma_commit(&dfull[gs & 1]);
-                    ++gs;
-                }
-                {                             // rgb_fn.2: r (A1[0:64]) -> 16 columns
-                    const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
-                    uint32_t acc = 0;
-                    ensure_e(gs - 2);
-                    for (int kb = 0; kb < 2; ++kb) kblock(d_col, tc::kColA1 + 32 * kb, 0, kI16, 4, acc);
-                    umma::mma_commit(&dfull[gs & 1]);
-                    ++gs;
-                }
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+            const uint32_t pb = tile_iter & 1;
+            const uint64_t descPE = umma::make_desc_k_sw128(umma::smem_u32(smem + tc::kOffPE + pb * 16384));
+            const uint64_t descPEDir = umma::make_desc_k_sw128(umma::smem_u32(smem + tc::kOffPEDir + pb * 16384));
+            NERF_PROF_BEGIN(tw)
+            umma::mbar_wait(&pe_full[pb], (tile_iter >> 1) & 1);
+            NERF_PROF_END(tw, 3)
+            umma::tc_fence_after();
+            for (int h = 0; h < 2; ++h) {                                   // mlp.0: A = PE(x) tile
+                uint32_t acc = 0;
+                ensure_e(gs - 2);
+                kblock(tc::kColD + 128u * (uint32_t)(gs & 1), -1, descPE, kI128, 4, acc);
+                if (leader) umma::mma_commit(&dfull[gs & 1]);
+                __syncwarp();
+                ++gs;
+            }
+            layer(tc::kColA0, false, descPE);     // mlp.2        reads A0 (epilogue writes A1)
+            layer(tc::kColA1, false, descPE);     // mlp.4        reads A1
+            layer(tc::kColA0, false, descPE);     // mlp.6        reads A0
+            layer(tc::kColA1, true, descPE);      // feature_fn.0 reads PE(x) + A1
+            layer(tc::kColA0, false, descPE);     // feature_fn.2 reads A0
+            layer(tc::kColA1, false, descPE);     // feature_fn.4 reads A1, feat -> A0
+            {                                     // rgb_fn.0: PE(dir) + feat (A0) -> D region, r -> A1[0:64]
+                const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
+                uint32_t acc = 0;
+                ensure_e(gs - 2);
+                kblock(d_col, -1, descPEDir, kI128, 2, acc);
+                if (leader) umma::mma_commit(&pe_empty[pb]);      // last read of this tile's PE buffers
+                __syncwarp();
+                kblock(d_col, tc::kColA0 + 0, 0, kI128, 4, acc);
+                kblock(d_col, tc::kColA0 + 32, 0, kI128, 4, acc);
+                ensure_e(gs - 1);
+                kblock(d_col, tc::kColA0 + 64, 0, kI128, 4, acc);
+                kblock(d_col, tc::kColA0 + 96, 0, kI128, 4, acc);
+                if (leader) umma::mma_commit(&dfull[gs & 1]);
+                __syncwarp();
+                ++gs;
+            }
+            {                                     // density_fn.0: feat (A0) -> 16 columns
+                const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
+                uint32_t acc = 0;
+                ensure_e(gs - 2);
+                for (int kb = 0; kb < 4; ++kb) kblock(d_col, tc::kColA0 + 32 * kb, 0, kI16, 4, acc);
+                if (leader) umma::mma_commit(&dfull[gs & 1]);
+                __syncwarp();
+                ++gs;
+            }
+            {                                     // rgb_fn.2: r (A1[0:64]) -> 16 columns
+                const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
+                uint32_t acc = 0;
+                ensure_e(gs - 2);
+                for (int kb = 0; kb < 2; ++kb) kblock(d_col, tc::kColA1 + 32 * kb, 0, kI16, 4, acc);
+                if (leader) umma::mma_commit(&dfull[gs & 1]);
+                __syncwarp();
+                ++gs;
             }
         }
+        NERF_PROF_END(t_mma_total, 0)
+        if (PROFILE && lane == 0) { for (int i = 0; i < 4; ++i) dbg[blockIdx.x * 16 + i] = prof[i]; dbg[blockIdx.x * 16 + 8] = tile_iter; }
+    } else if (warp >= 12) {
+        // ------------------------------------------------------------------ PE producers (128 threads, thread = row)
+        const int r = (warp - 12) * 32 + lane;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t pb = it & 1;
+            const int64_t row = tile * tc::kTileM + r;
+            const bool valid = row < total;
+            const int64_t n = valid ? row / S : 0;
+            float x[3] = {0.f, 0.f, 0.f}, u[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+                const float dx = __ldg(d_rays + n * 3), dy = __ldg(d_rays + n * 3 + 1), dz = __ldg(d_rays + n * 3 + 2);
+                if (samples) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) x[k] = samples[row * 3 + k];
+                } else {
+                    const float t = ts[row];                      // d * t + o (nerf_helpers.py:55)
+                    x[0] = __fadd_rn(__fmul_rn(dx, t), __ldg(o_rays + n * 3 + 0));
+                    x[1] = __fadd_rn(__fmul_rn(dy, t), __ldg(o_rays + n * 3 + 1));
+                    x[2] = __fadd_rn(__fmul_rn(dz, t), __ldg(o_rays + n * 3 + 2));
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) x[k] = __fdiv_rn(x[k], tcm::kPiF);           // nerf_model.py:377
+                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);                    // nerf_model.py:373
+                u[0] = __fdiv_rn(dx, nrm); u[1] = __fdiv_rn(dy, nrm); u[2] = __fdiv_rn(dz, nrm);
+            }
+            uint32_t v[32];
+            encode_row<10>(x, v);
+            umma::mbar_wait(&pe_empty[pb], ((it >> 1) & 1) ^ 1);      // MMAs of tile it-2 no longer read buffer pb
+            store_row_sw128(smem + tc::kOffPE + pb * 16384, r, v);
+            encode_row<4>(u, v);
+            store_row_sw128(smem + tc::kOffPEDir + pb * 16384, r, v);
+            umma::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&pe_full[pb]);
+        }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (256 threads)
+        // ------------------------------------------------------------------ epilogue (8 warps)
         const int q = warp & 3;                 // TMEM lane quarter this warp may touch
         const int wh = (warp - 4) >> 2;         // column half handled by this warp
         const int r = q * 32 + lane;            // row (sample) inside the tile
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         int64_t gs = 0;
+        NERF_PROF_BEGIN(t_epi_total)
 
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int64_t row = tile * tc::kTileM + r;
             const bool valid = row < total;
-            {   // ---- positional encodings for this tile
-                uint32_t v[32];
-                const int64_t n = valid ? row / S : 0;
-                if (wh == 0) {
-                    float x[3] = {0.f, 0.f, 0.f};
-                    if (valid) {
-                        if (samples) {
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) x[k] = samples[row * 3 + k];
-                        } else {
-                            const float t = ts[row];
-#pragma unroll
-                            for (int k = 0; k < 3; ++k)      // d * t + o (nerf_helpers.py:55)
-                                x[k] = __fadd_rn(__fmul_rn(__ldg(d_rays + n * 3 + k), t), __ldg(o_rays + n * 3 + k));
-                        }
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) x[k] = __fdiv_rn(x[k], tc::kPiF);     // nerf_model.py:377
-                    }
-                    encode_row<10>(x, v);
-                    store_row_sw128(sPE, r, v);
-                } else {
-                    float u[3] = {0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float dx = __ldg(d_rays + n * 3), dy = __ldg(d_rays + n * 3 + 1), dz = __ldg(d_rays + n * 3 + 2);
-                        const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);              // nerf_model.py:373
-                        u[0] = __fdiv_rn(dx, nrm); u[1] = __fdiv_rn(dy, nrm); u[2] = __fdiv_rn(dz, nrm);
-                    }
-                    encode_row<4>(u, v);
-                    store_row_sw128(sPEDir, r, v);
-                }
-                umma::fence_proxy_async_smem();
-                umma::mbar_arrive(pe_ready);
-            }
             // ---- 7 hidden layers x 2 halves, then rgb_fn.0: 128 columns -> bias, (ReLU), bf16 -> A buffer
             for (int s = 0; s < 15; ++s, ++gs) {
                 const int layer = s >> 1, nhalf = (s < 14) ? (s & 1) : 0;
                 const bool relu = (layer != 6);                       // feature_fn.4 is linear (nerf_model.py:347)
                 // writes: mlp.0 -> A0, mlp.2 -> A1, mlp.4 -> A0, mlp.6 -> A1, ff.0 -> A0, ff.2 -> A1, ff.4 -> A0, rgb_fn.0 -> A1
                 const uint32_t a_dst = (layer & 1) ? tc::kColA1 : tc::kColA0;
-                const float* bias = sBias + (s < 14 ? layer * 256 + nhalf * 128 : pk::kBiasR0);
+                const float* bias = sBias + (s < 14 ? layer * 256 + nhalf * 128 : pk::kBiasR0) + wh * 64;
+                NERF_PROF_BEGIN(tw)
                 umma::mbar_wait(&dfull[gs & 1], (uint32_t)((gs >> 1) & 1));
+                NERF_PROF_END(tw, 6)
                 umma::tc_fence_after();
-                const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
+                const uint32_t d_addr = tmem + lane_base + tc::kColD + 128u * (uint32_t)(gs & 1) + (uint32_t)(wh * 64);
+                uint32_t v0[32], v1[32];
+                umma::tmem_ld32(d_addr, v0);
+                umma::tmem_ld32(d_addr + 32, v1);
+                umma::tmem_wait_ld();
+                uint32_t p[16];
+                // output feature n = nhalf*128 + wh*64 + j is K index n of the next layer: TMEM column n/2
+                const uint32_t a_addr = tmem + lane_base + a_dst + (uint32_t)((nhalf * 128 + wh * 64) >> 1);
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int col = wh * 64 + c * 32;              // column inside this 128-wide half
-                    uint32_t v[32];
-                    umma::tmem_ld32(tmem + lane_base + d_col + col, v);
-                    umma::tmem_wait_ld();
-                    uint32_t p[16];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b4 = *(const float4*)(bias + col + 4 * j);
-                        const float x0 = __uint_as_float(v[4 * j + 0]) + b4.x, x1 = __uint_as_float(v[4 * j + 1]) + b4.y;
-                        const float x2 = __uint_as_float(v[4 * j + 2]) + b4.z, x3 = __uint_as_float(v[4 * j + 3]) + b4.w;
-                        p[2 * j + 0] = relu ? umma::pack_bf16_relu(x0, x1) : umma::pack_bf16(x0, x1);
-                        p[2 * j + 1] = relu ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
-                    }
-                    // output feature n = nhalf*128 + col + j is K index n of the next layer: TMEM column n/2
-                    umma::tmem_st16(tmem + lane_base + a_dst + (uint32_t)((nhalf * 128 + col) >> 1), p);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = *(const float4*)(bias + 4 * j);
+                    const float x0 = __uint_as_float(v0[4 * j + 0]) + b4.x, x1 = __uint_as_float(v0[4 * j + 1]) + b4.y;
+                    const float x2 = __uint_as_float(v0[4 * j + 2]) + b4.z, x3 = __uint_as_float(v0[4 * j + 3]) + b4.w;
+                    p[2 * j + 0] = relu ? umma::pack_bf16_relu(x0, x1) : umma::pack_bf16(x0, x1);
+                    p[2 * j + 1] = relu ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
                 }
+                umma::tmem_st16(a_addr, p);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = *(const float4*)(bias + 32 + 4 * j);
+                    const float x0 = __uint_as_float(v1[4 * j + 0]) + b4.x, x1 = __uint_as_float(v1[4 * j + 1]) + b4.y;
+                    const float x2 = __uint_as_float(v1[4 * j + 2]) + b4.z, x3 = __uint_as_float(v1[4 * j + 3]) + b4.w;
+                    p[2 * j + 0] = relu ? umma::pack_bf16_relu(x0, x1) : umma::pack_bf16(x0, x1);
+                    p[2 * j + 1] = relu ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
+                }
+                umma::tmem_st16(a_addr + 16, p);
                 umma::tmem_wait_st();
                 umma::tc_fence_before();
-                umma::mbar_arrive(&edone[gs & 1]);
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&edone[gs & 1]);
             }
             // ---- density_fn.0: column 0 -> sigma = relu(. + b) (nerf_model.py:350-353)
             {
+                NERF_PROF_BEGIN(tw)
                 umma::mbar_wait(&dfull[gs & 1], (uint32_t)((gs >> 1) & 1));
+                NERF_PROF_END(tw, 6)
                 umma::tc_fence_after();
                 if (wh == 0) {
                     uint32_t v[4];
@@ -334,12 +327,15 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                     if (valid) sigma_out[row] = fmaxf(__uint_as_float(v[0]) + sBias[pk::kBiasSigma], 0.f);
                 }
                 umma::tc_fence_before();
-                umma::mbar_arrive(&edone[gs & 1]);
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&edone[gs & 1]);
                 ++gs;
             }
             // ---- rgb_fn.2: columns 0..2 -> sigmoid(. + b) (nerf_model.py:358-359)
             {
+                NERF_PROF_BEGIN(tw)
                 umma::mbar_wait(&dfull[gs & 1], (uint32_t)((gs >> 1) & 1));
+                NERF_PROF_END(tw, 6)
                 umma::tc_fence_after();
                 if (wh == 0) {
                     uint32_t v[4];
@@ -354,10 +350,13 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                     }
                 }
                 umma::tc_fence_before();
-                umma::mbar_arrive(&edone[gs & 1]);
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&edone[gs & 1]);
                 ++gs;
             }
         }
+        NERF_PROF_END(t_epi_total, 5)
+        if (PROFILE && tid == 128) { for (int i = 5; i < 8; ++i) dbg[blockIdx.x * 16 + i] = prof[i]; }
     }
     umma::tc_fence_before();
     __syncthreads();
@@ -366,10 +365,23 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
 
 }  // namespace nerf
 
+namespace nerf {
+int launch_mlp_tc2(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
+                   int64_t total, int S, float* sigma, float* rgb, void* stream, long long* dbg);
+}
+
 using namespace nerf;
 
+// NERF_TC_PAIR=1 selects the CTA-pair (cta_group::2) kernel of mlp_tc2.cu; the default is the 1-CTA kernel of this
+// file, which measured faster on B200 (profiles/r01_notes.md): the per-half-layer MMA -> epilogue -> MMA dependency
+// loop is latency-bound and the pair's cross-CTA signalling lengthens it more than the halved weight traffic saves.
+static bool use_pair_kernel() {
+    static const bool v = [] { const char* e = getenv("NERF_TC_PAIR"); return e && e[0] == '1'; }();
+    return v;
+}
+
 static int launch_mlp_tc(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
-                         int64_t N, int S, float* sigma, float* rgb, void* stream) {
+                         int64_t N, int S, float* sigma, float* rgb, void* stream, long long* dbg = nullptr) {
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_forward_tc: bad size N=%lld S=%d", (long long)N, S);
     if (N == 0) return 0;
     NERF_REQUIRE(packed && d && sigma && rgb, "nerf_mlp_forward_tc: null pointer");
@@ -377,16 +389,33 @@ static int launch_mlp_tc(const void* packed, const float* o, const float* d, con
     NERF_REQUIRE(((uintptr_t)packed & 127) == 0, "nerf_mlp_forward_tc: packed buffer must be 128-byte aligned");
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
         if (e != cudaSuccess) { set_error("nerf_mlp_forward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
         attr_set = true;
     }
     const int64_t total = N * S;
+    if (use_pair_kernel()) return launch_mlp_tc2(packed, o, d, ts, samples, total, S, sigma, rgb, stream, dbg);
     const int64_t tiles = (total + tc::kTileM - 1) / tc::kTileM;
-    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    mlp_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, o, d, ts, samples, total, S,
-                                                                              sigma, rgb);
+    int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    if (dbg) {                                        // diagnostic runs only: NERF_TC_MAX_CTAS limits the grid
+        const char* e = getenv("NERF_TC_MAX_CTAS");
+        if (e && atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
+    }
+    if (dbg)
+        mlp_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, o, d, ts, samples,
+                                                                                        total, S, sigma, rgb, dbg);
+    else
+        mlp_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, o, d, ts, samples,
+                                                                                         total, S, sigma, rgb, nullptr);
     return check_launch("nerf_mlp_forward_tc");
+}
+
+// Diagnostic entry point (not in include/nerf_b200.h): same kernel with per-CTA cycle counters, dbg = [grid,16] int64.
+extern "C" int nerf_debug_mlp_tc_profile(const void* packed, const float* o, const float* d, const float* ts,
+                                         int64_t N, int S, float* sigma, float* rgb, long long* dbg, void* stream) {
+    return launch_mlp_tc(packed, o, d, ts, nullptr, N, S, sigma, rgb, stream, dbg);
 }
 
 extern "C" int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, const float* ts,

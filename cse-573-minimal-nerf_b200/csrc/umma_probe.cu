@@ -98,3 +98,56 @@ extern "C" int nerf_debug_umma(int mode, const void* A_bf16, const void* B_bf16,
                                                             d_col, D);
     return check_launch("nerf_debug_umma");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// TMEM bandwidth probe: `nwarps` warps each repeat `iters` x (ld 32x32b.x32 [+ st x16]) on their lane quarter.
+// out[0] = cycles (block-wide, first warp start to last warp end), out[1] = bytes moved by loads.
+namespace nerf {
+__global__ void __launch_bounds__(512, 1) tmem_bw_probe_kernel(int iters, int mode, long long* out) {
+    __shared__ uint32_t holder;
+    __shared__ long long t_begin[16], t_end[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) umma::tmem_alloc(&holder, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t base = holder + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        const uint32_t col = (uint32_t)(((i + (warp >> 2)) * 32) & 255);
+        if (mode == 0 || mode == 2) {
+            uint32_t v[32];
+            umma::tmem_ld32(base + col, v);
+            umma::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc ^= v[j];
+        }
+        if (mode == 1 || mode == 2) {
+            uint32_t p[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) p[j] = acc + j;
+            umma::tmem_st16(base + 256 + (col >> 1), p);
+            umma::tmem_wait_st();
+        }
+    }
+    const long long t1 = clock64();
+    if (lane == 0) { t_begin[warp] = t0; t_end[warp] = t1; }
+    if (acc == 0x12345678) out[7] = acc;
+    umma::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long b = t_begin[0], e = t_end[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { b = min(b, t_begin[w]); e = max(e, t_end[w]); }
+        out[0] = e - b;
+        out[1] = (long long)iters * (blockDim.x >> 5) * 4096;
+    }
+    if (warp == 0) umma::tmem_dealloc(holder, 512);
+}
+}  // namespace nerf
+
+extern "C" int nerf_debug_tmem_bw(int nwarps, int iters, int mode, long long* out, void* stream) {
+    nerf::tmem_bw_probe_kernel<<<1, nwarps * 32, 0, (cudaStream_t)stream>>>(iters, mode, out);
+    return nerf::check_launch("nerf_debug_tmem_bw");
+}

@@ -1,0 +1,49 @@
+"""Per-CTA cycle counters of the fused tcgen05 MLP kernel (diagnostic build of the same kernel).
+usage: python tools/profile_mlp_tc.py [N] [S]"""
+import ctypes
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT), str(ROOT / "cse-573-minimal-nerf_b200")]
+import torch
+import _native as nat
+import nerf_model
+import synthetic
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 192
+dev = torch.device("cuda")
+net = nerf_model.NeRFNetwork()
+net.load_state_dict(synthetic.make_state_dict(5, "dense"))
+net = net.to(dev)
+m = net.fine_network
+packed = m.packed_weights()
+o = torch.randn(N, 3, device=dev) * 0.3
+d = torch.nn.functional.normalize(torch.randn(N, 3, device=dev), dim=1)
+ts = (2 + 4 * torch.rand(N, S, device=dev)).contiguous()
+sigma = torch.empty(N, S, device=dev)
+rgb = torch.empty(N, S, 3, device=dev)
+fn = nat.lib().nerf_debug_mlp_tc_profile
+fn.restype = ctypes.c_int
+fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p] * 4
+dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+import os
+G = int(os.environ.get("NERF_TC_MAX_CTAS", "148"))
+for it in range(3):
+    dbg.zero_()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    nat.check(fn(nat.ptr(packed), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, nat.ptr(sigma), nat.ptr(rgb), nat.ptr(dbg), nat.stream()), "profile")
+    t1.record()
+    torch.cuda.synchronize()
+ms = t0.elapsed_time(t1)
+c = dbg.double().cpu()[:G]
+tiles = c[:, 8].clamp(min=1)
+names = ["mma_total", "mma_wait_full(weights)", "mma_wait_edone(epilogue)", "mma_wait_pe", "producer_wait_empty", "epi_total",
+         "epi_wait_dfull", "epi_pe_time"]
+print(f"N={N} S={S}: {ms:.3f} ms, {N*S*920832/ms/1e9:.1f} TFLOP/s, tiles/CTA {tiles.mean():.1f}")
+for i, n in enumerate(names):
+    per_tile = (c[:, i] / tiles)
+    print(f"  {n:28s} per tile: mean {per_tile.mean():9.0f} clk  min {per_tile.min():9.0f}  max {per_tile.max():9.0f}")
+print("  (tensor-pipe floor per tile: 14.7k clk)")
