@@ -29,6 +29,7 @@ _PROTOTYPES = {
     "nerf_weights": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "nerf_ray_color": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "nerf_composite": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nerf_composite_backward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "nerf_fine_sample": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _f32, _f32, _vp, _vp, _vp, _vp]),
     "nerf_merge_sort": (_int, [_vp, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp, _vp]),
     "nerf_positional_encoding": (_int, [_vp, _i64, _int, _int, _vp, _vp]),
@@ -36,6 +37,7 @@ _PROTOTYPES = {
     "nerf_packed_bytes": (ctypes.c_size_t, []),
     "nerf_pack_weights": (_int, [_vp, _vp, _vp]),
     "nerf_mlp_forward_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
+    "nerf_mlp_forward_tc_train": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "nerf_mlp_forward_tc_points": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
 }
 

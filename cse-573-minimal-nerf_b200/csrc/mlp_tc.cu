@@ -50,7 +50,8 @@ template <bool PROFILE>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_rays, const float* __restrict__ d_rays,
               const float* __restrict__ ts, const float* __restrict__ samples, int64_t total, int S,
-              float* __restrict__ sigma_out, float* __restrict__ rgb_out, long long* __restrict__ dbg) {
+              float* __restrict__ sigma_out, float* __restrict__ rgb_out, __nv_bfloat16* __restrict__ act_out,
+              long long* __restrict__ dbg) {
     long long prof[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -300,6 +301,15 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                     p[2 * j + 1] = relu ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
                 }
                 umma::tmem_st16(a_addr, p);
+                // training: keep what the next layer consumes (post-activation bf16), [row][1920] row-major:
+                // mlp.0..feature_fn.4 outputs at 256*layer, rgb_fn.0 output at 1792
+                uint4* act_row = nullptr;
+                if (act_out != nullptr && valid)
+                    act_row = (uint4*)(act_out + row * (int64_t)pk::kActFeatures + (s < 14 ? layer * 256 + nhalf * 128 : 1792) + wh * 64);
+                if (act_row) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) act_row[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 b4 = *(const float4*)(bias + 32 + 4 * j);
@@ -309,6 +319,10 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                     p[2 * j + 1] = relu ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
                 }
                 umma::tmem_st16(a_addr + 16, p);
+                if (act_row) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) act_row[4 + j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+                }
                 umma::tmem_wait_st();
                 umma::tc_fence_before();
                 __syncwarp();
@@ -381,7 +395,8 @@ static bool use_pair_kernel() {
 }
 
 static int launch_mlp_tc(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
-                         int64_t N, int S, float* sigma, float* rgb, void* stream, long long* dbg = nullptr) {
+                         int64_t N, int S, float* sigma, float* rgb, void* stream, long long* dbg = nullptr,
+                         void* act_out = nullptr) {
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_forward_tc: bad size N=%lld S=%d", (long long)N, S);
     if (N == 0) return 0;
     NERF_REQUIRE(packed && d && sigma && rgb, "nerf_mlp_forward_tc: null pointer");
@@ -396,7 +411,8 @@ static int launch_mlp_tc(const void* packed, const float* o, const float* d, con
         attr_set = true;
     }
     const int64_t total = N * S;
-    if (use_pair_kernel()) return launch_mlp_tc2(packed, o, d, ts, samples, total, S, sigma, rgb, stream, dbg);
+    NERF_REQUIRE(!act_out || ((uintptr_t)act_out & 15) == 0, "nerf_mlp_forward_tc: act_out must be 16-byte aligned");
+    if (use_pair_kernel() && !act_out) return launch_mlp_tc2(packed, o, d, ts, samples, total, S, sigma, rgb, stream, dbg);
     const int64_t tiles = (total + tc::kTileM - 1) / tc::kTileM;
     int grid = (int)(tiles < num_sms() ? tiles : num_sms());
     if (dbg) {                                        // diagnostic runs only: NERF_TC_MAX_CTAS limits the grid
@@ -405,10 +421,10 @@ static int launch_mlp_tc(const void* packed, const float* o, const float* d, con
     }
     if (dbg)
         mlp_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, o, d, ts, samples,
-                                                                                        total, S, sigma, rgb, dbg);
+                                                                                        total, S, sigma, rgb, (__nv_bfloat16*)act_out, dbg);
     else
         mlp_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, o, d, ts, samples,
-                                                                                         total, S, sigma, rgb, nullptr);
+                                                                                         total, S, sigma, rgb, (__nv_bfloat16*)act_out, nullptr);
     return check_launch("nerf_mlp_forward_tc");
 }
 
@@ -427,4 +443,12 @@ extern "C" int nerf_mlp_forward_tc(const void* packed, const float* o, const flo
 extern "C" int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
                                           int64_t N, int S, float* sigma, float* rgb, void* stream) {
     return launch_mlp_tc(packed, nullptr, d, nullptr, samples, N, S, sigma, rgb, stream);
+}
+
+// Training form: also writes the bf16 activations every layer consumed, act_out [N*S, 1920] row-major
+// (outputs of mlp.0, mlp.2, mlp.4, mlp.6, feature_fn.0, feature_fn.2, feature_fn.4 at 256*k, rgb_fn.0 at 1792).
+extern "C" int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
+                                         int64_t N, int S, float* sigma, float* rgb, void* act_out, void* stream) {
+    NERF_REQUIRE(N == 0 || act_out, "nerf_mlp_forward_tc_train: act_out is NULL");
+    return launch_mlp_tc(packed, o, d, ts, nullptr, N, S, sigma, rgb, stream, nullptr, act_out);
 }

@@ -48,6 +48,7 @@ struct Layout {
 // feature_fn.4 1536, rgb_fn.0 1792 (128), density_fn.0 1920 (pad 4), rgb_fn.2 1924 (pad 4)
 constexpr int kBiasFloats = 1928;
 constexpr int kBiasR0 = 1792, kBiasSigma = 1920, kBiasRgb = 1924;
+constexpr int kActFeatures = 1920;   // saved bf16 activations per sample (training): 7 x 256 + 128
 
 constexpr Layout make_layout() {
     Layout L{};

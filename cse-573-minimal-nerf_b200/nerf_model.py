@@ -136,28 +136,32 @@ class NeRFNetwork(LightningModule):
         self.last = {}                      # depth / acc / weights of the most recent forward
 
     def forward(self, o_rays, d_rays, rand=None):
-        """rand = (u_c [N,C], eps [N,1], u_f [N,F,1]) replaces the three torch.rand draws when given."""
+        """rand = (u_c [N,C], eps [N,1], u_f [N,F,1]) replaces the three torch.rand draws when given.
+        With gradients enabled the result is differentiable w.r.t. the 40 parameters (training.RenderFunction)."""
+        import training
         o, d = nat.dev(o_rays, "o_rays"), nat.dev(d_rays, "d_rays")
-        N, C, Fn = o.shape[0], self.coarse_samples, self.fine_samples
-        dv = o.device
-        if rand is None:        # the reference's draw order and shapes (nerf_helpers.py:52,139,154)
-            rand = (torch.rand((N, C), device=dv), torch.rand((N, 1), device=dv), torch.rand((N, Fn, 1), device=dv))
-        u_c, eps, u_f = rand
-        c_ts = self._coarse_ts(o, d, u_c)
-        c_sigma, c_rgb = self.coarse_network.forward_rays(o, d, c_ts)
-        c = nerf_helpers.composite(c_sigma, c_rgb, c_ts)
+        params = list(self.parameters())
+        # the differentiable path exists for the fused bf16 tensor-core kernels only; precision="fp32" networks
+        # (tight-parity / odd encoding sizes) always run the inference path and return tensors without a grad_fn
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params) and self.coarse_network.uses_tensor_cores():
+            u_c, eps, u_f = rand if rand is not None else (None, None, None)
+            ordered = self.coarse_network.ordered_params() + self.fine_network.ordered_params()
+            c_rgb, f_rgb = training.RenderFunction.apply(self, o, d, u_c, eps, u_f, *ordered)
+        else:
+            c_rgb, f_rgb, aux = training.forward_pass(self, o, d, rand, save=False)
+            self._publish(aux)
+        return {'fine_rgb_rays': f_rgb, 'coarse_rgb_rays': c_rgb}
+
+    def _publish(self, aux):
+        """The four density statistics the reference logs inside forward (nerf_model.py:105-106,124-125) + extras."""
+        c, f = aux["c"], aux["f"]
         self.log('coarse_density_norms', torch.sqrt(c["stats"][0]), batch_size=1)
         self.log('coarse_density_non_zeros', c["stats"][1], batch_size=1)
-        # near / far are NOT forwarded upstream (nerf_model.py:114-115): the sampler's 2.0 / 6.0 defaults apply
-        _, f_ts = nerf_helpers.inverse_transform_sampling(o, d, c["weights"], c_ts, Fn, rand=(eps, u_f))
-        _, ts = nerf_helpers.merge_samples(o, d, f_ts, c_ts, want_points=False)
-        f_sigma, f_rgb = self.fine_network.forward_rays(o, d, ts)
-        f = nerf_helpers.composite(f_sigma, f_rgb, ts, want_weights=False)
         self.log('fine_density_norms', torch.sqrt(f["stats"][0]), batch_size=1)
         self.log('fine_density_non_zeros', f["stats"][1], batch_size=1)
-        self.last = {"depth": f["depth"], "acc": f["acc"], "ts": ts, "coarse_ts": c_ts, "coarse_weights": c["weights"],
-                     "coarse_sigma": c_sigma, "fine_sigma": f_sigma, "coarse_rgb": c_rgb, "fine_rgb": f_rgb}
-        return {'fine_rgb_rays': f["rgb"], 'coarse_rgb_rays': c["rgb"]}
+        self.last = {"depth": f["depth"], "acc": f["acc"], "ts": aux["ts"], "coarse_ts": aux["c_ts"],
+                     "coarse_weights": c["weights"], "coarse_sigma": aux["c_sigma"], "fine_sigma": aux["f_sigma"],
+                     "coarse_rgb": aux["c_rgb"], "fine_rgb": aux["f_rgb"]}
 
     def _coarse_ts(self, o, d, u_c):
         N, C = u_c.shape

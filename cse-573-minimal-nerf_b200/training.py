@@ -1,0 +1,147 @@
+"""Training path of NeRFNetwork: fused forward that keeps activations + the backward chain.
+
+`RenderFunction` is the autograd node behind `NeRFNetwork.forward` when gradients are enabled.  Forward =
+the same kernels as inference (stratified sampling, fused tcgen05 MLP, compositing, inverse-CDF sampling, merge
+sort) with the MLP launched in its training form, which also stores the bf16 activations every layer consumed
+([samples, 1920] per network).  Backward =
+  * hand-written compositing backward (`nerf_composite_backward`): dL/d ray colour -> dL/d(sigma, rgb) pre-activations
+  * the dgrad / wgrad chain through the 10 Linear layers of each network.  ROUND-1 STATUS: these GEMMs run as bf16
+    cuBLAS calls (`torch.mm(..., out_dtype=float32)`), i.e. library GEMMs, with fp32 accumulation; they are the
+    on-device reference the hand-written tcgen05 dgrad / wgrad kernels (next round) are validated against.
+No gradient flows from the fine loss into the coarse network: the sampler's indices and depths carry none
+(nerf_model.py:114-120), so the two chains are independent.
+"""
+import math
+
+import torch
+
+import _native as nat
+import nerf_helpers
+
+BF = torch.bfloat16
+F32 = torch.float32
+ACT = 1920          # saved activations per sample: outputs of mlp.0/2/4/6, feature_fn.0/2/4 (7 x 256) + rgb_fn.0 (128)
+
+
+def _pe(x, L):
+    import nerf_model
+    return nerf_model.positional_encoding(x, L)
+
+
+def mlp_forward_train(model, o, d, ts):
+    """Fused MLP in training form.  Returns sigma [N,S,1], rgb [N,S,3], acts [N*S, 1920] bf16."""
+    N, S = ts.shape[0], ts.shape[1]
+    sigma = torch.empty((N, S, 1), device=ts.device, dtype=F32)
+    rgb = torch.empty((N, S, 3), device=ts.device, dtype=F32)
+    acts = torch.empty((N * S, ACT), device=ts.device, dtype=BF)
+    packed = model.packed_weights()
+    with nat.timed_kernel("mlp_tc_kernel(train)", N * S):
+        nat.check(nat.lib().nerf_mlp_forward_tc_train(nat.ptr(packed), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S,
+                                                      nat.ptr(sigma), nat.ptr(rgb), nat.ptr(acts), nat.stream()),
+                  "nerf_mlp_forward_tc_train")
+    return sigma, rgb, acts
+
+
+def composite_backward(sigma, rgb, ts, g_ray):
+    N, S = sigma.shape[0], sigma.shape[1]
+    dsig = torch.empty((N * S,), device=sigma.device, dtype=F32)
+    drgb = torch.empty((N * S, 3), device=sigma.device, dtype=F32)
+    g = nat.dev(g_ray, "g_ray")
+    nat.check(nat.lib().nerf_composite_backward(nat.ptr(sigma), nat.ptr(rgb), nat.ptr(ts), nat.ptr(g), N, S,
+                                                nat.ptr(dsig), nat.ptr(drgb), nat.stream()), "nerf_composite_backward")
+    return dsig, drgb
+
+
+def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray):
+    """Gradients of one network's 20 parameters (state_dict order) given dL/d(ray colour) [N,3]."""
+    N, S = ts.shape[0], ts.shape[1]
+    M = N * S
+    dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
+    P = [p.detach() for p in model.ordered_params()]
+    W = [P[2 * i] for i in range(10)]
+    Wb = [w.to(BF) for w in W]
+    h = [acts[:, 256 * k:256 * (k + 1)] for k in range(7)]        # outputs of mlp.0,2,4,6, feature_fn.0,2,4
+    feat, r = h[6], acts[:, 1792:1920]
+    pts = (d[:, None, :] * ts + o[:, None, :]).reshape(M, 3)
+    pe_x = _pe(pts / math.pi, model.position_dim).to(BF)                                    # [M,60]
+    unit = d / torch.linalg.norm(d, dim=1, keepdim=True)
+    pe_d = _pe(unit, model.direction_dim).to(BF).repeat_interleave(S, dim=0)               # [M,24]
+    ones = torch.ones((1, M), device=ts.device, dtype=BF)
+
+    def wgrad(dz, a):                      # dW[out,in] = dz^T a, fp32 accumulate/output
+        return torch.mm(dz.t(), a, out_dtype=F32)
+
+    def bgrad(dz):
+        return torch.mm(ones, dz, out_dtype=F32)[0]
+
+    grads = [None] * 20
+    # rgb_fn.2 (nerf_model.py:358): rgb_pre = r W9^T + b9
+    g9 = drgb.to(BF)
+    grads[18], grads[19] = wgrad(g9, r), drgb.sum(0)
+    dr = torch.mm(g9, Wb[9]) * (r > 0)
+    # rgb_fn.0 (nerf_model.py:356, 387): r_pre = [feat, PE(dir)] W8^T + b8
+    grads[16], grads[17] = torch.cat([wgrad(dr, feat), wgrad(dr, pe_d)], dim=1), bgrad(dr)
+    dfeat = torch.mm(dr, Wb[8][:, :256])
+    # density_fn.0 (nerf_model.py:351, 385): sigma_pre = feat W7^T + b7
+    gs = dsig.to(BF)[:, None]
+    grads[14], grads[15] = wgrad(gs, feat), dsig.sum().reshape(1)
+    dz = dfeat + gs * Wb[7]
+    # feature_fn.4 (linear), feature_fn.2, feature_fn.0 (input = [h3, PE(x)]), mlp.6, mlp.4, mlp.2, mlp.0
+    for li in (6, 5, 4, 3, 2, 1):
+        a = h[li - 1]
+        if li == 4:
+            grads[8], grads[9] = torch.cat([wgrad(dz, a), wgrad(dz, pe_x)], dim=1), bgrad(dz)
+            dz = torch.mm(dz, Wb[4][:, :256]) * (a > 0)
+        else:
+            grads[2 * li], grads[2 * li + 1] = wgrad(dz, a), bgrad(dz)
+            dz = torch.mm(dz, Wb[li]) * (a > 0)
+    grads[0], grads[1] = wgrad(dz, pe_x), bgrad(dz)
+    return grads
+
+
+def forward_pass(net, o, d, rand, save):
+    """Shared by inference and training: returns (coarse_rgb, fine_rgb, aux dict)."""
+    N, C, Fn = o.shape[0], net.coarse_samples, net.fine_samples
+    dv = o.device
+    if rand is None:        # the reference's draw order and shapes (nerf_helpers.py:52,139,154)
+        rand = (torch.rand((N, C), device=dv), torch.rand((N, 1), device=dv), torch.rand((N, Fn, 1), device=dv))
+    u_c, eps, u_f = rand
+    c_ts = net._coarse_ts(o, d, u_c)
+    if save:
+        c_sigma, c_rgb, c_acts = mlp_forward_train(net.coarse_network, o, d, c_ts)
+    else:
+        c_sigma, c_rgb = net.coarse_network.forward_rays(o, d, c_ts)
+        c_acts = None
+    c = nerf_helpers.composite(c_sigma, c_rgb, c_ts)
+    # near / far are NOT forwarded upstream (nerf_model.py:114-115): the sampler's 2.0 / 6.0 defaults apply
+    _, f_ts = nerf_helpers.inverse_transform_sampling(o, d, c["weights"], c_ts, Fn, rand=(eps, u_f))
+    _, ts = nerf_helpers.merge_samples(o, d, f_ts, c_ts, want_points=False)
+    if save:
+        f_sigma, f_rgb, f_acts = mlp_forward_train(net.fine_network, o, d, ts)
+    else:
+        f_sigma, f_rgb = net.fine_network.forward_rays(o, d, ts)
+        f_acts = None
+    f = nerf_helpers.composite(f_sigma, f_rgb, ts, want_weights=False)
+    aux = {"c": c, "f": f, "c_ts": c_ts, "ts": ts, "c_sigma": c_sigma, "c_rgb": c_rgb, "f_sigma": f_sigma, "f_rgb": f_rgb,
+           "c_acts": c_acts, "f_acts": f_acts}
+    return c["rgb"], f["rgb"], aux
+
+
+class RenderFunction(torch.autograd.Function):
+    """(o, d, u_c, eps, u_f, *40 parameters) -> (coarse_rgb_rays [N,3], fine_rgb_rays [N,3])."""
+
+    @staticmethod
+    def forward(ctx, net, o, d, u_c, eps, u_f, *params):
+        rand = None if u_c is None else (u_c, eps, u_f)
+        c_rgb, f_rgb, aux = forward_pass(net, o, d, rand, save=True)
+        ctx.net, ctx.o, ctx.d, ctx.aux = net, o, d, aux
+        net._publish(aux)
+        return c_rgb, f_rgb
+
+    @staticmethod
+    def backward(ctx, g_c, g_f):
+        net, o, d, a = ctx.net, ctx.o, ctx.d, ctx.aux
+        gc = mlp_backward(net.coarse_network, o, d, a["c_ts"], a["c_sigma"], a["c_rgb"], a["c_acts"], g_c.contiguous())
+        gf = mlp_backward(net.fine_network, o, d, a["ts"], a["f_sigma"], a["f_rgb"], a["f_acts"], g_f.contiguous())
+        ctx.aux = None
+        return (None,) * 6 + tuple(gc) + tuple(gf)

@@ -65,6 +65,12 @@ int nerf_composite(const float* sigma, const float* rgb, const float* ts, int64_
                    float* deltas, float* weights, float* ray_rgb, float* depth, float* acc,
                    float* stats2, void* stream);
 
+/* ---- backward of H2+H3+H4 (training; autograd of nerf_model.py:109-111 / :128-130).  g_ray [N,3] = dL/d ray_rgb.
+ * Outputs are the gradients w.r.t. the head PRE-activations (ReLU / sigmoid derivatives of nerf_model.py:352,359
+ * folded in): dsigma_pre [N,S], drgb_pre [N,S,3]. */
+int nerf_composite_backward(const float* sigma, const float* rgb, const float* ts, const float* g_ray, int64_t N, int S,
+                            float* dsigma_pre, float* drgb_pre, void* stream);
+
 /* ---- H5: inverse-CDF fine sampling.  nerf_helpers.py:106-156.
  * w, ts: [N,C] coarse weights and depths.  eps: [N] and u: [N,F] raw uniforms.  q_base: [F] query grid
  * (the reference's torch.arange(0, 1, 1/F), evaluated by the host).  cdf = sequential fp32 cumsum / last;
@@ -104,6 +110,10 @@ int nerf_pack_weights(const float* const* params20_host, void* packed, void* str
  * Samples are given as rays + depths: sample (n,s) sits at o[n] + ts[n,s]*d[n].  sigma [N,S], rgb [N,S,3]. */
 int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, const float* ts,
                         int64_t N, int S, float* sigma, float* rgb, void* stream);
+/* Training form: also stores the bf16 activations each layer consumed, act_out [N*S, 1920] row-major (outputs of
+ * mlp.0, mlp.2, mlp.4, mlp.6, feature_fn.0, feature_fn.2, feature_fn.4 at column 256*k; rgb_fn.0 at 1792). */
+int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
+                              int64_t N, int S, float* sigma, float* rgb, void* act_out, void* stream);
 /* Same kernel with explicit sample points [N,S,3] (the NeRFModel.forward(samples, direc) call surface). */
 int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
                                int64_t N, int S, float* sigma, float* rgb, void* stream);
