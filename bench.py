@@ -169,6 +169,65 @@ def cpu_baseline(args):
                       f"{os.cpu_count()} threads"}
 
 
+TRAIN_FLOP_PER_SAMPLE = 2 * (460416 + 460416 + 426624)     # fwd + wgrad + needed dgrad
+
+
+def bench_train(args, rank, world, dev):
+    """BASELINE.json configs[2]/[3]: training steps on 4096-ray batches (per GPU), random-init coarse + fine MLP, Adam;
+    data-parallel across ranks with one all-reduce of the flat gradient buffer per step."""
+    import torch.distributed as dist
+    import dataloader
+    import nerf_model
+    import synthetic
+    from trainer import FlatGradients
+    torch.manual_seed(1234 + rank)
+    net = nerf_model.NeRFNetwork()
+    net.load_state_dict(synthetic.make_state_dict(0, "init"))
+    net = net.to(dev)
+    opt = net.configure_optimizers()["optimizer"]
+    grads = FlatGradients(net.parameters())
+    H = W = 800
+    c2w, focal = frame_setup(H, W, 7 * rank + 3)
+    image = torch.from_numpy(synthetic.analytic_scene_rgba(c2w.numpy(), H, W, focal)[..., :3].copy()).to(dev)
+    n = CHUNK
+
+    def step():
+        xs, ys = dataloader.sample_random_coordinates(n, H, W, device=dev)
+        o, d = dataloader.get_rays_at(H, W, focal, c2w, xs, ys)
+        rgb = image[ys, xs].float() / 255.0
+        grads.zero()
+        loss = net.training_step({"origin": o[None], "direc": d[None], "rgb": rgb[None]}, 0)
+        loss.backward()
+        grads.all_reduce_mean()
+        opt.step()
+        return loss
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(args.steps, 1) * 4
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        loss = step()
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    pk = peaks()
+    tfl = n * 256 * TRAIN_FLOP_PER_SAMPLE / (ms * 1e-3) / 1e12
+    return {"metric": "rays/sec train (device-timed)", "value": n * world / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
+            "steps": steps, "rays_per_step_per_gpu": n, "final_loss": float(loss),
+            "algorithmic_tflops_per_gpu": tfl, "frac_of_sustained_peak": tfl / pk["tflops_sustained"],
+            "backward": "compositing backward hand-written; dgrad/wgrad GEMMs via cuBLAS bf16 (round-1 interim)",
+            "collective": "one NCCL all-reduce of the 924 680-float flat gradient buffer per step" if world > 1 else None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -297,6 +356,8 @@ def main():
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     e2e_value = nrays * world / (float(e_ms.item()) * 1e-3)
 
+    train = bench_train(args, rank, world, dev)
+
     if rank == 0:
         line = {
             "metric": "rays/sec render (device-timed)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -304,7 +365,7 @@ def main():
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(host_o.numel() * 4 * 2),
                     "d2h_bytes_per_step": int(host_im.numel()), "ms_per_step": float(e_ms.item())},
-            "gpu_launches": launches, "roofline": roofline, "clocks": clocks.summary(),
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks.summary(), "train": train,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)

@@ -158,16 +158,20 @@ def generate_360_view_synthesis(model, save_dir: Path, epoch, height=800, width=
 
 
 def view_reconstruction(model, all_o_rays, all_d_rays, N=4096):
-    """Render every ray of an [H,W,3] ray grid through `model` in chunks of N; returns uint8 [H,W,3]."""
-    H, W, C = all_o_rays.shape
-    o = nat.dev(all_o_rays, "all_o_rays").reshape(H * W, C)
-    d = nat.dev(all_d_rays, "all_d_rays").reshape(H * W, C)
-    out = torch.empty((H * W, 3), device=o.device, dtype=torch.float32)
-    with torch.no_grad():
-        for i in range(0, H * W, N):
-            out[i:i + N] = model.forward(o[i:i + N], d[i:i + N])['fine_rgb_rays']
-    im = (out * 255).clamp_(0, 255).to(torch.uint8)          # truncation, as numpy's astype(uint8)
-    return im.reshape(H, W, C).cpu().numpy()
+    """Render every ray of an [H,W,3] ray grid through `model` in chunks of N; returns uint8 [H,W,3].
+    Under torch.distributed (one process per GPU) every rank renders a contiguous slab of the rays and the uint8
+    slabs are all-gathered, so each rank returns the whole image."""
+    import multi_gpu
+    o_all, d_all = nat.dev(all_o_rays, "all_o_rays"), nat.dev(all_d_rays, "all_d_rays")
+
+    def render_rays(o, d):
+        out = torch.empty((o.shape[0], 3), device=o.device, dtype=torch.float32)
+        with torch.no_grad():
+            for i in range(0, o.shape[0], N):
+                out[i:i + N] = model.forward(o[i:i + N], d[i:i + N])['fine_rgb_rays']
+        return out
+    # (x * 255).clamp(0, 255).to(uint8) truncates like numpy's astype(uint8) upstream (nerf_helpers.py:207-210)
+    return multi_gpu.sharded_render(render_rays, o_all, d_all).cpu().numpy()
 
 
 def torch_to_numpy(torch_tensor, is_normalized_image=False):
