@@ -222,7 +222,7 @@ def bench_train(args, rank, world, dev):
     pk = peaks()
     tfl = n * 256 * TRAIN_FLOP_PER_SAMPLE / (ms * 1e-3) / 1e12
     return {"metric": "rays/sec train (device-timed)", "value": n * world / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
-            "steps": steps, "rays_per_step_per_gpu": n, "final_loss": float(loss),
+            "steps": steps, "rays_per_step_per_gpu": n, "final_loss": float(loss.detach()),
             "algorithmic_tflops_per_gpu": tfl, "frac_of_sustained_peak": tfl / pk["tflops_sustained"],
             "backward": "compositing backward hand-written; dgrad/wgrad GEMMs via cuBLAS bf16 (round-1 interim)",
             "collective": "one NCCL all-reduce of the 924 680-float flat gradient buffer per step" if world > 1 else None}
@@ -247,6 +247,7 @@ def main():
         return
 
     import torch.distributed as dist
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
