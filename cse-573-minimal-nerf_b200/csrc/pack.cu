@@ -7,6 +7,7 @@
 namespace nerf {
 
 __constant__ pk::Layout c_pack_layout = pk::kLayout;
+__constant__ pk::LayoutT c_pack_layout_t = pk::kLayoutT;
 
 struct PackParams { const float* p[20]; };
 
@@ -36,9 +37,42 @@ pack_weights_kernel(PackParams P, uint8_t* __restrict__ packed) {
     }
 }
 
+__global__ void __launch_bounds__(256)
+pack_weights_t_kernel(PackParams P, uint8_t* __restrict__ packed) {
+    const int s = blockIdx.x;
+    if (s < pk::kStagesT) {
+        const pk::Stage st = c_pack_layout_t.st[s];
+        const float* W = P.p[2 * st.param];
+        uint8_t* tile = packed + st.offset;
+        for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
+            const int k = e >> 7, r = e & 127;          // consecutive threads walk r: coalesced reads of W rows
+            const float v = W[(size_t)(st.k0 + k) * st.in_features + st.n0 + r];
+            *(__nv_bfloat16*)(tile + umma::sw128_offset(r, k)) = __float2bfloat16_rn(v);
+        }
+    } else {
+        float* c = (float*)(packed + c_pack_layout_t.const_offset);
+        for (int i = threadIdx.x; i < pk::kConstFloatsT; i += blockDim.x)
+            c[i] = (i < 384) ? P.p[18][i] : P.p[14][i - 384];      // rgb_fn.2.weight [3,128], density_fn.0.weight [1,256]
+    }
+}
+
 }  // namespace nerf
 
 using namespace nerf;
+
+extern "C" size_t nerf_packed_t_bytes(void) { return pk::kLayoutT.total_bytes; }
+
+extern "C" int nerf_pack_weights_t(const float* const* params20_host, void* packed_t, void* stream) {
+    NERF_REQUIRE(params20_host && packed_t, "nerf_pack_weights_t: null pointer");
+    NERF_REQUIRE(((uintptr_t)packed_t & 127) == 0, "nerf_pack_weights_t: buffer must be 128-byte aligned");
+    PackParams P;
+    for (int i = 0; i < 20; ++i) {
+        NERF_REQUIRE(params20_host[i], "nerf_pack_weights_t: params20_host[%d] is NULL", i);
+        P.p[i] = params20_host[i];
+    }
+    pack_weights_t_kernel<<<pk::kStagesT + 1, 256, 0, (cudaStream_t)stream>>>(P, (uint8_t*)packed_t);
+    return check_launch("nerf_pack_weights_t");
+}
 
 extern "C" size_t nerf_packed_bytes(void) { return pk::kLayout.total_bytes; }
 

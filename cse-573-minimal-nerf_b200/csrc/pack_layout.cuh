@@ -35,6 +35,7 @@ struct Stage {
     uint16_t k0;       // first input column of W in this tile
     uint16_t in_features;
     uint32_t offset;   // byte offset inside the packed buffer
+    uint8_t transposed;  // 0: tile[r][k] = W[n0+r][k0+k] (forward);  1: tile[r][k] = W[k0+k][n0+r] (dgrad: B = W^T)
 };
 
 struct Layout {
@@ -84,6 +85,44 @@ constexpr Layout make_layout() {
 
 constexpr Layout kLayout = make_layout();
 static_assert(kLayout.weight_bytes == 57u * kStageBytesFull + 6u * kStageBytesSmall, "stage accounting");
+
+
+// ---- backward (dgrad) image: B = W^T stages in the order mlp_tc_bwd.cu consumes them, then two fp32 constant blocks
+//   steps 0,1   rgb_fn.0 dgrad   d feat[:, 128h:128h+128] = dr[128 x K=128] . W8[:, 128h:...]      2 stages per half
+//   steps 2..13 feature_fn.4, feature_fn.2, feature_fn.0 (h part), mlp.6, mlp.4, mlp.2              4 stages per half
+constexpr int kStagesT = 52;
+struct LayoutT {
+    Stage st[kStagesT];
+    uint32_t weight_bytes;
+    uint32_t const_offset;   // fp32: rgb_fn.2.weight [3,128] (384 floats) then density_fn.0.weight [256]
+    uint32_t total_bytes;
+};
+constexpr int kConstFloatsT = 640;
+
+constexpr LayoutT make_layout_t() {
+    LayoutT L{};
+    int s = 0;
+    uint32_t off = 0;
+    auto add = [&](int param, int kin0, int nout0, int in_features) {
+        L.st[s].param = (uint8_t)param; L.st[s].rows = 128; L.st[s].valid_rows = 128; L.st[s].kvalid = 64;
+        L.st[s].n0 = (uint16_t)kin0; L.st[s].k0 = (uint16_t)nout0; L.st[s].in_features = (uint16_t)in_features;
+        L.st[s].offset = off; L.st[s].transposed = 1;
+        off += 128u * 128u;
+        ++s;
+    };
+    for (int h = 0; h < 2; ++h)
+        for (int kb = 0; kb < 2; ++kb) add(8, 128 * h, 64 * kb, 280);                        // rgb_fn.0
+    const int order[6] = {6, 5, 4, 3, 2, 1};                                                 // feature_fn.4 ... mlp.2
+    for (int i = 0; i < 6; ++i)
+        for (int h = 0; h < 2; ++h)
+            for (int kb = 0; kb < 4; ++kb) add(order[i], 128 * h, 64 * kb, order[i] == 4 ? 316 : 256);
+    L.weight_bytes = off;
+    L.const_offset = off;
+    L.total_bytes = off + kConstFloatsT * 4u;
+    return L;
+}
+constexpr LayoutT kLayoutT = make_layout_t();
+static_assert(kLayoutT.weight_bytes == 52u * kStageBytesFull, "backward stage accounting");
 
 }  // namespace pk
 }  // namespace nerf

@@ -57,6 +57,8 @@ class NeRFModel(nn.Module):
         self.rgb_fn = nn.Sequential(nn.Linear(256 + de, 128), ACT_FN, nn.Linear(128, 3), nn.Sigmoid())
         self._packed = None
         self._packed_key = None
+        self._packed_t = None
+        self._packed_t_key = None
 
     # ---- parameter plumbing
     def ordered_params(self):
@@ -87,6 +89,18 @@ class NeRFModel(nn.Module):
             nat.check(nat.lib().nerf_pack_weights(arr, nat.ptr(self._packed), nat.stream()), "nerf_pack_weights")
             self._packed_key = key
         return self._packed
+
+    def packed_weights_t(self):
+        """W^T stage image for the tcgen05 dgrad kernel (training); re-packed whenever a parameter changed."""
+        params = self.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed_t is None or self._packed_t_key != key or self._packed_t.device != params[0].device:
+            arr, keep = self._param_ptrs()
+            if self._packed_t is None or self._packed_t.device != params[0].device:
+                self._packed_t = torch.empty(nat.lib().nerf_packed_t_bytes(), dtype=torch.uint8, device=params[0].device)
+            nat.check(nat.lib().nerf_pack_weights_t(arr, nat.ptr(self._packed_t), nat.stream()), "nerf_pack_weights_t")
+            self._packed_t_key = key
+        return self._packed_t
 
     # ---- forward
     def forward(self, samples, direc):

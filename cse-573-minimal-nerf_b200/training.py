@@ -53,7 +53,53 @@ def composite_backward(sigma, rgb, ts, g_ray):
 
 
 def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray):
-    """Gradients of one network's 20 parameters (state_dict order) given dL/d(ray colour) [N,3]."""
+    """Gradients of one network's 20 parameters (state_dict order) given dL/d(ray colour) [N,3].
+    dgrad chain: hand-written tcgen05 kernel (mlp_tc_bwd.cu).  wgrad: dz^T . (layer input) as bf16 cuBLAS GEMMs with
+    fp32 output (round-1 interim), all 8 hidden bias gradients as one ones-vector GEMV over dz."""
+    N, S = ts.shape[0], ts.shape[1]
+    M = N * S
+    dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
+    dz = torch.empty((M, ACT), device=ts.device, dtype=BF)
+    with nat.timed_kernel("mlp_tc_bwd_kernel", M):
+        nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(acts), nat.ptr(dsig), nat.ptr(drgb),
+                                                 N, S, nat.ptr(dz), nat.stream()), "nerf_mlp_backward_tc")
+    feat, r, dr = acts[:, 1536:1792], acts[:, 1792:1920], dz[:, 1792:1920]
+    pts = (d[:, None, :] * ts + o[:, None, :]).reshape(M, 3)
+    pe, de = 6 * model.position_dim, 6 * model.direction_dim
+    # PE operands padded to 64 / 32 columns so the library picks aligned tensor-core kernels
+    pe_x = torch.zeros((M, 64), device=ts.device, dtype=BF)
+    pe_x[:, :pe] = _pe(pts / math.pi, model.position_dim)
+    unit = d / torch.linalg.norm(d, dim=1, keepdim=True)
+    pe_d = torch.zeros((N, 32), device=ts.device, dtype=BF)
+    pe_d[:, :de] = _pe(unit, model.direction_dim)
+    pe_d = pe_d.repeat_interleave(S, dim=0)                                                 # [M,32]
+
+    def wgrad(g, a):
+        return torch.mm(g.t(), a, out_dtype=F32)
+    # bias gradients of the 8 hidden layers + density row in ONE GEMM: [ones; dsig]^T-style 16-row left operand
+    left = torch.zeros((16, M), device=ts.device, dtype=BF)
+    left[0] = 1.0
+    left[1] = dsig
+    red = torch.mm(left, acts.new_empty(0) if False else dz, out_dtype=F32)                 # row 0: column sums of dz
+    bsum = red[0]
+    grads = [None] * 20
+    grads[0], grads[1] = wgrad(dz[:, 0:256], pe_x)[:, :pe], bsum[0:256]                     # mlp.0
+    for li in (1, 2, 3, 5, 6):                                                              # mlp.2/4/6, feature_fn.2/4
+        grads[2 * li], grads[2 * li + 1] = wgrad(dz[:, 256 * li:256 * li + 256], acts[:, 256 * (li - 1):256 * li]), \
+            bsum[256 * li:256 * li + 256]
+    dz4 = dz[:, 1024:1280]                                                                  # feature_fn.0: input [h3, PE(x)]
+    grads[8], grads[9] = torch.cat([wgrad(dz4, acts[:, 768:1024]), wgrad(dz4, pe_x)[:, :pe]], dim=1), bsum[1024:1280]
+    grads[14], grads[15] = torch.mm(left, feat, out_dtype=F32)[1:2], dsig.sum().reshape(1)  # density_fn.0
+    grads[16], grads[17] = torch.cat([wgrad(dr, feat), wgrad(dr, pe_d)[:, :de]], dim=1), bsum[1792:1920]   # rgb_fn.0
+    g9 = torch.zeros((M, 16), device=ts.device, dtype=BF)
+    g9[:, :3] = drgb
+    grads[18], grads[19] = wgrad(g9, r)[:3], drgb.sum(0)                                    # rgb_fn.2
+    return grads
+
+
+def mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray):
+    """The same gradients with the whole chain as library GEMMs + elementwise torch ops: on-device reference for the
+    hand-written dgrad kernel (tests/test_gpu_training.py)."""
     N, S = ts.shape[0], ts.shape[1]
     M = N * S
     dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)

@@ -114,6 +114,14 @@ int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, cons
  * mlp.0, mlp.2, mlp.4, mlp.6, feature_fn.0, feature_fn.2, feature_fn.4 at column 256*k; rgb_fn.0 at 1792). */
 int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
                               int64_t N, int S, float* sigma, float* rgb, void* act_out, void* stream);
+/* ---- backward of H8 (dgrad chain) on the tensor cores.  packed_t = nerf_pack_weights_t image (W^T stages, bf16).
+ * acts: the forward's saved activations [N*S,1920]; dsigma_pre [N*S], drgb_pre [N*S,3] from nerf_composite_backward.
+ * dz_out [N*S,1920] bf16: gradient w.r.t. every layer's pre-activation, same column map as acts
+ * (mlp.0 .. feature_fn.4 at 256*k, rgb_fn.0 at 1792); the weight gradients are dz^T . (layer input). */
+size_t nerf_packed_t_bytes(void);
+int nerf_pack_weights_t(const float* const* params20_host, void* packed_t, void* stream);
+int nerf_mlp_backward_tc(const void* packed_t, const void* acts, const float* dsigma_pre, const float* drgb_pre,
+                         int64_t N, int S, void* dz_out, void* stream);
 /* Same kernel with explicit sample points [N,S,3] (the NeRFModel.forward(samples, direc) call surface). */
 int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
                                int64_t N, int S, float* sigma, float* rgb, void* stream);

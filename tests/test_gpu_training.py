@@ -107,3 +107,27 @@ def test_short_optimisation_reduces_loss():
         losses.append(loss.item())
     print("loss trajectory:", " ".join(f"{l:.4f}" for l in losses[::5]), f"-> {losses[-1]:.4f}")
     assert np.isfinite(losses).all() and losses[-1] < 0.7 * losses[0]
+
+
+def test_dgrad_kernel_matches_library_chain():
+    """Hand-written tcgen05 dgrad chain vs the same chain as cuBLAS GEMMs + elementwise ops, several tiles per CTA and a
+    ragged last tile: all 20 gradients of one network."""
+    import training
+    torch.manual_seed(1)
+    net = make_net(4, "dense")
+    N, S = 700, 67                                        # 46 900 samples = 366.4 tiles
+    o = torch.randn(N, 3, device=DEV) * 0.3
+    d = F.normalize(torch.randn(N, 3, device=DEV), dim=1) * 1.05
+    ts = (2.0 + 4.0 * torch.sort(torch.rand(N, S, 1, device=DEV), dim=1).values).contiguous()
+    model = net.fine_network
+    sigma, rgb, acts = training.mlp_forward_train(model, o, d, ts)
+    g_ray = torch.randn(N, 3, device=DEV) / N
+    got = training.mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray)
+    ref = training.mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray)
+    torch.cuda.synchronize()
+    names = [n for n, _ in model.named_parameters()]
+    for name, a, b in zip(names, got, ref):
+        a, b = a.float().flatten(), b.float().flatten()
+        cos = F.cosine_similarity(a, b, dim=0).item()
+        rel = ((a - b).norm() / b.norm().clamp(min=1e-20)).item()
+        assert cos > 0.999 and rel < 0.03, f"{name}: cosine {cos:.5f} rel {rel:.4f}"

@@ -41,9 +41,10 @@ ms = t0.elapsed_time(t1)
 c = dbg.double().cpu()[:G]
 tiles = c[:, 8].clamp(min=1)
 names = ["mma_total", "mma_wait_full(weights)", "mma_wait_edone(epilogue)", "mma_wait_pe", "producer_wait_empty", "epi_total",
-         "epi_wait_dfull", "epi_pe_time"]
+         "epi_wait_dfull", "epi_pe_time", "tiles", "epi_seg_ld+wait", "epi_seg_math1", "epi_seg_wait_st", "epi_seg_fence+arrive", "epi_seg_st1", "epi_seg_math2(+act store)", "epi_seg_st2"]
 print(f"N={N} S={S}: {ms:.3f} ms, {N*S*920832/ms/1e9:.1f} TFLOP/s, tiles/CTA {tiles.mean():.1f}")
 for i, n in enumerate(names):
+    if i == 8: continue
     per_tile = (c[:, i] / tiles)
     print(f"  {n:28s} per tile: mean {per_tile.mean():9.0f} clk  min {per_tile.min():9.0f}  max {per_tile.max():9.0f}")
 print("  (tensor-pipe floor per tile: 14.7k clk)")
