@@ -3,9 +3,11 @@
 // 5th-gen tensor cores (tcgen05.mma, cta_group::1, M = 128 samples per tile), fp32 accumulation in TMEM.
 //
 // Per CTA (one per SM, persistent over 128-sample tiles):
-//   warp 0      weight producer: streams the 63 pre-swizzled [rows x 64] bf16 weight stages of the network
-//               (pack_layout.cuh) through an 11-slot shared-memory ring with cp.async.bulk (TMA engine),
-//               full/empty mbarriers.  The stream is ~0.92 MB per tile and stays L2-resident.
+//   warps 0,3   weight producers: stream the network's pre-swizzled bf16 weight image (pack_layout.cuh; 0.92 MB per
+//               tile, L2-resident) through a 4-slot x 32 KB shared-memory ring with cp.async.bulk (TMA engine),
+//               full/empty mbarriers.  K-blocks consumed back to back travel as ONE copy of up to 32 KB and the two
+//               warps alternate stages: the copy engine retires ~one request per 550 clk per issuing lane whatever its
+//               size, so 16 KB requests from one lane capped the stream at ~30 B/clk/SM (measured).
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma.  Hidden activations never touch shared
 //               memory: they live in TMEM as the A operand (bf16 pairs, lane = sample); only PE(x) / PE(dir)
 //               come from swizzled shared-memory tiles (skip concat = one extra K block accumulated into the
@@ -27,8 +29,9 @@ namespace nerf {
 
 namespace tc {
 constexpr int kTileM = 128;
-constexpr int kSlots = 9;
-constexpr int kThreads = 512;          // warp 0 producer, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue, 12-15 PE
+constexpr int kSlots = 4;
+constexpr uint32_t kSlotBytes = 32768;
+constexpr int kThreads = 512;          // warps 0,3 weight producers, 1 MMA, 2 TMEM alloc, 4-11 epilogue, 12-15 PE
 constexpr int kEpiWarps = 8;
 constexpr int kPEWarps = 4;
 constexpr uint32_t kColD = 0, kColA0 = 256, kColA1 = 384;
@@ -37,7 +40,7 @@ constexpr uint32_t kColD = 0, kColA0 = 256, kColA1 = 384;
 constexpr uint32_t kOffPE = 0;             // 2 x [128 x 64] bf16 PE(x) tiles (double buffered across tiles)
 constexpr uint32_t kOffPEDir = 32768;      // 2 x [128 x 64] bf16 PE(dir) tiles
 constexpr uint32_t kOffRing = 65536;
-constexpr uint32_t kOffBias = kOffRing + kSlots * 16384;
+constexpr uint32_t kOffBias = kOffRing + kSlots * kSlotBytes;
 constexpr uint32_t kOffBars = kOffBias + ((pk::kBiasFloats * 4 + 15) / 16) * 16;
 constexpr uint32_t kNumBars = 2 * kSlots + 8;
 constexpr uint32_t kOffTmemHolder = kOffBars + kNumBars * 8;
@@ -89,25 +92,28 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ weight producer (warp-uniform, one lane issues)
+    if (warp == 0 || warp == 3) {
+        // ------------------------------------------------------------------ weight producers: two warps alternate the merged
+        // stages so that two bulk copies are always in flight (one issuing lane sustains only ~1 request / 550 clk)
         const bool leader = umma::elect_one();
+        const uint32_t me = (warp == 0) ? 0u : 1u;
         uint32_t cnt = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int s = 0; s < pk::kStages; ++s, ++cnt) {
+            for (int s = 0; s < kMergedStages; ++s, ++cnt) {
+                if ((cnt & 1u) != me) continue;
                 const uint32_t slot = cnt % tc::kSlots, ph = (cnt / tc::kSlots) & 1;
                 NERF_PROF_BEGIN(tw)
                 umma::mbar_wait(&empty[slot], ph ^ 1);
                 NERF_PROF_END(tw, 4)
                 if (leader) {
-                    const StageRef st = c_stages.s[s];
+                    const StageRef st = c_merged.s[s];
                     umma::mbar_arrive_expect_tx(&full[slot], st.bytes);
-                    umma::bulk_g2s(sRing + slot * 16384, packed + st.offset, st.bytes, &full[slot]);
+                    umma::bulk_g2s(sRing + slot * tc::kSlotBytes, packed + st.offset, st.bytes, &full[slot]);
                 }
                 __syncwarp();
             }
         }
-        if (PROFILE && lane == 0) dbg[blockIdx.x * 16 + 4] = prof[4];
+        if (PROFILE && lane == 0 && warp == 0) dbg[blockIdx.x * 16 + 4] = prof[4];
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
         const bool leader = umma::elect_one();
@@ -128,19 +134,26 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
             NERF_PROF_END(tw, 2)
             umma::tc_fence_after();
         };
-        // one K=64 weight stage: nk16 K=16 slices; A from TMEM columns (a_col >= 0) or from a smem tile
-        auto kblock = [&](uint32_t d_col, int a_col, uint64_t a_desc, uint32_t idesc, int nk16, uint32_t& acc) {
+        // one merged weight stage = nkb K=64 blocks ([rows x 64] tiles of tile_bytes each, back to back in the slot), nk16
+        // K=16 slices per block; A from TMEM columns (a_col >= 0, 32 columns per block) or from a smem tile (1 block)
+        auto stage = [&](uint32_t d_col, int a_col, uint64_t a_desc, uint32_t idesc, int nkb, uint32_t tile_bytes, int nk16,
+                         uint32_t& acc) {
             const uint32_t slot = cnt % tc::kSlots, ph = (cnt / tc::kSlots) & 1;
             NERF_PROF_BEGIN(tw)
             umma::mbar_wait(&full[slot], ph);
             NERF_PROF_END(tw, 1)
             umma::tc_fence_after();
             if (leader) {
-                const uint64_t bdesc = umma::make_desc_k_sw128(umma::smem_u32(sRing + slot * 16384));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint64_t bdesc = umma::make_desc_k_sw128(umma::smem_u32(sRing + slot * tc::kSlotBytes + kb * tile_bytes));
 #pragma unroll 4
-                for (int k = 0; k < nk16; ++k) {
-                    if (a_col >= 0) umma::mma_ts(tmem + d_col, tmem + (uint32_t)a_col + 8u * k, bdesc + 2u * k, idesc, acc | (uint32_t)k);
-                    else            umma::mma_ss(tmem + d_col, a_desc + 2u * k, bdesc + 2u * k, idesc, acc | (uint32_t)k);
+                    for (int k = 0; k < nk16; ++k) {
+                        if (a_col >= 0)
+                            umma::mma_ts(tmem + d_col, tmem + (uint32_t)a_col + 32u * kb + 8u * k, bdesc + 2u * k, idesc,
+                                         acc | (uint32_t)(kb | k));
+                        else
+                            umma::mma_ss(tmem + d_col, a_desc + 2u * k, bdesc + 2u * k, idesc, acc | (uint32_t)k);
+                    }
                 }
                 umma::mma_commit(&empty[slot]);
             }
@@ -154,12 +167,10 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                 const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
                 uint32_t acc = 0;
                 ensure_e(gs - 2);
-                if (pe_first) kblock(d_col, -1, descPE, kI128, 4, acc);
-                kblock(d_col, a_base + 0, 0, kI128, 4, acc);
-                kblock(d_col, a_base + 32, 0, kI128, 4, acc);
+                if (pe_first) stage(d_col, -1, descPE, kI128, 1, 16384, 4, acc);
+                stage(d_col, a_base + 0, 0, kI128, 2, 16384, 4, acc);
                 if (h == 0) ensure_e(gs - 1);
-                kblock(d_col, a_base + 64, 0, kI128, 4, acc);
-                kblock(d_col, a_base + 96, 0, kI128, 4, acc);
+                stage(d_col, a_base + 64, 0, kI128, 2, 16384, 4, acc);
                 if (leader) umma::mma_commit(&dfull[gs & 1]);
                 __syncwarp();
                 ++gs;
@@ -177,7 +188,7 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
             for (int h = 0; h < 2; ++h) {                                   // mlp.0: A = PE(x) tile
                 uint32_t acc = 0;
                 ensure_e(gs - 2);
-                kblock(tc::kColD + 128u * (uint32_t)(gs & 1), -1, descPE, kI128, 4, acc);
+                stage(tc::kColD + 128u * (uint32_t)(gs & 1), -1, descPE, kI128, 1, 16384, 4, acc);
                 if (leader) umma::mma_commit(&dfull[gs & 1]);
                 __syncwarp();
                 ++gs;
@@ -192,14 +203,12 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                 const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
                 uint32_t acc = 0;
                 ensure_e(gs - 2);
-                kblock(d_col, -1, descPEDir, kI128, 2, acc);
+                stage(d_col, -1, descPEDir, kI128, 1, 16384, 2, acc);
                 if (leader) umma::mma_commit(&pe_empty[pb]);      // last read of this tile's PE buffers
                 __syncwarp();
-                kblock(d_col, tc::kColA0 + 0, 0, kI128, 4, acc);
-                kblock(d_col, tc::kColA0 + 32, 0, kI128, 4, acc);
+                stage(d_col, tc::kColA0 + 0, 0, kI128, 2, 16384, 4, acc);
                 ensure_e(gs - 1);
-                kblock(d_col, tc::kColA0 + 64, 0, kI128, 4, acc);
-                kblock(d_col, tc::kColA0 + 96, 0, kI128, 4, acc);
+                stage(d_col, tc::kColA0 + 64, 0, kI128, 2, 16384, 4, acc);
                 if (leader) umma::mma_commit(&dfull[gs & 1]);
                 __syncwarp();
                 ++gs;
@@ -208,7 +217,7 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                 const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
                 uint32_t acc = 0;
                 ensure_e(gs - 2);
-                for (int kb = 0; kb < 4; ++kb) kblock(d_col, tc::kColA0 + 32 * kb, 0, kI16, 4, acc);
+                stage(d_col, tc::kColA0, 0, kI16, 4, 2048, 4, acc);
                 if (leader) umma::mma_commit(&dfull[gs & 1]);
                 __syncwarp();
                 ++gs;
@@ -217,7 +226,7 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                 const uint32_t d_col = tc::kColD + 128u * (uint32_t)(gs & 1);
                 uint32_t acc = 0;
                 ensure_e(gs - 2);
-                for (int kb = 0; kb < 2; ++kb) kblock(d_col, tc::kColA1 + 32 * kb, 0, kI16, 4, acc);
+                stage(d_col, tc::kColA1, 0, kI16, 2, 2048, 4, acc);
                 if (leader) umma::mma_commit(&dfull[gs & 1]);
                 __syncwarp();
                 ++gs;

@@ -26,6 +26,37 @@ constexpr StageTable make_stage_table() {
 }
 static __constant__ StageTable c_stages = make_stage_table();
 
+// Merged stages for the 1-CTA forward kernel: the copy engine completes about one request per ~550 clk per issuing
+// lane whatever its size (profiles/r01_notes.md), so K-blocks that are consumed back to back are fetched as ONE bulk copy
+// of up to 32 KB (the packed image is contiguous in consumption order; only this table changes):
+//   mlp.0: 1 block per half | 256-wide layers: 2 + 2 blocks per half | feature_fn.0 / rgb_fn.0: PE block, then 2 + 2 |
+//   density_fn.0: its 4 small blocks | rgb_fn.2: its 2 small blocks.
+constexpr int kMergedStages = 33;
+struct MergedTable { StageRef s[kMergedStages]; };
+constexpr MergedTable make_merged_table() {
+    MergedTable t{};
+    int m = 0, i = 0;
+    auto take = [&](int nblocks) {
+        t.s[m].offset = pk::kLayout.st[i].offset;
+        uint32_t bytes = 0;
+        for (int j = 0; j < nblocks; ++j) bytes += (uint32_t)pk::kLayout.st[i + j].rows * 128u;
+        t.s[m].bytes = bytes;
+        i += nblocks;
+        ++m;
+    };
+    take(1); take(1);                                            // mlp.0
+    for (int l = 0; l < 3; ++l) for (int h = 0; h < 2; ++h) { take(2); take(2); }      // mlp.2/4/6
+    for (int h = 0; h < 2; ++h) { take(1); take(2); take(2); }                        // feature_fn.0
+    for (int l = 0; l < 2; ++l) for (int h = 0; h < 2; ++h) { take(2); take(2); }      // feature_fn.2/4
+    take(1); take(2); take(2);                                                         // rgb_fn.0
+    take(4);                                                                           // density_fn.0
+    take(2);                                                                           // rgb_fn.2
+    return t;
+}
+static __constant__ MergedTable c_merged = make_merged_table();
+static_assert(make_merged_table().s[kMergedStages - 1].offset + make_merged_table().s[kMergedStages - 1].bytes ==
+                  pk::kLayout.weight_bytes, "merged stage table must cover the whole weight image");
+
 // cos / sin of a = fl32(2^i pi) * x for |a| up to a few thousand: Cody-Waite reduction by 2 pi in two FMAs,
 // then the MUFU approximations on [-pi, pi] (abs error ~1e-6, far below bf16 resolution).
 __device__ __forceinline__ void fast_sincos(float a, float& s, float& c) {

@@ -151,3 +151,80 @@ extern "C" int nerf_debug_tmem_bw(int nwarps, int iters, int mode, long long* ou
     nerf::tmem_bw_probe_kernel<<<1, nwarps * 32, 0, (cudaStream_t)stream>>>(iters, mode, out);
     return nerf::check_launch("nerf_debug_tmem_bw");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Copy-engine streaming probe: one producer lane streams `nstages` x `bytes` from an L2-resident buffer through a
+// `slots`-deep shared-memory ring; a consumer warp releases every slot as soon as it is full.  mode 0: cp.async.bulk
+// (1-D), mode 1: cp.async.bulk.tensor.2d (tensor map, box = 64 bf16 x bytes/128 rows).  out[blockIdx] = cycles.
+#include <cuda.h>
+namespace nerf {
+__global__ void __launch_bounds__(160, 1)
+copy_stream_probe_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ src, uint32_t src_bytes, int mode,
+                         uint32_t bytes, int slots, int nstages, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full[16], empty[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < slots; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
+        umma::fence_mbar_init();
+    }
+    __syncthreads();
+    const long long t0 = clock64();
+    const int nprod = (int)(blockDim.x >> 5) - 1;      // warps 0..nprod-1 produce (stage s handled by warp s % nprod), last warp consumes
+    if (warp < nprod) {
+        if (lane == 0) {
+            uint32_t off = (uint32_t)warp * bytes;
+            for (int s = warp; s < nstages; s += nprod) {
+                const int slot = s % slots, ph = (s / slots) & 1;
+                umma::mbar_wait(&empty[slot], ph ^ 1);
+                umma::mbar_arrive_expect_tx(&full[slot], bytes);
+                if (mode == 0) {
+                    umma::bulk_g2s(smem + slot * bytes, src + off, bytes, &full[slot]);
+                } else {
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                                     umma::smem_u32(smem + slot * bytes)),
+                                 "l"(&tmap), "r"(umma::smem_u32(&full[slot])), "r"(0), "r"((int)(off >> 7))
+                                 : "memory");
+                }
+                off += bytes * nprod;
+                if (off + bytes > src_bytes) off = (uint32_t)warp * bytes;
+            }
+        }
+    } else {
+        for (int s = 0; s < nstages; ++s) {
+            const int slot = s % slots, ph = (s / slots) & 1;
+            umma::mbar_wait(&full[slot], ph);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&empty[slot]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
+}
+}  // namespace nerf
+
+extern "C" int nerf_debug_copy_stream(const void* src, uint32_t src_bytes, int mode, uint32_t bytes, int slots, int nstages, int grid,
+                                      int nprod, long long* out, void* stream) {
+    using namespace nerf;
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    NERF_REQUIRE(fn && slots <= 16 && bytes % 128 == 0 && (mode == 0 || bytes / 128 <= 256) && nprod >= 1 && nprod <= 4, "nerf_debug_copy_stream: bad args");
+    CUtensorMap tm;
+    const cuuint64_t gdim[2] = {64, src_bytes / 128};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t estride[2] = {1, 1};
+    const cuuint32_t box[2] = {64, bytes / 128 <= 256 ? bytes / 128 : 256};
+    CUresult r = ((EncodeTiledFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(src), gdim, gstride, box, estride,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NERF_REQUIRE(r == CUDA_SUCCESS, "nerf_debug_copy_stream: tensor map encode failed (%d)", (int)r);
+    const size_t smem = (size_t)slots * bytes + 1024;
+    cudaFuncSetAttribute(copy_stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    copy_stream_probe_kernel<<<grid, 32 * (nprod + 1), smem, (cudaStream_t)stream>>>(tm, (const uint8_t*)src, src_bytes, mode, bytes, slots, nstages, out);
+    return check_launch("nerf_debug_copy_stream");
+}
