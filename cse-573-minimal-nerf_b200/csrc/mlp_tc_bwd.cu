@@ -15,8 +15,9 @@ namespace nerf {
 
 namespace tb {
 constexpr int kTileM = 128;
-constexpr int kSlots = 9;
-constexpr int kThreads = 512;          // warp 0 producer, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue, 12-15 dr producers
+constexpr int kSlots = 4;
+constexpr uint32_t kSlotBytes = 32768;
+constexpr int kThreads = 512;          // warps 0,3 W^T producers, 1 MMA, 2 TMEM alloc, 4-11 epilogue, 12-15 dr producers
 constexpr int kEpiWarps = 8;
 constexpr int kProdWarps = 4;
 constexpr int kSteps = 14;
@@ -24,7 +25,7 @@ constexpr uint32_t kColD = 0, kColA0 = 256, kColA1 = 384;
 
 constexpr uint32_t kOffDr = 0;             // 2 buffers x 2 K-blocks x [128 x 64] bf16 (dr, K = 128)
 constexpr uint32_t kOffRing = 65536;
-constexpr uint32_t kOffConst = kOffRing + kSlots * 16384;               // fp32 W9 [3][128], w7 [256]
+constexpr uint32_t kOffConst = kOffRing + kSlots * kSlotBytes;               // fp32 W9 [3][128], w7 [256]
 constexpr uint32_t kOffBars = kOffConst + pk::kConstFloatsT * 4;
 constexpr uint32_t kNumBars = 2 * kSlots + 8;
 constexpr uint32_t kOffTmemHolder = kOffBars + kNumBars * 8;
@@ -32,13 +33,8 @@ constexpr uint32_t kSmemBytes = kOffTmemHolder + 16 + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 }  // namespace tb
 
-struct StageTableT { StageRef s[pk::kStagesT]; };
-constexpr StageTableT make_stage_table_t() {
-    StageTableT t{};
-    for (int i = 0; i < pk::kStagesT; ++i) { t.s[i].offset = pk::kLayoutT.st[i].offset; t.s[i].bytes = 16384; }
-    return t;
-}
-static __constant__ StageTableT c_stages_t = make_stage_table_t();
+// All 52 K-blocks are 16 KB and consumed in pairs: fetched as 26 requests of 32 KB (see mlp_tc_common.cuh on why).
+constexpr int kMergedStagesT = pk::kStagesT / 2;
 
 __global__ void __launch_bounds__(tb::kThreads, 1)
 mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __restrict__ acts,
@@ -81,17 +77,19 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ W^T stage producer
+    if (warp == 0 || warp == 3) {
+        // ------------------------------------------------------------------ W^T stage producers (two warps alternate 32 KB requests)
         const bool leader = umma::elect_one();
+        const uint32_t me = (warp == 0) ? 0u : 1u;
         uint32_t cnt = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int s = 0; s < pk::kStagesT; ++s, ++cnt) {
+            for (int s = 0; s < kMergedStagesT; ++s, ++cnt) {
+                if ((cnt & 1u) != me) continue;
                 const uint32_t slot = cnt % tb::kSlots, ph = (cnt / tb::kSlots) & 1;
                 umma::mbar_wait(&empty[slot], ph ^ 1);
                 if (leader) {
-                    umma::mbar_arrive_expect_tx(&full[slot], 16384);
-                    umma::bulk_g2s(sRing + slot * 16384, packed_t + c_stages_t.s[s].offset, 16384, &full[slot]);
+                    umma::mbar_arrive_expect_tx(&full[slot], tb::kSlotBytes);
+                    umma::bulk_g2s(sRing + slot * tb::kSlotBytes, packed_t + (size_t)s * tb::kSlotBytes, tb::kSlotBytes, &full[slot]);
                 }
                 __syncwarp();
             }
@@ -110,16 +108,23 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
             }
             umma::tc_fence_after();
         };
-        auto kblock = [&](uint32_t d_col, int a_col, uint64_t a_desc, uint32_t& acc) {
+        // one 32 KB request = two K=64 blocks; A block kb from TMEM columns a_col + 32 kb, or from smem tile a_desc + kb * 16 KB
+        auto stage2 = [&](uint32_t d_col, int a_col, uint32_t a_smem, uint32_t& acc) {
             const uint32_t slot = cnt % tb::kSlots, ph = (cnt / tb::kSlots) & 1;
             umma::mbar_wait(&full[slot], ph);
             umma::tc_fence_after();
             if (leader) {
-                const uint64_t bdesc = umma::make_desc_k_sw128(umma::smem_u32(sRing + slot * 16384));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (a_col >= 0) umma::mma_ts(tmem + d_col, tmem + (uint32_t)a_col + 8u * k, bdesc + 2u * k, kI128, acc | (uint32_t)k);
-                    else            umma::mma_ss(tmem + d_col, a_desc + 2u * k, bdesc + 2u * k, kI128, acc | (uint32_t)k);
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t bdesc = umma::make_desc_k_sw128(umma::smem_u32(sRing + slot * tb::kSlotBytes + kb * 16384));
+                    const uint64_t adesc = umma::make_desc_k_sw128(a_smem + kb * 16384);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (a_col >= 0)
+                            umma::mma_ts(tmem + d_col, tmem + (uint32_t)a_col + 32u * kb + 8u * k, bdesc + 2u * k, kI128, acc | (uint32_t)(kb | k));
+                        else
+                            umma::mma_ss(tmem + d_col, adesc + 2u * k, bdesc + 2u * k, kI128, acc | (uint32_t)(kb | k));
+                    }
                 }
                 umma::mma_commit(&empty[slot]);
             }
@@ -142,8 +147,7 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
                 const uint32_t d_col = tb::kColD + 128u * (uint32_t)(gs & 1);
                 uint32_t acc = 0;
                 ensure_e(gs - 2);
-                kblock(d_col, -1, umma::make_desc_k_sw128(dr_base), acc);
-                kblock(d_col, -1, umma::make_desc_k_sw128(dr_base + 16384), acc);
+                stage2(d_col, -1, dr_base, acc);
                 if (h == 1) {                                   // last read of this tile's dr buffers
                     if (leader) umma::mma_commit(&dr_empty[pb]);
                     __syncwarp();
@@ -156,11 +160,9 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
                     const uint32_t d_col = tb::kColD + 128u * (uint32_t)(gs & 1);
                     uint32_t acc = 0;
                     ensure_e(gs - 2);
-                    kblock(d_col, a_base + 0, 0, acc);
-                    kblock(d_col, a_base + 32, 0, acc);
+                    stage2(d_col, a_base + 0, 0, acc);
                     if (h == 0) ensure_e(gs - 1);
-                    kblock(d_col, a_base + 64, 0, acc);
-                    kblock(d_col, a_base + 96, 0, acc);
+                    stage2(d_col, a_base + 64, 0, acc);
                     step_done();
                 }
             }
