@@ -310,14 +310,16 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                     p[2 * j + 1] = relu ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
                 }
                 umma::tmem_st16(a_addr, p);
-                // training: keep what the next layer consumes (post-activation bf16), [row][1920] row-major:
-                // mlp.0..feature_fn.4 outputs at 256*layer, rgb_fn.0 output at 1792
-                uint4* act_row = nullptr;
-                if (act_out != nullptr && valid)
-                    act_row = (uint4*)(act_out + row * (int64_t)pk::kActFeatures + (s < 14 ? layer * 256 + nhalf * 128 : 1792) + wh * 64);
-                if (act_row) {
+                // training: keep what the next layer consumes (post-activation bf16) in the tiled chunk-major layout
+                // (pack_layout.cuh): outputs of mlp.0..feature_fn.4 at feature 256*layer, rgb_fn.0 at 1792.  Lanes are
+                // consecutive rows, so every 16-byte store of the warp lands in one contiguous 512-byte run.  Rows past
+                // `total` are stored too (finite values; their dz is zero) so wgrad can read whole tiles.
+                uint4* act_chunk = nullptr;
+                if (act_out != nullptr)
+                    act_chunk = (uint4*)(act_out + pk::tiled_offset(row, (s < 14 ? layer * 256 + nhalf * 128 : 1792) + wh * 64, pk::kActChunks));
+                if (act_chunk) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) act_row[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) act_chunk[j * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -328,9 +330,9 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                     p[2 * j + 1] = relu ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
                 }
                 umma::tmem_st16(a_addr + 16, p);
-                if (act_row) {
+                if (act_chunk) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) act_row[4 + j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) act_chunk[(4 + j) * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
                 }
                 umma::tmem_wait_st();
                 umma::tc_fence_before();
@@ -454,8 +456,9 @@ extern "C" int nerf_mlp_forward_tc_points(const void* packed, const float* sampl
     return launch_mlp_tc(packed, nullptr, d, nullptr, samples, N, S, sigma, rgb, stream);
 }
 
-// Training form: also writes the bf16 activations every layer consumed, act_out [N*S, 1920] row-major
-// (outputs of mlp.0, mlp.2, mlp.4, mlp.6, feature_fn.0, feature_fn.2, feature_fn.4 at 256*k, rgb_fn.0 at 1792).
+// Training form: also writes the bf16 activations every layer consumed (outputs of mlp.0, mlp.2, mlp.4, mlp.6,
+// feature_fn.0, feature_fn.2, feature_fn.4 at feature 256*k, rgb_fn.0 at 1792) in the tiled chunk-major layout of
+// pack_layout.cuh; act_out holds ceil(N*S/128)*128 rows x 1920 features.
 extern "C" int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
                                          int64_t N, int S, float* sigma, float* rgb, void* act_out, void* stream) {
     NERF_REQUIRE(N == 0 || act_out, "nerf_mlp_forward_tc_train: act_out is NULL");

@@ -6,7 +6,8 @@
 //     dz6  = dr . W8[:, :256] + dsigma_pre (x) w7              steps 0,1   (A = dr tile in shared memory, SS)
 //     dz5  = (dz6 . W6) * [h5 > 0]                             steps 2,3   (A = previous dz in TMEM, TS; B = W^T stages)
 //     dz4 .. dz0 likewise through feature_fn.2, feature_fn.0 (h columns), mlp.6, mlp.4, mlp.2     steps 4..13
-//   every dz is written to global (bf16, [samples, 1920], same column map as the saved activations) for wgrad.
+//   every dz is written to global (bf16, tiled chunk-major like the saved activations, pack_layout.cuh) for wgrad,
+//   plus a 16-wide heads block [dsigma_pre, drgb_pre, 0..] at features 1920..1935.
 // ReLU masks come from the forward's saved activations (prefetched into registers before the accumulator wait).
 // mlp.0's dgrad (d PE) is not needed: the inputs carry no gradient.
 #include "mlp_tc_common.cuh"
@@ -55,7 +56,6 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t num_tiles = (total + tb::kTileM - 1) / tb::kTileM;
-    constexpr int64_t kAct = pk::kActFeatures;
 
     if (tid == 0) {
         for (int i = 0; i < tb::kSlots; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
@@ -183,9 +183,9 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
             for (int kb = 0; kb < 2; ++kb) {
                 uint32_t v[32];
                 uint4 m[8];                                              // r[row, 64kb : 64kb+64] (bf16) for the ReLU mask
+                const uint4* msrc = (const uint4*)(acts + pk::tiled_offset(row, 1792 + kb * 64, pk::kActChunks));
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    m[j] = valid ? *(const uint4*)(acts + row * kAct + 1792 + kb * 64 + j * 8) : make_uint4(0, 0, 0, 0);
+                for (int j = 0; j < 8; ++j) m[j] = msrc[j * 128];
                 const uint32_t* mw = (const uint32_t*)m;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -198,11 +198,15 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
                     v[j] = umma::pack_bf16(a, b);
                 }
                 store_row_sw128(smem + tb::kOffDr + pb * 32768 + kb * 16384, r, v);
-                if (valid) {
-                    uint4* dst = (uint4*)(dz_out + row * kAct + 1792 + kb * 64);
+                uint4* dst = (uint4*)(dz_out + pk::tiled_offset(row, 1792 + kb * 64, pk::kDzChunks));
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
+                for (int j = 0; j < 8; ++j) dst[j * 128] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            {   // heads block (features 1920..1935): [dsigma_pre, drgb_pre x3, 0 ...] in bf16 for the head weight gradients
+                const float dsg = valid ? dsigma_pre[row] : 0.f;
+                uint4* dst = (uint4*)(dz_out + pk::tiled_offset(row, 1920, pk::kDzChunks));
+                dst[0] = make_uint4(umma::pack_bf16(dsg, g0), umma::pack_bf16(g1, g2), 0u, 0u);
+                dst[128] = make_uint4(0u, 0u, 0u, 0u);
             }
             umma::fence_proxy_async_smem();
             __syncwarp();
@@ -228,9 +232,9 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
                 // ReLU mask source: saved output of layer j (post-ReLU), except dz6 (feature_fn.4 is linear)
                 uint4 m[8];
                 if (j < 6) {
+                    const uint4* msrc = (const uint4*)(acts + pk::tiled_offset(row, j * 256 + col0, pk::kActChunks));
 #pragma unroll
-                    for (int t = 0; t < 8; ++t)
-                        m[t] = valid ? *(const uint4*)(acts + row * kAct + j * 256 + col0 + t * 8) : make_uint4(0, 0, 0, 0);
+                    for (int t = 0; t < 8; ++t) m[t] = msrc[t * 128];
                 }
                 const uint32_t* mw = (const uint32_t*)m;
                 umma::mbar_wait(&dfull[gs & 1], (uint32_t)((gs >> 1) & 1));
@@ -261,10 +265,10 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
                     umma::tmem_st16(a_addr, *(const uint32_t(*)[16])(p));
                     umma::tmem_st16(a_addr + 16, *(const uint32_t(*)[16])(p + 16));
                 }
-                if (valid) {
-                    uint4* dst = (uint4*)(dz_out + row * kAct + j * 256 + col0);
+                {   // rows past `total` carry zeros (their dsigma / drgb are zero), so wgrad can read whole tiles
+                    uint4* dst = (uint4*)(dz_out + pk::tiled_offset(row, j * 256 + col0, pk::kDzChunks));
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) dst[t] = make_uint4(p[4 * t], p[4 * t + 1], p[4 * t + 2], p[4 * t + 3]);
+                    for (int t = 0; t < 8; ++t) dst[t * 128] = make_uint4(p[4 * t], p[4 * t + 1], p[4 * t + 2], p[4 * t + 3]);
                 }
                 if (j > 0) umma::tmem_wait_st();
                 umma::tc_fence_before();

@@ -50,6 +50,20 @@ struct Layout {
 constexpr int kBiasFloats = 1928;
 constexpr int kBiasR0 = 1792, kBiasSigma = 1920, kBiasRgb = 1924;
 constexpr int kActFeatures = 1920;   // saved bf16 activations per sample (training): 7 x 256 + 128
+// Training tensors (saved activations `acts`, pre-activation gradients `dz`) are stored TILED CHUNK-MAJOR:
+//   element (row, feature f) of 128-row tile t lives at  ((t * kChunks + f/8) * 128 + row%128) * 8 + f%8   (bf16 elements)
+// i.e. per tile, 16-byte chunks of 8 features are the slow index and the 128 rows the fast one.  A warp whose lanes are
+// consecutive rows therefore reads/writes 512 contiguous bytes per instruction, and a [128 rows x 64 features] block is a
+// contiguous 16 KB that is, as it stands, the UMMA no-swizzle MN-major canonical layout (core-matrix strides: 2048 B along
+// the features, 128 B along the rows) that wgrad (contraction over rows) consumes.
+// dz has two extra chunks (features 1920..1935): [dsigma_pre, drgb_pre x3, 0 ...] in bf16, the A/B operand of the two
+// head weight gradients.
+constexpr int kActChunks = kActFeatures / 8;        // 240
+constexpr int kDzFeatures = kActFeatures + 16;      // 1936
+constexpr int kDzChunks = kDzFeatures / 8;          // 242
+__host__ __device__ constexpr int64_t tiled_offset(int64_t row, int feature, int chunks_per_tile) {
+    return (((row >> 7) * chunks_per_tile + (feature >> 3)) * 128 + (row & 127)) * 8 + (feature & 7);
+}
 
 constexpr Layout make_layout() {
     Layout L{};

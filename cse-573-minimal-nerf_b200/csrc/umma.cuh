@@ -127,6 +127,20 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                               // [61,64) layout = SWIZZLE_128B
     return d;
 }
+// Shared-memory matrix descriptor, MN-major operand, no swizzle ("interleave"): 8 x 8 core matrices of 128 B whose rows
+// are K indices and whose 16-byte row holds 8 consecutive M/N elements; `mn_stride` = bytes between core matrices that are
+// 8 elements apart along M/N (SBO field), `k_stride` = bytes between core matrices 8 apart along K (LBO field).
+__device__ __forceinline__ uint64_t make_desc_mn_interleave(uint32_t smem_addr, uint32_t mn_stride, uint32_t k_stride) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((k_stride >> 4) & 0x3FFF) << 16;      // leading byte offset
+    d |= (uint64_t)((mn_stride >> 4) & 0x3FFF) << 32;     // stride byte offset
+    d |= (uint64_t)1 << 46;                               // descriptor version = 1 (sm_100)
+    return d;                                             // layout type 0 = SWIZZLE_NONE
+}
+// Instruction descriptor bits for MN-major ("transposed") operands.
+constexpr uint32_t kIdescAMajorMN = 1u << 15, kIdescBMajorMN = 1u << 16;
+
 // Byte offset of element (row, k) inside such a tile (k < 64).
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t k) {
     return row * 128u + ((((k >> 3) ^ (row & 7u)) << 4) | ((k & 7u) << 1));

@@ -27,11 +27,23 @@ umma_probe_kernel(int mode, const __nv_bfloat16* __restrict__ A, const __nv_bflo
     const uint32_t tmem = tmem_holder;
 
     // stage B (and A for SS) into swizzled shared memory
+    if (mode != 2)
     for (int e = tid; e < N * K; e += blockDim.x) {
         const int n = e / K, k = e % K;
         *(__nv_bfloat16*)(sB + (size_t)(k / 64) * N * 128 + umma::sw128_offset(n, k % 64)) = B[e];
     }
-    if (mode == 0) {
+    if (mode == 2) {
+        // MN-major, no swizzle: A given as [K][128] (M contiguous), B as [K][N]; chunk-major staging
+        // element (k, m) -> (m/8) * (K*16) + k*16 + (m%8)*2   (the layout the training path saves activations in)
+        for (int e = tid; e < 128 * K; e += blockDim.x) {
+            const int k = e / 128, m = e % 128;
+            *(__nv_bfloat16*)(sA + (size_t)(m / 8) * (K * 16) + k * 16 + (m % 8) * 2) = A[e];
+        }
+        for (int e = tid; e < N * K; e += blockDim.x) {
+            const int k = e / N, n = e % N;
+            *(__nv_bfloat16*)(sB + (size_t)(n / 8) * (K * 16) + k * 16 + (n % 8) * 2) = B[e];
+        }
+    } else if (mode == 0) {
         for (int e = tid; e < 128 * K; e += blockDim.x) {
             const int m = e / K, k = e % K;
             *(__nv_bfloat16*)(sA + (size_t)(k / 64) * 16384 + umma::sw128_offset(m, k % 64)) = A[e];
@@ -54,7 +66,15 @@ umma_probe_kernel(int mode, const __nv_bfloat16* __restrict__ A, const __nv_bflo
     __syncthreads();
     umma::tc_fence_after();
 
-    if (tid == 0) {
+    if (tid == 0 && mode == 2) {
+        const uint32_t idesc = umma::make_idesc_bf16(128, N) | umma::kIdescAMajorMN | umma::kIdescBMajorMN;
+        for (int k16 = 0; k16 < K / 16; ++k16) {          // one K=16 slice = two 8-deep core-matrix rows = 256 B further along K
+            const uint64_t adesc = umma::make_desc_mn_interleave(umma::smem_u32(sA) + k16 * 256, K * 16, 128);
+            const uint64_t bdesc = umma::make_desc_mn_interleave(umma::smem_u32(sB) + k16 * 256, K * 16, 128);
+            umma::mma_ss(tmem + d_col, adesc, bdesc, idesc, k16 > 0);
+        }
+        umma::mma_commit(&bar);
+    } else if (tid == 0) {
         const uint32_t idesc = umma::make_idesc_bf16(128, N);
         uint32_t acc = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -89,7 +109,7 @@ extern "C" int nerf_debug_umma(int mode, const void* A_bf16, const void* B_bf16,
                                void* stream) {
     using namespace nerf;
     NERF_REQUIRE(A_bf16 && B_bf16 && D, "nerf_debug_umma: null pointer");
-    NERF_REQUIRE((mode == 0 || mode == 1) && K % 64 == 0 && K >= 64 && K <= 256 && N % 16 == 0 && N >= 16 && N <= 256 &&
+    NERF_REQUIRE((mode == 0 || mode == 1 || mode == 2) && K % 64 == 0 && K >= 64 && K <= 256 && N % 16 == 0 && N >= 16 && N <= 256 &&
                      d_col >= 0 && d_col + N <= 256,
                  "nerf_debug_umma: bad shape");
     const size_t smem = (size_t)(K / 64) * (16384 + (size_t)N * 128) + 1024;

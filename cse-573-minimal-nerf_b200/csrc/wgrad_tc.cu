@@ -1,0 +1,357 @@
+// wgrad_tc.cu - weight and bias gradients of one NeRFModel on the tensor cores.
+//
+//   dW_l[n_out, k_in] = sum_samples dz_l[s, n_out] * a_l[s, k_in]          db_l[n_out] = sum_samples dz_l[s, n_out]
+//
+// The contraction runs over samples, so both operands are "MN-major" for the MMA.  The training path stores activations
+// (`acts`) and pre-activation gradients (`dz`) tiled chunk-major (pack_layout.cuh), in which every [128 samples x 64
+// features] block is a contiguous 16 KB that already IS the UMMA no-swizzle MN-major canonical layout: operands arrive by
+// plain 32 / 64 KB bulk copies, no transposition anywhere.
+//
+// Work decomposition (one launch per network, one CTA per SM):
+//   a "job" = one product D[128 rows of n_out] x [all k_in columns] (fp32 in TMEM), i.e. one 128-row half of a layer's dW;
+//   18 jobs (table below); each job is split-K over the 128-sample tiles among a fixed group of CTAs, the two halves of
+//   a layer walk the same tiles in adjacent CTAs so their common B operand is read from HBM once and from L2 once.
+//   At the end every CTA adds its partial D (and bias sums) to the fp32 gradients with atomics.
+// Per CTA: warps 0 and 2 issue the A / B bulk copies (2-deep ring of whole tiles), warp 1 issues tcgen05.mma
+// (M128 x N<=256 x K16, both operands MN-major, A and B from shared memory), warps 4-7 sum the dz tile's columns for the
+// bias gradient while it sits in shared memory and run the final TMEM -> atomics epilogue, warps 8-11 recompute PE(x) /
+// PE(dir) tiles for the three products whose input is a positional encoding.  The kernel is HBM-bound by design
+// (96 KB of operands per 1024 clk of MMA); its roofline is bytes / HBM bandwidth.
+#include "mlp_tc_common.cuh"
+
+namespace nerf {
+
+namespace wg {
+constexpr int kThreads = 384;
+constexpr int kSlots = 2;
+constexpr uint32_t kABytes = 32768;        // [128 samples x 128 n_out]
+constexpr uint32_t kBBytes = 65536;        // [128 samples x up to 256 k_in]
+constexpr uint32_t kPEBytes = 16384;       // [128 samples x 64] recomputed encoding
+constexpr uint32_t kOffA = 0;
+constexpr uint32_t kOffB = kSlots * kABytes;                       // 65536
+constexpr uint32_t kOffPE = kOffB + kSlots * kBBytes;              // 196608
+constexpr uint32_t kOffBars = kOffPE + kPEBytes;                   // 212992 (single PE buffer)
+constexpr uint32_t kOffTmemHolder = kOffBars + 16 * 8;
+constexpr uint32_t kSmemBytes = kOffTmemHolder + 16 + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+enum { SRC_ACTS = 0, SRC_DZ = 1 };
+enum { PE_NONE = 0, PE_X = 1, PE_DIR = 2 };
+enum { OUT_NORMAL = 0, OUT_DENSITY = 1, OUT_RGB = 2 };
+
+struct Job {
+    uint8_t a_src;        // where the M operand (128 features) comes from
+    uint16_t a_feat;      // its first feature
+    uint8_t b_cols;       // columns of the B block read from memory / 16 (0 = none)
+    uint8_t b_src;
+    uint16_t b_feat;
+    uint8_t pe;           // extra (or only) B operand recomputed in the kernel
+    uint8_t out_kind;
+    uint8_t w_param;      // index of the weight gradient (state_dict order 0..9)
+    uint16_t row0;        // first dW row of this half
+    uint16_t in_features; // leading dimension of dW
+    uint16_t pe_col0;     // dW column of the PE part, valid PE columns
+    uint8_t pe_valid;
+    uint8_t bias;         // 1: this job also produces db[row0 : row0+128] (column sums of its A operand)
+    uint8_t ctas;         // CTAs that split this job's tiles
+};
+
+// dz feature offsets: layer k's pre-activation gradient at 256 k (k = 0..6), rgb_fn.0 at 1792, heads block at 1920.
+// acts feature offsets: output of layer k at 256 k, rgb_fn.0 output r at 1792.
+__constant__ Job c_jobs[18] = {
+    // a_src  a_feat b/16 b_src    b_feat pe      out          w  row0 in   pecol pev bias ctas
+    {SRC_DZ, 0,     0,  SRC_ACTS, 0,    PE_X,   OUT_NORMAL,  0, 0,   60,  0,   60, 1, 4},     // mlp.0 half 0
+    {SRC_DZ, 128,   0,  SRC_ACTS, 0,    PE_X,   OUT_NORMAL,  0, 128, 60,  0,   60, 1, 4},     // mlp.0 half 1
+    {SRC_DZ, 256,   16, SRC_ACTS, 0,    PE_NONE, OUT_NORMAL, 1, 0,   256, 0,   0,  1, 9},     // mlp.2
+    {SRC_DZ, 384,   16, SRC_ACTS, 0,    PE_NONE, OUT_NORMAL, 1, 128, 256, 0,   0,  1, 9},
+    {SRC_DZ, 512,   16, SRC_ACTS, 256,  PE_NONE, OUT_NORMAL, 2, 0,   256, 0,   0,  1, 9},     // mlp.4
+    {SRC_DZ, 640,   16, SRC_ACTS, 256,  PE_NONE, OUT_NORMAL, 2, 128, 256, 0,   0,  1, 9},
+    {SRC_DZ, 768,   16, SRC_ACTS, 512,  PE_NONE, OUT_NORMAL, 3, 0,   256, 0,   0,  1, 9},     // mlp.6
+    {SRC_DZ, 896,   16, SRC_ACTS, 512,  PE_NONE, OUT_NORMAL, 3, 128, 256, 0,   0,  1, 9},
+    {SRC_DZ, 1024,  16, SRC_ACTS, 768,  PE_X,   OUT_NORMAL,  4, 0,   316, 256, 60, 1, 10},    // feature_fn.0: [h3 | PE(x)]
+    {SRC_DZ, 1152,  16, SRC_ACTS, 768,  PE_X,   OUT_NORMAL,  4, 128, 316, 256, 60, 1, 10},
+    {SRC_DZ, 1280,  16, SRC_ACTS, 1024, PE_NONE, OUT_NORMAL, 5, 0,   256, 0,   0,  1, 9},     // feature_fn.2
+    {SRC_DZ, 1408,  16, SRC_ACTS, 1024, PE_NONE, OUT_NORMAL, 5, 128, 256, 0,   0,  1, 9},
+    {SRC_DZ, 1536,  16, SRC_ACTS, 1280, PE_NONE, OUT_NORMAL, 6, 0,   256, 0,   0,  1, 9},     // feature_fn.4
+    {SRC_DZ, 1664,  16, SRC_ACTS, 1280, PE_NONE, OUT_NORMAL, 6, 128, 256, 0,   0,  1, 9},
+    {SRC_DZ, 1792,  16, SRC_ACTS, 1536, PE_DIR, OUT_NORMAL,  8, 0,   280, 256, 24, 1, 12},    // rgb_fn.0: [feat | PE(dir)]
+    {SRC_ACTS, 1536, 1, SRC_DZ,   1920, PE_NONE, OUT_DENSITY, 7, 0,  256, 0,   0,  0, 4},     // density_fn.0: feat^T . heads, half 0
+    {SRC_ACTS, 1664, 1, SRC_DZ,   1920, PE_NONE, OUT_DENSITY, 7, 128, 256, 0,  0,  0, 4},
+    {SRC_ACTS, 1792, 1, SRC_DZ,   1920, PE_NONE, OUT_RGB,    9, 0,   128, 0,   0,  2, 4},     // rgb_fn.2: r^T . heads (+ head biases)
+};
+constexpr int kNumJobs = 18;
+constexpr int kGridCtas = 2 * 4 + 6 * 9 + 2 * 10 + 4 * 9 + 12 + 3 * 4;     // 142
+}  // namespace wg
+
+struct Grads { float* p[20]; };
+
+__global__ void __launch_bounds__(wg::kThreads, 1)
+wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __restrict__ dz, const float* __restrict__ o_rays,
+                const float* __restrict__ d_rays, const float* __restrict__ ts, int64_t total, int S, Grads G) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + wg::kOffBars);
+    uint64_t* fullA = bars;            // [2]
+    uint64_t* fullB = bars + 2;        // [2]
+    uint64_t* empty = bars + 4;        // [2]  MMA commit + 4 bias-sum warps
+    uint64_t* pe_full = bars + 6;      // [1]
+    uint64_t* pe_empty = bars + 7;     // [1]
+    uint64_t* done = bars + 8;         // [1]
+    uint32_t* tmem_holder = (uint32_t*)(smem + wg::kOffTmemHolder);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t num_tiles = (total + 127) / 128;
+
+    // which job, and which share of its tiles, this CTA owns
+    int job_idx = 0, first = 0;
+    {
+        int b = blockIdx.x;
+        // the two halves of a layer are interleaved (CTA 2i, 2i+1 walk the same tiles) so they share B through L2
+        while (job_idx < wg::kNumJobs) {
+            const bool paired = (job_idx + 1 < wg::kNumJobs) && wg::c_jobs[job_idx].w_param == wg::c_jobs[job_idx + 1].w_param &&
+                                wg::c_jobs[job_idx].row0 == 0 && wg::c_jobs[job_idx + 1].row0 == 128;
+            const int span = paired ? 2 * wg::c_jobs[job_idx].ctas : wg::c_jobs[job_idx].ctas;
+            if (b < span) {
+                if (paired) { first = b >> 1; job_idx += (b & 1); }
+                else first = b;
+                break;
+            }
+            b -= span;
+            job_idx += paired ? 2 : 1;
+        }
+    }
+    if (job_idx >= wg::kNumJobs) return;                 // spare CTAs
+    const wg::Job job = wg::c_jobs[job_idx];
+    const int stride = job.ctas;
+    const int b_cols = job.b_cols * 16;
+    const bool has_pe = job.pe != wg::PE_NONE;
+    const int a_chunks = (job.a_src == wg::SRC_DZ) ? pk::kDzChunks : pk::kActChunks;
+    const int bsrc_chunks = (job.b_src == wg::SRC_DZ) ? pk::kDzChunks : pk::kActChunks;
+    const __nv_bfloat16* a_base = (job.a_src == wg::SRC_DZ ? dz : acts) + (int64_t)(job.a_feat >> 3) * 1024;
+    const __nv_bfloat16* b_base = (job.b_src == wg::SRC_DZ ? dz : acts) + (int64_t)(job.b_feat >> 3) * 1024;
+    const uint32_t b_bytes = (uint32_t)b_cols * 256u;    // 128 rows x b_cols x 2 B
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&fullA[i], 1);
+            umma::mbar_init(&fullB[i], 1);
+            umma::mbar_init(&empty[i], job.bias ? 5 : 1);
+        }
+        umma::mbar_init(pe_full, 4);
+        umma::mbar_init(pe_empty, 1);
+        umma::mbar_init(done, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 3) umma::tmem_alloc(tmem_holder, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+
+    if (warp == 0 || warp == 2) {
+        // ------------------------------------------------------------------ operand producers: warp 0 -> A tiles, warp 2 -> B tiles
+        const bool leader = umma::elect_one();
+        if (warp == 0 || b_cols > 0) {
+            uint32_t it = 0;
+            for (int64_t tile = first; tile < num_tiles; tile += stride, ++it) {
+                const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+                umma::mbar_wait(&empty[slot], ph ^ 1);
+                if (leader) {
+                    if (warp == 0) {
+                        umma::mbar_arrive_expect_tx(&fullA[slot], wg::kABytes);
+                        umma::bulk_g2s(smem + wg::kOffA + slot * wg::kABytes, a_base + tile * (int64_t)a_chunks * 1024, wg::kABytes, &fullA[slot]);
+                    } else {
+                        umma::mbar_arrive_expect_tx(&fullB[slot], b_bytes);
+                        umma::bulk_g2s(smem + wg::kOffB + slot * wg::kBBytes, b_base + tile * (int64_t)bsrc_chunks * 1024, b_bytes, &fullB[slot]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const bool leader = umma::elect_one();
+        const uint32_t kMN = umma::kIdescAMajorMN | umma::kIdescBMajorMN;
+        const uint32_t idescB = umma::make_idesc_bf16(128, b_cols > 0 ? b_cols : 16) | kMN;
+        const uint32_t idescPE = umma::make_idesc_bf16(128, 64) | kMN;
+        uint32_t it = 0;
+        for (int64_t tile = first; tile < num_tiles; tile += stride, ++it) {
+            const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+            umma::mbar_wait(&fullA[slot], ph);
+            if (b_cols > 0) umma::mbar_wait(&fullB[slot], ph);
+            if (has_pe) umma::mbar_wait(pe_full, it & 1);
+            umma::tc_fence_after();
+            if (leader) {
+                const uint32_t a_addr = umma::smem_u32(smem + wg::kOffA + slot * wg::kABytes);
+                const uint32_t b_addr = umma::smem_u32(smem + wg::kOffB + slot * wg::kBBytes);
+                const uint32_t pe_addr = umma::smem_u32(smem + wg::kOffPE);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                 // 128 samples = 8 K=16 slices, 256 B apart along the rows
+                    const uint64_t adesc = umma::make_desc_mn_interleave(a_addr + k * 256, 2048, 128);
+                    if (b_cols > 0)
+                        umma::mma_ss(tmem, adesc, umma::make_desc_mn_interleave(b_addr + k * 256, 2048, 128), idescB, (it | (uint32_t)k) != 0);
+                    if (has_pe)
+                        umma::mma_ss(tmem + (uint32_t)b_cols, adesc, umma::make_desc_mn_interleave(pe_addr + k * 256, 2048, 128), idescPE,
+                                     (it | (uint32_t)k) != 0);
+                }
+                umma::mma_commit(&empty[slot]);
+                if (has_pe) umma::mma_commit(pe_empty);
+            }
+            __syncwarp();
+        }
+        if (leader) umma::mma_commit(done);
+        __syncwarp();
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------------ PE producers (thread = sample row), chunk-major tile
+        if (has_pe) {
+            const int r = (warp - 8) * 32 + lane;
+            uint32_t it = 0;
+            for (int64_t tile = first; tile < num_tiles; tile += stride, ++it) {
+                const int64_t row = tile * 128 + r;
+                const bool valid = row < total;
+                const int64_t n = valid ? row / S : 0;
+                float x[3] = {0.f, 0.f, 0.f};
+                if (valid) {
+                    const float dx = __ldg(d_rays + n * 3), dy = __ldg(d_rays + n * 3 + 1), dzz = __ldg(d_rays + n * 3 + 2);
+                    if (job.pe == wg::PE_X) {
+                        const float t = ts[row];
+                        x[0] = __fdiv_rn(__fadd_rn(__fmul_rn(dx, t), __ldg(o_rays + n * 3 + 0)), tcm::kPiF);
+                        x[1] = __fdiv_rn(__fadd_rn(__fmul_rn(dy, t), __ldg(o_rays + n * 3 + 1)), tcm::kPiF);
+                        x[2] = __fdiv_rn(__fadd_rn(__fmul_rn(dzz, t), __ldg(o_rays + n * 3 + 2)), tcm::kPiF);
+                    } else {
+                        const float nrm = sqrtf(dx * dx + dy * dy + dzz * dzz);
+                        x[0] = __fdiv_rn(dx, nrm); x[1] = __fdiv_rn(dy, nrm); x[2] = __fdiv_rn(dzz, nrm);
+                    }
+                }
+                uint32_t v[32];
+                if (job.pe == wg::PE_X) encode_row<10>(x, v); else encode_row<4>(x, v);
+                if (!valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                umma::mbar_wait(pe_empty, (it & 1) ^ 1);
+                uint4* dst = (uint4*)(smem + wg::kOffPE) + r;          // chunk c of row r at c * 2048 + r * 16
+#pragma unroll
+                for (int c = 0; c < 8; ++c) dst[c * 128] = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                umma::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(pe_full);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ bias sums while the tiles are resident, then the epilogue
+        const int t = (warp - 4) * 32 + lane;          // 0..127
+        float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (job.bias) {
+            // job.bias == 1: column sums of the A tile (dz half).  == 2: of the B tile's heads block (dsigma, drgb).
+            const int chunk = t >> 3, rsub = t & 7;    // 16 chunks x 8 row phases
+            uint32_t it = 0;
+            for (int64_t tile = first; tile < num_tiles; tile += stride, ++it) {
+                const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+                const uint8_t* src;
+                if (job.bias == 1) { umma::mbar_wait(&fullA[slot], ph); src = smem + wg::kOffA + slot * wg::kABytes; }
+                else               { umma::mbar_wait(&fullB[slot], ph); src = smem + wg::kOffB + slot * wg::kBBytes; }
+                if (job.bias == 1 || chunk < 2) {
+#pragma unroll 4
+                    for (int k = 0; k < 16; ++k) {
+                        const uint4 q = *(const uint4*)(src + chunk * 2048 + (rsub + 8 * k) * 16);
+                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            bsum[2 * j] += __uint_as_float(w[j] << 16);
+                            bsum[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&empty[slot]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                bsum[j] += __shfl_xor_sync(kFull, bsum[j], 1);
+                bsum[j] += __shfl_xor_sync(kFull, bsum[j], 2);
+                bsum[j] += __shfl_xor_sync(kFull, bsum[j], 4);
+            }
+            if (rsub == 0) {
+                if (job.bias == 1) {
+                    float* db = G.p[2 * job.w_param + 1] + job.row0 + chunk * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) atomicAdd(db + j, bsum[j]);
+                } else if (chunk == 0) {               // heads block: [dsigma, drgb0, drgb1, drgb2]
+                    atomicAdd(G.p[15], bsum[0]);
+                    atomicAdd(G.p[19] + 0, bsum[1]);
+                    atomicAdd(G.p[19] + 1, bsum[2]);
+                    atomicAdd(G.p[19] + 2, bsum[3]);
+                }
+            }
+        }
+        // ---- epilogue: D[m = lane (row of this half), n] -> atomics into dW (skipped by CTAs that had no tile)
+        umma::mbar_wait(done, 0);
+        umma::tc_fence_after();
+        if (first < num_tiles) {
+        const int m = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        float* dW = G.p[2 * job.w_param];
+        if (job.out_kind == wg::OUT_NORMAL) {
+            float* rowp = dW + (size_t)(job.row0 + m) * job.in_features;
+            for (int c0 = 0; c0 < b_cols; c0 += 32) {
+                uint32_t v[32];
+                umma::tmem_ld32(tmem + lane_base + c0, v);
+                umma::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(rowp + c0 + j, __uint_as_float(v[j]));
+            }
+            if (has_pe) {
+                float* pep = rowp + job.pe_col0;
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    umma::tmem_ld32(tmem + lane_base + b_cols + c0, v);
+                    umma::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < job.pe_valid) atomicAdd(pep + c0 + j, __uint_as_float(v[j]));
+                }
+            }
+        } else {
+            uint32_t v[4];
+            umma::tmem_ld4(tmem + lane_base, v);
+            umma::tmem_wait_ld();
+            if (job.out_kind == wg::OUT_DENSITY) {
+                atomicAdd(dW + job.row0 + m, __uint_as_float(v[0]));                     // density_fn.0.weight [1,256]
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) atomicAdd(dW + c * 128 + m, __uint_as_float(v[1 + c]));   // rgb_fn.2.weight [3,128]
+            }
+        }
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 3) umma::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
+                             float* const* grads20_host, void* stream) {
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_wgrad_tc: bad size");
+    if (N == 0) return 0;
+    NERF_REQUIRE(acts && dz && o && d && ts && grads20_host, "nerf_wgrad_tc: null pointer");
+    NERF_REQUIRE(((uintptr_t)acts & 127) == 0 && ((uintptr_t)dz & 127) == 0, "nerf_wgrad_tc: acts / dz must be 128-byte aligned");
+    Grads G;
+    for (int i = 0; i < 20; ++i) {
+        NERF_REQUIRE(grads20_host[i], "nerf_wgrad_tc: grads20_host[%d] is NULL", i);
+        G.p[i] = grads20_host[i];
+    }
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::kSmemBytes);
+        if (e != cudaSuccess) { set_error("nerf_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
+        attr_set = true;
+    }
+    wgrad_tc_kernel<<<wg::kGridCtas, wg::kThreads, wg::kSmemBytes, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)acts, (const __nv_bfloat16*)dz, o, d, ts, N * S, S, G);
+    return check_launch("nerf_wgrad_tc");
+}

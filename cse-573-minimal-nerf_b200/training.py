@@ -21,6 +21,18 @@ import nerf_helpers
 BF = torch.bfloat16
 F32 = torch.float32
 ACT = 1920          # saved activations per sample: outputs of mlp.0/2/4/6, feature_fn.0/2/4 (7 x 256) + rgb_fn.0 (128)
+DZ = ACT + 16       # dz carries a 16-wide heads block [dsigma_pre, drgb_pre x3, 0 ...] after the 1920 layer columns
+TILE = 128
+
+
+def padded_rows(M):
+    return (M + TILE - 1) // TILE * TILE
+
+
+def untile(buf, M, features):
+    """Tiled chunk-major training tensor (csrc/pack_layout.cuh) -> plain [M, features] row-major copy."""
+    tiles = padded_rows(M) // TILE
+    return buf.view(tiles, features // 8, TILE, 8).permute(0, 2, 1, 3).reshape(tiles * TILE, features)[:M]
 
 
 def _pe(x, L):
@@ -29,11 +41,12 @@ def _pe(x, L):
 
 
 def mlp_forward_train(model, o, d, ts):
-    """Fused MLP in training form.  Returns sigma [N,S,1], rgb [N,S,3], acts [N*S, 1920] bf16."""
+    """Fused MLP in training form.  Returns sigma [N,S,1], rgb [N,S,3] and the saved bf16 activations in the tiled
+    chunk-major layout (ceil(N*S/128)*128 rows x 1920 features, flat)."""
     N, S = ts.shape[0], ts.shape[1]
     sigma = torch.empty((N, S, 1), device=ts.device, dtype=F32)
     rgb = torch.empty((N, S, 3), device=ts.device, dtype=F32)
-    acts = torch.empty((N * S, ACT), device=ts.device, dtype=BF)
+    acts = torch.empty((padded_rows(N * S) * ACT,), device=ts.device, dtype=BF)
     packed = model.packed_weights()
     with nat.timed_kernel("mlp_tc_kernel(train)", N * S):
         nat.check(nat.lib().nerf_mlp_forward_tc_train(nat.ptr(packed), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S,
@@ -53,16 +66,40 @@ def composite_backward(sigma, rgb, ts, g_ray):
 
 
 def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray):
-    """Gradients of one network's 20 parameters (state_dict order) given dL/d(ray colour) [N,3].
-    dgrad chain: hand-written tcgen05 kernel (mlp_tc_bwd.cu).  wgrad: dz^T . (layer input) as bf16 cuBLAS GEMMs with
-    fp32 output (round-1 interim), all 8 hidden bias gradients as one ones-vector GEMV over dz."""
+    """Gradients of one network's 20 parameters (state_dict order) given dL/d(ray colour) [N,3]: all hand-written kernels -
+    compositing backward, tcgen05 dgrad chain (mlp_tc_bwd.cu), tcgen05 wgrad + bias sums (wgrad_tc.cu)."""
+    import ctypes
     N, S = ts.shape[0], ts.shape[1]
     M = N * S
     dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
-    dz = torch.empty((M, ACT), device=ts.device, dtype=BF)
+    dz_t = torch.empty((padded_rows(M) * DZ,), device=ts.device, dtype=BF)
     with nat.timed_kernel("mlp_tc_bwd_kernel", M):
         nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(acts), nat.ptr(dsig), nat.ptr(drgb),
-                                                 N, S, nat.ptr(dz), nat.stream()), "nerf_mlp_backward_tc")
+                                                 N, S, nat.ptr(dz_t), nat.stream()), "nerf_mlp_backward_tc")
+    params = model.ordered_params()
+    flat = torch.zeros(sum(p.numel() for p in params), device=ts.device, dtype=F32)
+    grads, off = [], 0
+    for p in params:
+        grads.append(flat[off:off + p.numel()].view_as(p))
+        off += p.numel()
+    arr = (ctypes.c_void_p * 20)(*[g.data_ptr() for g in grads])
+    with nat.timed_kernel("wgrad_tc_kernel", M):
+        nat.check(nat.lib().nerf_wgrad_tc(nat.ptr(acts), nat.ptr(dz_t), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, arr, nat.stream()),
+                  "nerf_wgrad_tc")
+    return grads
+
+
+def mlp_backward_library_wgrad(model, o, d, ts, sigma, rgb, acts, g_ray):
+    """Same gradients with the hand-written dgrad kernel but the weight gradients as bf16 cuBLAS GEMMs on untiled copies
+    (kept as an on-device cross-check of wgrad_tc.cu)."""
+    N, S = ts.shape[0], ts.shape[1]
+    M = N * S
+    dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
+    dz_t = torch.empty((padded_rows(M) * DZ,), device=ts.device, dtype=BF)
+    with nat.timed_kernel("mlp_tc_bwd_kernel", M):
+        nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(acts), nat.ptr(dsig), nat.ptr(drgb),
+                                                 N, S, nat.ptr(dz_t), nat.stream()), "nerf_mlp_backward_tc")
+    acts, dz = untile(acts, M, ACT), untile(dz_t, M, DZ)        # interim: the library wgrad GEMMs want row-major operands
     feat, r, dr = acts[:, 1536:1792], acts[:, 1792:1920], dz[:, 1792:1920]
     pts = (d[:, None, :] * ts + o[:, None, :]).reshape(M, 3)
     pe, de = 6 * model.position_dim, 6 * model.direction_dim
@@ -80,7 +117,7 @@ def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray):
     left = torch.zeros((16, M), device=ts.device, dtype=BF)
     left[0] = 1.0
     left[1] = dsig
-    red = torch.mm(left, acts.new_empty(0) if False else dz, out_dtype=F32)                 # row 0: column sums of dz
+    red = torch.mm(left, dz, out_dtype=F32)                                                 # row 0: column sums of dz
     bsum = red[0]
     grads = [None] * 20
     grads[0], grads[1] = wgrad(dz[:, 0:256], pe_x)[:, :pe], bsum[0:256]                     # mlp.0
@@ -102,6 +139,7 @@ def mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray):
     hand-written dgrad kernel (tests/test_gpu_training.py)."""
     N, S = ts.shape[0], ts.shape[1]
     M = N * S
+    acts = untile(acts, M, ACT)
     dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
     P = [p.detach() for p in model.ordered_params()]
     W = [P[2 * i] for i in range(10)]

@@ -110,18 +110,26 @@ int nerf_pack_weights(const float* const* params20_host, void* packed, void* str
  * Samples are given as rays + depths: sample (n,s) sits at o[n] + ts[n,s]*d[n].  sigma [N,S], rgb [N,S,3]. */
 int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, const float* ts,
                         int64_t N, int S, float* sigma, float* rgb, void* stream);
-/* Training form: also stores the bf16 activations each layer consumed, act_out [N*S, 1920] row-major (outputs of
- * mlp.0, mlp.2, mlp.4, mlp.6, feature_fn.0, feature_fn.2, feature_fn.4 at column 256*k; rgb_fn.0 at 1792). */
+/* Training form: also stores the bf16 activations each layer consumed (outputs of mlp.0, mlp.2, mlp.4, mlp.6,
+ * feature_fn.0, feature_fn.2, feature_fn.4 at feature 256*k; rgb_fn.0 at 1792).  act_out: ceil(N*S/128)*128 rows x 1920
+ * features, TILED CHUNK-MAJOR: element (row, f) at ((row/128 * 240 + f/8) * 128 + row%128) * 8 + f%8. */
 int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
                               int64_t N, int S, float* sigma, float* rgb, void* act_out, void* stream);
 /* ---- backward of H8 (dgrad chain) on the tensor cores.  packed_t = nerf_pack_weights_t image (W^T stages, bf16).
- * acts: the forward's saved activations [N*S,1920]; dsigma_pre [N*S], drgb_pre [N*S,3] from nerf_composite_backward.
- * dz_out [N*S,1920] bf16: gradient w.r.t. every layer's pre-activation, same column map as acts
- * (mlp.0 .. feature_fn.4 at 256*k, rgb_fn.0 at 1792); the weight gradients are dz^T . (layer input). */
+ * acts: the forward's saved activations (tiled chunk-major, see above); dsigma_pre [N*S], drgb_pre [N*S,3] from
+ * nerf_composite_backward.  dz_out: ceil(N*S/128)*128 rows x 1936 features bf16, tiled chunk-major with 242 chunks per
+ * tile: gradient w.r.t. every layer's pre-activation at the same feature offsets as acts (mlp.0 .. feature_fn.4 at 256*k,
+ * rgb_fn.0 at 1792) + a heads block [dsigma_pre, drgb_pre x3, 0..] at 1920; weight gradients are dz^T . (layer input). */
 size_t nerf_packed_t_bytes(void);
 int nerf_pack_weights_t(const float* const* params20_host, void* packed_t, void* stream);
 int nerf_mlp_backward_tc(const void* packed_t, const void* acts, const float* dsigma_pre, const float* drgb_pre,
                          int64_t N, int S, void* dz_out, void* stream);
+/* ---- weight / bias gradients of one network on the tensor cores: dW_l += dz_l^T . (input of layer l), db_l += sum dz_l.
+ * acts, dz: the tiled chunk-major training tensors written by nerf_mlp_forward_tc_train / nerf_mlp_backward_tc;
+ * o, d, ts as in the forward (PE(x) / PE(dir) operands are recomputed).  grads20_host: HOST array of 20 device pointers
+ * (state_dict order, fp32, nn.Linear layout), ACCUMULATED into with atomics - zero them first. */
+int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
+                  float* const* grads20_host, void* stream);
 /* Same kernel with explicit sample points [N,S,3] (the NeRFModel.forward(samples, direc) call surface). */
 int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
                                int64_t N, int S, float* sigma, float* rgb, void* stream);

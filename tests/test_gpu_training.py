@@ -122,12 +122,14 @@ def test_dgrad_kernel_matches_library_chain():
     model = net.fine_network
     sigma, rgb, acts = training.mlp_forward_train(model, o, d, ts)
     g_ray = torch.randn(N, 3, device=DEV) / N
-    got = training.mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray)
-    ref = training.mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray)
+    got = training.mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray)                   # tcgen05 dgrad + tcgen05 wgrad
+    mid = training.mlp_backward_library_wgrad(model, o, d, ts, sigma, rgb, acts, g_ray)     # tcgen05 dgrad + cuBLAS wgrad
+    ref = training.mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray)         # everything as library ops
     torch.cuda.synchronize()
     names = [n for n, _ in model.named_parameters()]
-    for name, a, b in zip(names, got, ref):
-        a, b = a.float().flatten(), b.float().flatten()
-        cos = F.cosine_similarity(a, b, dim=0).item()
-        rel = ((a - b).norm() / b.norm().clamp(min=1e-20)).item()
-        assert cos > 0.999 and rel < 0.03, f"{name}: cosine {cos:.5f} rel {rel:.4f}"
+    for name, a, m, b in zip(names, got, mid, ref):
+        a, m, b = a.float().flatten(), m.float().flatten(), b.float().flatten()
+        for tag, x, y, tol in (("wgrad kernel vs library wgrad", a, m, 0.01), ("kernels vs library chain", a, b, 0.03)):
+            cos = F.cosine_similarity(x, y, dim=0).item()
+            rel = ((x - y).norm() / y.norm().clamp(min=1e-20)).item()
+            assert cos > 0.999 and rel < tol, f"{name} ({tag}): cosine {cos:.5f} rel {rel:.4f}"
