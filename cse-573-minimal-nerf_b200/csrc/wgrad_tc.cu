@@ -8,15 +8,17 @@
 // plain 32 / 64 KB bulk copies, no transposition anywhere.
 //
 // Work decomposition (one launch per network, one CTA per SM):
-//   a "job" = one product D[128 rows of n_out] x [all k_in columns] (fp32 in TMEM), i.e. one 128-row half of a layer's dW;
-//   18 jobs (table below); each job is split-K over the 128-sample tiles among a fixed group of CTAs, the two halves of
-//   a layer walk the same tiles in adjacent CTAs so their common B operand is read from HBM once and from L2 once.
-//   At the end every CTA adds its partial D (and bias sums) to the fp32 gradients with atomics.
-// Per CTA: warps 0 and 2 issue the A / B bulk copies (2-deep ring of whole tiles), warp 1 issues tcgen05.mma
-// (M128 x N<=256 x K16, both operands MN-major, A and B from shared memory), warps 4-7 sum the dz tile's columns for the
-// bias gradient while it sits in shared memory and run the final TMEM -> atomics epilogue, warps 8-11 recompute PE(x) /
-// PE(dir) tiles for the three products whose input is a positional encoding.  The kernel is HBM-bound by design
-// (96 KB of operands per 1024 clk of MMA); its roofline is bytes / HBM bandwidth.
+//   a "job" = up to four 128-row A blocks (halves of a layer's dz, or halves of feat / r for the two small heads) that all
+//   multiply the SAME B operand (a 256-wide activation block and / or a recomputed PE tile); block i accumulates into its
+//   own TMEM region D_i[128 x (b_cols + pe_cols)] (fp32).  10 jobs (table below); each is split-K over the 128-sample
+//   tiles among a fixed group of CTAs.  Per tile a CTA reads every operand once: ~1.1 MB per tile over all jobs against
+//   0.96 MB of acts + dz, the minimum.  At the end every CTA adds its partial D (and bias sums) to the fp32 gradients with
+//   atomics.
+// Per CTA: warp 0 issues the A-block bulk copies (2 x 32 KB ring), warp 2 the B-tile copies (2 x 64 KB ring), warp 1 issues
+// tcgen05.mma (M128 x N<=256 x K16, both operands MN-major from shared memory), warps 4-7 sum the dz blocks' columns for
+// the bias gradients while they sit in shared memory and run the final TMEM -> atomics epilogue, warps 8-11 recompute the
+// PE(x) / PE(dir) tile for the products whose input is a positional encoding.  The kernel is HBM-bound by design (128 KB of
+// operands per 2048 clk of MMA); its roofline is bytes / HBM bandwidth.
 #include "mlp_tc_common.cuh"
 
 namespace nerf {
@@ -39,48 +41,48 @@ enum { SRC_ACTS = 0, SRC_DZ = 1 };
 enum { PE_NONE = 0, PE_X = 1, PE_DIR = 2 };
 enum { OUT_NORMAL = 0, OUT_DENSITY = 1, OUT_RGB = 2 };
 
+struct Block {
+    uint8_t src;          // SRC_ACTS / SRC_DZ
+    uint16_t feat;        // first of its 128 features
+    uint8_t w_param;      // weight gradient it contributes to (state_dict order 0..9)
+    uint16_t row0;        // first dW row (OUT_NORMAL) / first dW column (OUT_DENSITY)
+    uint16_t in_features; // leading dimension of that dW
+    uint16_t pe_col0;     // dW column where the PE part goes
+    uint8_t bias;         // 1: also accumulate db[w_param][row0 : row0+128] = column sums of this block
+};
 struct Job {
-    uint8_t a_src;        // where the M operand (128 features) comes from
-    uint16_t a_feat;      // its first feature
-    uint8_t b_cols;       // columns of the B block read from memory / 16 (0 = none)
+    uint8_t nA;
+    Block blk[4];
+    uint8_t b_cols16;     // columns of the B tile read from memory / 16 (0 = none)
     uint8_t b_src;
     uint16_t b_feat;
-    uint8_t pe;           // extra (or only) B operand recomputed in the kernel
+    uint8_t pe;           // PE_NONE / PE_X / PE_DIR: extra (or only) B operand recomputed in the kernel
+    uint8_t pe_valid;     // valid PE columns (60 / 24)
     uint8_t out_kind;
-    uint8_t w_param;      // index of the weight gradient (state_dict order 0..9)
-    uint16_t row0;        // first dW row of this half
-    uint16_t in_features; // leading dimension of dW
-    uint16_t pe_col0;     // dW column of the PE part, valid PE columns
-    uint8_t pe_valid;
-    uint8_t bias;         // 1: this job also produces db[row0 : row0+128] (column sums of its A operand)
+    uint8_t heads_bias;   // 1: db of the two heads = column sums of the B tile (the dz heads block)
     uint8_t ctas;         // CTAs that split this job's tiles
 };
 
 // dz feature offsets: layer k's pre-activation gradient at 256 k (k = 0..6), rgb_fn.0 at 1792, heads block at 1920.
 // acts feature offsets: output of layer k at 256 k, rgb_fn.0 output r at 1792.
-__constant__ Job c_jobs[18] = {
-    // a_src  a_feat b/16 b_src    b_feat pe      out          w  row0 in   pecol pev bias ctas
-    {SRC_DZ, 0,     0,  SRC_ACTS, 0,    PE_X,   OUT_NORMAL,  0, 0,   60,  0,   60, 1, 4},     // mlp.0 half 0
-    {SRC_DZ, 128,   0,  SRC_ACTS, 0,    PE_X,   OUT_NORMAL,  0, 128, 60,  0,   60, 1, 4},     // mlp.0 half 1
-    {SRC_DZ, 256,   16, SRC_ACTS, 0,    PE_NONE, OUT_NORMAL, 1, 0,   256, 0,   0,  1, 9},     // mlp.2
-    {SRC_DZ, 384,   16, SRC_ACTS, 0,    PE_NONE, OUT_NORMAL, 1, 128, 256, 0,   0,  1, 9},
-    {SRC_DZ, 512,   16, SRC_ACTS, 256,  PE_NONE, OUT_NORMAL, 2, 0,   256, 0,   0,  1, 9},     // mlp.4
-    {SRC_DZ, 640,   16, SRC_ACTS, 256,  PE_NONE, OUT_NORMAL, 2, 128, 256, 0,   0,  1, 9},
-    {SRC_DZ, 768,   16, SRC_ACTS, 512,  PE_NONE, OUT_NORMAL, 3, 0,   256, 0,   0,  1, 9},     // mlp.6
-    {SRC_DZ, 896,   16, SRC_ACTS, 512,  PE_NONE, OUT_NORMAL, 3, 128, 256, 0,   0,  1, 9},
-    {SRC_DZ, 1024,  16, SRC_ACTS, 768,  PE_X,   OUT_NORMAL,  4, 0,   316, 256, 60, 1, 10},    // feature_fn.0: [h3 | PE(x)]
-    {SRC_DZ, 1152,  16, SRC_ACTS, 768,  PE_X,   OUT_NORMAL,  4, 128, 316, 256, 60, 1, 10},
-    {SRC_DZ, 1280,  16, SRC_ACTS, 1024, PE_NONE, OUT_NORMAL, 5, 0,   256, 0,   0,  1, 9},     // feature_fn.2
-    {SRC_DZ, 1408,  16, SRC_ACTS, 1024, PE_NONE, OUT_NORMAL, 5, 128, 256, 0,   0,  1, 9},
-    {SRC_DZ, 1536,  16, SRC_ACTS, 1280, PE_NONE, OUT_NORMAL, 6, 0,   256, 0,   0,  1, 9},     // feature_fn.4
-    {SRC_DZ, 1664,  16, SRC_ACTS, 1280, PE_NONE, OUT_NORMAL, 6, 128, 256, 0,   0,  1, 9},
-    {SRC_DZ, 1792,  16, SRC_ACTS, 1536, PE_DIR, OUT_NORMAL,  8, 0,   280, 256, 24, 1, 12},    // rgb_fn.0: [feat | PE(dir)]
-    {SRC_ACTS, 1536, 1, SRC_DZ,   1920, PE_NONE, OUT_DENSITY, 7, 0,  256, 0,   0,  0, 4},     // density_fn.0: feat^T . heads, half 0
-    {SRC_ACTS, 1664, 1, SRC_DZ,   1920, PE_NONE, OUT_DENSITY, 7, 128, 256, 0,  0,  0, 4},
-    {SRC_ACTS, 1792, 1, SRC_DZ,   1920, PE_NONE, OUT_RGB,    9, 0,   128, 0,   0,  2, 4},     // rgb_fn.2: r^T . heads (+ head biases)
+#define NB {0, 0, 0, 0, 0, 0, 0}
+__constant__ Job c_jobs[10] = {
+    // dz0 and dz4 halves x PE(x): dW(mlp.0)[:, 0:60] and dW(feature_fn.0)[:, 256:316], and both layers' biases
+    {4, {{SRC_DZ, 0, 0, 0, 60, 0, 1}, {SRC_DZ, 128, 0, 128, 60, 0, 1}, {SRC_DZ, 1024, 4, 0, 316, 256, 1}, {SRC_DZ, 1152, 4, 128, 316, 256, 1}},
+     0, SRC_ACTS, 0, PE_X, 60, OUT_NORMAL, 0, 17},
+    {2, {{SRC_DZ, 256, 1, 0, 256, 0, 1}, {SRC_DZ, 384, 1, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 0, PE_NONE, 0, OUT_NORMAL, 0, 17},      // mlp.2
+    {2, {{SRC_DZ, 512, 2, 0, 256, 0, 1}, {SRC_DZ, 640, 2, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 256, PE_NONE, 0, OUT_NORMAL, 0, 17},    // mlp.4
+    {2, {{SRC_DZ, 768, 3, 0, 256, 0, 1}, {SRC_DZ, 896, 3, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 512, PE_NONE, 0, OUT_NORMAL, 0, 17},    // mlp.6
+    {2, {{SRC_DZ, 1024, 4, 0, 316, 0, 0}, {SRC_DZ, 1152, 4, 128, 316, 0, 0}, NB, NB}, 16, SRC_ACTS, 768, PE_NONE, 0, OUT_NORMAL, 0, 17},  // feature_fn.0 (h3 part)
+    {2, {{SRC_DZ, 1280, 5, 0, 256, 0, 1}, {SRC_DZ, 1408, 5, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1024, PE_NONE, 0, OUT_NORMAL, 0, 17}, // feature_fn.2
+    {2, {{SRC_DZ, 1536, 6, 0, 256, 0, 1}, {SRC_DZ, 1664, 6, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1280, PE_NONE, 0, OUT_NORMAL, 0, 17}, // feature_fn.4
+    {1, {{SRC_DZ, 1792, 8, 0, 280, 256, 1}, NB, NB, NB}, 16, SRC_ACTS, 1536, PE_DIR, 24, OUT_NORMAL, 0, 13},                             // rgb_fn.0: [feat | PE(dir)]
+    {2, {{SRC_ACTS, 1536, 7, 0, 256, 0, 0}, {SRC_ACTS, 1664, 7, 128, 256, 0, 0}, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_DENSITY, 0, 9},  // density_fn.0: feat^T . heads
+    {1, {{SRC_ACTS, 1792, 9, 0, 128, 0, 0}, NB, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_RGB, 1, 5},                                    // rgb_fn.2: r^T . heads (+ head biases)
 };
-constexpr int kNumJobs = 18;
-constexpr int kGridCtas = 2 * 4 + 6 * 9 + 2 * 10 + 4 * 9 + 12 + 3 * 4;     // 142
+#undef NB
+constexpr int kNumJobs = 10;
+constexpr int kGridCtas = 7 * 17 + 13 + 9 + 5;     // 146
 }  // namespace wg
 
 struct Grads { float* p[20]; };
@@ -92,50 +94,36 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + wg::kOffBars);
     uint64_t* fullA = bars;            // [2]
-    uint64_t* fullB = bars + 2;        // [2]
-    uint64_t* empty = bars + 4;        // [2]  MMA commit + 4 bias-sum warps
-    uint64_t* pe_full = bars + 6;      // [1]
-    uint64_t* pe_empty = bars + 7;     // [1]
-    uint64_t* done = bars + 8;         // [1]
+    uint64_t* emptyA = bars + 2;       // [2]  MMA commit + 4 bias-sum warps
+    uint64_t* fullB = bars + 4;        // [2]
+    uint64_t* emptyB = bars + 6;       // [2]  MMA commit (+ 4 bias-sum warps for the heads job)
+    uint64_t* pe_full = bars + 8;
+    uint64_t* pe_empty = bars + 9;
+    uint64_t* done = bars + 10;
     uint32_t* tmem_holder = (uint32_t*)(smem + wg::kOffTmemHolder);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t num_tiles = (total + 127) / 128;
 
     // which job, and which share of its tiles, this CTA owns
-    int job_idx = 0, first = 0;
-    {
-        int b = blockIdx.x;
-        // the two halves of a layer are interleaved (CTA 2i, 2i+1 walk the same tiles) so they share B through L2
-        while (job_idx < wg::kNumJobs) {
-            const bool paired = (job_idx + 1 < wg::kNumJobs) && wg::c_jobs[job_idx].w_param == wg::c_jobs[job_idx + 1].w_param &&
-                                wg::c_jobs[job_idx].row0 == 0 && wg::c_jobs[job_idx + 1].row0 == 128;
-            const int span = paired ? 2 * wg::c_jobs[job_idx].ctas : wg::c_jobs[job_idx].ctas;
-            if (b < span) {
-                if (paired) { first = b >> 1; job_idx += (b & 1); }
-                else first = b;
-                break;
-            }
-            b -= span;
-            job_idx += paired ? 2 : 1;
-        }
-    }
+    int job_idx = 0, first = blockIdx.x;
+    while (job_idx < wg::kNumJobs && first >= wg::c_jobs[job_idx].ctas) { first -= wg::c_jobs[job_idx].ctas; ++job_idx; }
     if (job_idx >= wg::kNumJobs) return;                 // spare CTAs
     const wg::Job job = wg::c_jobs[job_idx];
-    const int stride = job.ctas;
-    const int b_cols = job.b_cols * 16;
+    const int stride = job.ctas, nA = job.nA;
+    const int b_cols = job.b_cols16 * 16;
     const bool has_pe = job.pe != wg::PE_NONE;
-    const int a_chunks = (job.a_src == wg::SRC_DZ) ? pk::kDzChunks : pk::kActChunks;
+    const int region_cols = b_cols + (has_pe ? 64 : 0);  // TMEM columns per A block
     const int bsrc_chunks = (job.b_src == wg::SRC_DZ) ? pk::kDzChunks : pk::kActChunks;
-    const __nv_bfloat16* a_base = (job.a_src == wg::SRC_DZ ? dz : acts) + (int64_t)(job.a_feat >> 3) * 1024;
     const __nv_bfloat16* b_base = (job.b_src == wg::SRC_DZ ? dz : acts) + (int64_t)(job.b_feat >> 3) * 1024;
     const uint32_t b_bytes = (uint32_t)b_cols * 256u;    // 128 rows x b_cols x 2 B
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&fullA[i], 1);
+            umma::mbar_init(&emptyA[i], 5);
             umma::mbar_init(&fullB[i], 1);
-            umma::mbar_init(&empty[i], job.bias ? 5 : 1);
+            umma::mbar_init(&emptyB[i], job.heads_bias ? 5 : 1);
         }
         umma::mbar_init(pe_full, 4);
         umma::mbar_init(pe_empty, 1);
@@ -148,22 +136,35 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
-    if (warp == 0 || warp == 2) {
-        // ------------------------------------------------------------------ operand producers: warp 0 -> A tiles, warp 2 -> B tiles
+    if (warp == 0) {
+        // ------------------------------------------------------------------ A-block producer (2 x 32 KB ring)
         const bool leader = umma::elect_one();
-        if (warp == 0 || b_cols > 0) {
+        uint32_t ua = 0;
+        for (int64_t tile = first; tile < num_tiles; tile += stride) {
+            for (int i = 0; i < nA; ++i, ++ua) {
+                const uint32_t slot = ua & 1, ph = (ua >> 1) & 1;
+                umma::mbar_wait(&emptyA[slot], ph ^ 1);
+                if (leader) {
+                    const wg::Block bk = job.blk[i];
+                    const int chunks = (bk.src == wg::SRC_DZ) ? pk::kDzChunks : pk::kActChunks;
+                    const __nv_bfloat16* src = (bk.src == wg::SRC_DZ ? dz : acts) + (tile * chunks + (bk.feat >> 3)) * 1024;
+                    umma::mbar_arrive_expect_tx(&fullA[slot], wg::kABytes);
+                    umma::bulk_g2s(smem + wg::kOffA + slot * wg::kABytes, src, wg::kABytes, &fullA[slot]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ B-tile producer (2 x 64 KB ring)
+        if (b_cols > 0) {
+            const bool leader = umma::elect_one();
             uint32_t it = 0;
             for (int64_t tile = first; tile < num_tiles; tile += stride, ++it) {
                 const uint32_t slot = it & 1, ph = (it >> 1) & 1;
-                umma::mbar_wait(&empty[slot], ph ^ 1);
+                umma::mbar_wait(&emptyB[slot], ph ^ 1);
                 if (leader) {
-                    if (warp == 0) {
-                        umma::mbar_arrive_expect_tx(&fullA[slot], wg::kABytes);
-                        umma::bulk_g2s(smem + wg::kOffA + slot * wg::kABytes, a_base + tile * (int64_t)a_chunks * 1024, wg::kABytes, &fullA[slot]);
-                    } else {
-                        umma::mbar_arrive_expect_tx(&fullB[slot], b_bytes);
-                        umma::bulk_g2s(smem + wg::kOffB + slot * wg::kBBytes, b_base + tile * (int64_t)bsrc_chunks * 1024, b_bytes, &fullB[slot]);
-                    }
+                    umma::mbar_arrive_expect_tx(&fullB[slot], b_bytes);
+                    umma::bulk_g2s(smem + wg::kOffB + slot * wg::kBBytes, b_base + tile * (int64_t)bsrc_chunks * 1024, b_bytes, &fullB[slot]);
                 }
                 __syncwarp();
             }
@@ -174,27 +175,36 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
         const uint32_t kMN = umma::kIdescAMajorMN | umma::kIdescBMajorMN;
         const uint32_t idescB = umma::make_idesc_bf16(128, b_cols > 0 ? b_cols : 16) | kMN;
         const uint32_t idescPE = umma::make_idesc_bf16(128, 64) | kMN;
-        uint32_t it = 0;
+        uint32_t it = 0, ua = 0;
         for (int64_t tile = first; tile < num_tiles; tile += stride, ++it) {
-            const uint32_t slot = it & 1, ph = (it >> 1) & 1;
-            umma::mbar_wait(&fullA[slot], ph);
-            if (b_cols > 0) umma::mbar_wait(&fullB[slot], ph);
+            const uint32_t bslot = it & 1, bph = (it >> 1) & 1;
+            if (b_cols > 0) umma::mbar_wait(&fullB[bslot], bph);
             if (has_pe) umma::mbar_wait(pe_full, it & 1);
-            umma::tc_fence_after();
-            if (leader) {
-                const uint32_t a_addr = umma::smem_u32(smem + wg::kOffA + slot * wg::kABytes);
-                const uint32_t b_addr = umma::smem_u32(smem + wg::kOffB + slot * wg::kBBytes);
-                const uint32_t pe_addr = umma::smem_u32(smem + wg::kOffPE);
+            for (int i = 0; i < nA; ++i, ++ua) {
+                const uint32_t slot = ua & 1, ph = (ua >> 1) & 1;
+                umma::mbar_wait(&fullA[slot], ph);
+                umma::tc_fence_after();
+                if (leader) {
+                    const uint32_t a_addr = umma::smem_u32(smem + wg::kOffA + slot * wg::kABytes);
+                    const uint32_t b_addr = umma::smem_u32(smem + wg::kOffB + bslot * wg::kBBytes);
+                    const uint32_t pe_addr = umma::smem_u32(smem + wg::kOffPE);
+                    const uint32_t d_col = (uint32_t)(i * region_cols);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {                 // 128 samples = 8 K=16 slices, 256 B apart along the rows
-                    const uint64_t adesc = umma::make_desc_mn_interleave(a_addr + k * 256, 2048, 128);
-                    if (b_cols > 0)
-                        umma::mma_ss(tmem, adesc, umma::make_desc_mn_interleave(b_addr + k * 256, 2048, 128), idescB, (it | (uint32_t)k) != 0);
-                    if (has_pe)
-                        umma::mma_ss(tmem + (uint32_t)b_cols, adesc, umma::make_desc_mn_interleave(pe_addr + k * 256, 2048, 128), idescPE,
-                                     (it | (uint32_t)k) != 0);
+                    for (int k = 0; k < 8; ++k) {             // 128 samples = 8 K=16 slices, 256 B apart along the rows
+                        const uint64_t adesc = umma::make_desc_mn_interleave(a_addr + k * 256, 2048, 128);
+                        if (b_cols > 0)
+                            umma::mma_ss(tmem + d_col, adesc, umma::make_desc_mn_interleave(b_addr + k * 256, 2048, 128), idescB,
+                                         (it | (uint32_t)k) != 0);
+                        if (has_pe)
+                            umma::mma_ss(tmem + d_col + (uint32_t)b_cols, adesc, umma::make_desc_mn_interleave(pe_addr + k * 256, 2048, 128),
+                                         idescPE, (it | (uint32_t)k) != 0);
+                    }
+                    umma::mma_commit(&emptyA[slot]);
                 }
-                umma::mma_commit(&empty[slot]);
+                __syncwarp();
+            }
+            if (leader) {
+                if (b_cols > 0) umma::mma_commit(&emptyB[bslot]);
                 if (has_pe) umma::mma_commit(pe_empty);
             }
             __syncwarp();
@@ -241,88 +251,113 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ bias sums while the tiles are resident, then the epilogue
         const int t = (warp - 4) * 32 + lane;          // 0..127
-        float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (job.bias) {
-            // job.bias == 1: column sums of the A tile (dz half).  == 2: of the B tile's heads block (dsigma, drgb).
-            const int chunk = t >> 3, rsub = t & 7;    // 16 chunks x 8 row phases
-            uint32_t it = 0;
-            for (int64_t tile = first; tile < num_tiles; tile += stride, ++it) {
-                const uint32_t slot = it & 1, ph = (it >> 1) & 1;
-                const uint8_t* src;
-                if (job.bias == 1) { umma::mbar_wait(&fullA[slot], ph); src = smem + wg::kOffA + slot * wg::kABytes; }
-                else               { umma::mbar_wait(&fullB[slot], ph); src = smem + wg::kOffB + slot * wg::kBBytes; }
-                if (job.bias == 1 || chunk < 2) {
+        const int chunk = t >> 3, rsub = t & 7;        // 16 chunks x 8 row phases
+        float bsum[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bsum[i][j] = 0.f;
+        auto add_block = [&](const uint8_t* src, float (&acc)[8]) {
 #pragma unroll 4
-                    for (int k = 0; k < 16; ++k) {
-                        const uint4 q = *(const uint4*)(src + chunk * 2048 + (rsub + 8 * k) * 16);
-                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            for (int k = 0; k < 16; ++k) {
+                const uint4 q = *(const uint4*)(src + chunk * 2048 + (rsub + 8 * k) * 16);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            bsum[2 * j] += __uint_as_float(w[j] << 16);
-                            bsum[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-                        }
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    acc[2 * j] += __uint_as_float(w[j] << 16);
+                    acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
                 }
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&empty[slot]);
             }
+        };
+        {
+            uint32_t it = 0, ua = 0;
+            for (int64_t tile = first; tile < num_tiles; tile += stride, ++it) {
+                if (job.heads_bias) {                  // column sums of the dz heads block (the B tile): [dsigma, drgb x3, 0..]
+                    const uint32_t bslot = it & 1, bph = (it >> 1) & 1;
+                    umma::mbar_wait(&fullB[bslot], bph);
+                    if (chunk == 0) add_block(smem + wg::kOffB + bslot * wg::kBBytes, bsum[3]);
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(&emptyB[bslot]);
+                }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                bsum[j] += __shfl_xor_sync(kFull, bsum[j], 1);
-                bsum[j] += __shfl_xor_sync(kFull, bsum[j], 2);
-                bsum[j] += __shfl_xor_sync(kFull, bsum[j], 4);
-            }
-            if (rsub == 0) {
-                if (job.bias == 1) {
-                    float* db = G.p[2 * job.w_param + 1] + job.row0 + chunk * 8;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) atomicAdd(db + j, bsum[j]);
-                } else if (chunk == 0) {               // heads block: [dsigma, drgb0, drgb1, drgb2]
-                    atomicAdd(G.p[15], bsum[0]);
-                    atomicAdd(G.p[19] + 0, bsum[1]);
-                    atomicAdd(G.p[19] + 1, bsum[2]);
-                    atomicAdd(G.p[19] + 2, bsum[3]);
+                for (int i = 0; i < 4; ++i) {
+                    if (i < nA) {
+                        const uint32_t slot = ua & 1, ph = (ua >> 1) & 1;
+                        umma::mbar_wait(&fullA[slot], ph);
+                        if (job.blk[i].bias) add_block(smem + wg::kOffA + slot * wg::kABytes, bsum[i]);
+                        __syncwarp();
+                        if (lane == 0) umma::mbar_arrive(&emptyA[slot]);
+                        ++ua;
+                    }
                 }
             }
         }
-        // ---- epilogue: D[m = lane (row of this half), n] -> atomics into dW (skipped by CTAs that had no tile)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                bsum[i][j] += __shfl_xor_sync(kFull, bsum[i][j], 1);
+                bsum[i][j] += __shfl_xor_sync(kFull, bsum[i][j], 2);
+                bsum[i][j] += __shfl_xor_sync(kFull, bsum[i][j], 4);
+            }
+        if (rsub == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < nA && job.blk[i].bias) {
+                    float* db = G.p[2 * job.blk[i].w_param + 1] + job.blk[i].row0 + chunk * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) atomicAdd(db + j, bsum[i][j]);
+                }
+            }
+            if (job.heads_bias && chunk == 0) {
+                atomicAdd(G.p[15], bsum[3][0]);                        // density_fn.0.bias
+                atomicAdd(G.p[19] + 0, bsum[3][1]);                    // rgb_fn.2.bias
+                atomicAdd(G.p[19] + 1, bsum[3][2]);
+                atomicAdd(G.p[19] + 2, bsum[3][3]);
+            }
+        }
+        // ---- epilogue: D_i[m = lane (row of block i), n] -> atomics into dW (skipped by CTAs that had no tile)
         umma::mbar_wait(done, 0);
         umma::tc_fence_after();
         if (first < num_tiles) {
-        const int m = (warp & 3) * 32 + lane;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        float* dW = G.p[2 * job.w_param];
-        if (job.out_kind == wg::OUT_NORMAL) {
-            float* rowp = dW + (size_t)(job.row0 + m) * job.in_features;
-            for (int c0 = 0; c0 < b_cols; c0 += 32) {
-                uint32_t v[32];
-                umma::tmem_ld32(tmem + lane_base + c0, v);
-                umma::tmem_wait_ld();
+            const int m = (warp & 3) * 32 + lane;
+            const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+            for (int i = 0; i < nA; ++i) {
+                const wg::Block bk = job.blk[i];
+                float* dW = G.p[2 * bk.w_param];
+                const uint32_t d_col = (uint32_t)(i * region_cols);
+                if (job.out_kind == wg::OUT_NORMAL) {
+                    float* rowp = dW + (size_t)(bk.row0 + m) * bk.in_features;
+                    for (int c0 = 0; c0 < b_cols; c0 += 32) {
+                        uint32_t v[32];
+                        umma::tmem_ld32(tmem + lane_base + d_col + c0, v);
+                        umma::tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(rowp + c0 + j, __uint_as_float(v[j]));
-            }
-            if (has_pe) {
-                float* pep = rowp + job.pe_col0;
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t v[32];
-                    umma::tmem_ld32(tmem + lane_base + b_cols + c0, v);
+                        for (int j = 0; j < 32; ++j) atomicAdd(rowp + c0 + j, __uint_as_float(v[j]));
+                    }
+                    if (has_pe) {
+                        float* pep = rowp + bk.pe_col0;
+                        for (int c0 = 0; c0 < 64; c0 += 32) {
+                            uint32_t v[32];
+                            umma::tmem_ld32(tmem + lane_base + d_col + b_cols + c0, v);
+                            umma::tmem_wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < job.pe_valid) atomicAdd(pep + c0 + j, __uint_as_float(v[j]));
+                        }
+                    }
+                } else {
+                    uint32_t v[4];
+                    umma::tmem_ld4(tmem + lane_base + d_col, v);
                     umma::tmem_wait_ld();
+                    if (job.out_kind == wg::OUT_DENSITY) {
+                        atomicAdd(dW + bk.row0 + m, __uint_as_float(v[0]));                      // density_fn.0.weight [1,256]
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < job.pe_valid) atomicAdd(pep + c0 + j, __uint_as_float(v[j]));
+                        for (int c = 0; c < 3; ++c) atomicAdd(dW + c * 128 + m, __uint_as_float(v[1 + c]));   // rgb_fn.2.weight [3,128]
+                    }
                 }
             }
-        } else {
-            uint32_t v[4];
-            umma::tmem_ld4(tmem + lane_base, v);
-            umma::tmem_wait_ld();
-            if (job.out_kind == wg::OUT_DENSITY) {
-                atomicAdd(dW + job.row0 + m, __uint_as_float(v[0]));                     // density_fn.0.weight [1,256]
-            } else {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) atomicAdd(dW + c * 128 + m, __uint_as_float(v[1 + c]));   // rgb_fn.2.weight [3,128]
-            }
-        }
         }
     }
     umma::tc_fence_before();
