@@ -224,7 +224,9 @@ def bench_train(args, rank, world, dev):
     return {"metric": "rays/sec train (device-timed)", "value": n * world / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
             "steps": steps, "rays_per_step_per_gpu": n, "final_loss": float(loss.detach()),
             "algorithmic_tflops_per_gpu": tfl, "frac_of_sustained_peak": tfl / pk["tflops_sustained"],
-            "backward": "compositing backward hand-written; dgrad/wgrad GEMMs via cuBLAS bf16 (round-1 interim)",
+            "backward": "hand-written: composite_backward_kernel, mlp_tc_bwd_kernel (tcgen05 dgrad chain), "
+                        "wgrad_tc_kernel (tcgen05 wgrad + bias sums); Adam = torch fused",
+            "hbm_bytes_per_step_per_gpu_est": int(n * 256 * (3840 + 240 + 240 + 3872 + 1.14 * 7712)),
             "collective": "one NCCL all-reduce of the 924 680-float flat gradient buffer per step" if world > 1 else None}
 
 

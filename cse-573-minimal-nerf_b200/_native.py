@@ -37,7 +37,7 @@ _PROTOTYPES = {
     "nerf_packed_bytes": (ctypes.c_size_t, []),
     "nerf_pack_weights": (_int, [_vp, _vp, _vp]),
     "nerf_mlp_forward_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
-    "nerf_mlp_forward_tc_train": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
+    "nerf_mlp_forward_tc_train": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     "nerf_packed_t_bytes": (ctypes.c_size_t, []),
     "nerf_pack_weights_t": (_int, [_vp, _vp, _vp]),
     "nerf_mlp_backward_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1)
 mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_rays, const float* __restrict__ d_rays,
               const float* __restrict__ ts, const float* __restrict__ samples, int64_t total, int S,
               float* __restrict__ sigma_out, float* __restrict__ rgb_out, __nv_bfloat16* __restrict__ act_out,
-              long long* __restrict__ dbg) {
+              unsigned long long* __restrict__ mask_out, long long* __restrict__ dbg) {
     long long prof[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -314,6 +314,14 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                 // (pack_layout.cuh): outputs of mlp.0..feature_fn.4 at feature 256*layer, rgb_fn.0 at 1792.  Lanes are
                 // consecutive rows, so every 16-byte store of the warp lands in one contiguous 512-byte run.  Rows past
                 // `total` are stored too (finite values; their dz is zero) so wgrad can read whole tiles.
+                unsigned long long mbits = 0ull;
+                if (act_out != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        mbits |= (unsigned long long)((p[j] & 0x00007FFFu) != 0u) << (2 * j);
+                        mbits |= (unsigned long long)((p[j] & 0x7FFF0000u) != 0u) << (2 * j + 1);
+                    }
+                }
                 uint4* act_chunk = nullptr;
                 if (act_out != nullptr)
                     act_chunk = (uint4*)(act_out + pk::tiled_offset(row, (s < 14 ? layer * 256 + nhalf * 128 : 1792) + wh * 64, pk::kActChunks));
@@ -333,6 +341,14 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
                 if (act_chunk) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) act_chunk[(4 + j) * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        mbits |= (unsigned long long)((p[j] & 0x00007FFFu) != 0u) << (32 + 2 * j);
+                        mbits |= (unsigned long long)((p[j] & 0x7FFF0000u) != 0u) << (33 + 2 * j);
+                    }
+                    // sign bits of this row's 64 outputs (what the dgrad kernel masks with): 8 B instead of 128 B to re-read
+                    const int blk = ((s < 14 ? layer * 256 + nhalf * 128 : 1792) + wh * 64) >> 6;
+                    mask_out[((row >> 7) * pk::kMaskWords + blk) * 128 + (row & 127)] = mbits;
                 }
                 umma::tmem_wait_st();
                 umma::tc_fence_before();
@@ -407,7 +423,7 @@ static bool use_pair_kernel() {
 
 static int launch_mlp_tc(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
                          int64_t N, int S, float* sigma, float* rgb, void* stream, long long* dbg = nullptr,
-                         void* act_out = nullptr) {
+                         void* act_out = nullptr, void* mask_out = nullptr) {
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_forward_tc: bad size N=%lld S=%d", (long long)N, S);
     if (N == 0) return 0;
     NERF_REQUIRE(packed && d && sigma && rgb, "nerf_mlp_forward_tc: null pointer");
@@ -432,10 +448,10 @@ static int launch_mlp_tc(const void* packed, const float* o, const float* d, con
     }
     if (dbg)
         mlp_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, o, d, ts, samples,
-                                                                                        total, S, sigma, rgb, (__nv_bfloat16*)act_out, dbg);
+                                                                                        total, S, sigma, rgb, (__nv_bfloat16*)act_out, (unsigned long long*)mask_out, dbg);
     else
         mlp_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, o, d, ts, samples,
-                                                                                         total, S, sigma, rgb, (__nv_bfloat16*)act_out, nullptr);
+                                                                                         total, S, sigma, rgb, (__nv_bfloat16*)act_out, (unsigned long long*)mask_out, nullptr);
     return check_launch("nerf_mlp_forward_tc");
 }
 
@@ -460,7 +476,7 @@ extern "C" int nerf_mlp_forward_tc_points(const void* packed, const float* sampl
 // feature_fn.0, feature_fn.2, feature_fn.4 at feature 256*k, rgb_fn.0 at 1792) in the tiled chunk-major layout of
 // pack_layout.cuh; act_out holds ceil(N*S/128)*128 rows x 1920 features.
 extern "C" int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
-                                         int64_t N, int S, float* sigma, float* rgb, void* act_out, void* stream) {
-    NERF_REQUIRE(N == 0 || act_out, "nerf_mlp_forward_tc_train: act_out is NULL");
-    return launch_mlp_tc(packed, o, d, ts, nullptr, N, S, sigma, rgb, stream, nullptr, act_out);
+                                         int64_t N, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream) {
+    NERF_REQUIRE(N == 0 || (act_out && mask_out), "nerf_mlp_forward_tc_train: act_out / mask_out is NULL");
+    return launch_mlp_tc(packed, o, d, ts, nullptr, N, S, sigma, rgb, stream, nullptr, act_out, mask_out);
 }

@@ -8,7 +8,7 @@
 //     dz4 .. dz0 likewise through feature_fn.2, feature_fn.0 (h columns), mlp.6, mlp.4, mlp.2     steps 4..13
 //   every dz is written to global (bf16, tiled chunk-major like the saved activations, pack_layout.cuh) for wgrad,
 //   plus a 16-wide heads block [dsigma_pre, drgb_pre, 0..] at features 1920..1935.
-// ReLU masks come from the forward's saved activations (prefetched into registers before the accumulator wait).
+// ReLU masks are the 64-bit sign words the forward kernel wrote per (row, 64-feature block): 8 B instead of 128 B per step.
 // mlp.0's dgrad (d PE) is not needed: the inputs carry no gradient.
 #include "mlp_tc_common.cuh"
 
@@ -38,7 +38,7 @@ static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 constexpr int kMergedStagesT = pk::kStagesT / 2;
 
 __global__ void __launch_bounds__(tb::kThreads, 1)
-mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __restrict__ acts,
+mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const unsigned long long* __restrict__ masks,
                   const float* __restrict__ dsigma_pre, const float* __restrict__ drgb_pre, int64_t total,
                   __nv_bfloat16* __restrict__ dz_out) {
     extern __shared__ uint8_t smem_raw[];
@@ -182,19 +182,15 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
                 uint32_t v[32];
-                uint4 m[8];                                              // r[row, 64kb : 64kb+64] (bf16) for the ReLU mask
-                const uint4* msrc = (const uint4*)(acts + pk::tiled_offset(row, 1792 + kb * 64, pk::kActChunks));
-#pragma unroll
-                for (int j = 0; j < 8; ++j) m[j] = msrc[j * 128];
-                const uint32_t* mw = (const uint32_t*)m;
+                // sign bits of r[row, 64kb : 64kb+64] (rgb_fn.0's ReLU output), written by the forward kernel
+                const unsigned long long mb = masks[((row >> 7) * pk::kMaskWords + 28 + kb) * 128 + (row & 127)];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int k = kb * 64 + 2 * j;
                     float a = g0 * W9[k] + g1 * W9[128 + k] + g2 * W9[256 + k];            // nerf_model.py:358 backward
                     float b = g0 * W9[k + 1] + g1 * W9[128 + k + 1] + g2 * W9[256 + k + 1];
-                    // saved r is post-ReLU (>= 0): positive <=> low/high bf16 is neither +0 nor -0
-                    if ((mw[j] & 0x00007FFFu) == 0u) a = 0.f;
-                    if ((mw[j] & 0x7FFF0000u) == 0u) b = 0.f;
+                    if (!((mb >> (2 * j)) & 1ull)) a = 0.f;
+                    if (!((mb >> (2 * j + 1)) & 1ull)) b = 0.f;
                     v[j] = umma::pack_bf16(a, b);
                 }
                 store_row_sw128(smem + tb::kOffDr + pb * 32768 + kb * 16384, r, v);
@@ -230,13 +226,8 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
                 const int j = 6 - (s >> 1);                 // output: dz_j (gradient w.r.t. the pre-activation of layer j)
                 const int col0 = nhalf * 128 + wh * 64;     // first of this warp's 64 feature columns
                 // ReLU mask source: saved output of layer j (post-ReLU), except dz6 (feature_fn.4 is linear)
-                uint4 m[8];
-                if (j < 6) {
-                    const uint4* msrc = (const uint4*)(acts + pk::tiled_offset(row, j * 256 + col0, pk::kActChunks));
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) m[t] = msrc[t * 128];
-                }
-                const uint32_t* mw = (const uint32_t*)m;
+                unsigned long long mb = 0ull;
+                if (j < 6) mb = masks[((row >> 7) * pk::kMaskWords + ((j * 256 + col0) >> 6)) * 128 + (row & 127)];
                 umma::mbar_wait(&dfull[gs & 1], (uint32_t)((gs >> 1) & 1));
                 umma::tc_fence_after();
                 const uint32_t d_addr = tmem + lane_base + tb::kColD + 128u * (uint32_t)(gs & 1) + (uint32_t)(wh * 64);
@@ -254,8 +245,8 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
                         a = fmaf(dsg, w7[col0 + 2 * t], a);
                         b = fmaf(dsg, w7[col0 + 2 * t + 1], b);
                     } else {
-                        if ((mw[t] & 0x00007FFFu) == 0u) a = 0.f;
-                        if ((mw[t] & 0x7FFF0000u) == 0u) b = 0.f;
+                        if (!((mb >> (2 * t)) & 1ull)) a = 0.f;
+                        if (!((mb >> (2 * t + 1)) & 1ull)) b = 0.f;
                     }
                     p[t] = umma::pack_bf16(a, b);
                 }
@@ -286,12 +277,12 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const __nv_bfloat16* __r
 
 using namespace nerf;
 
-extern "C" int nerf_mlp_backward_tc(const void* packed_t, const void* acts, const float* dsigma_pre, const float* drgb_pre,
+extern "C" int nerf_mlp_backward_tc(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre,
                                     int64_t N, int S, void* dz_out, void* stream) {
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_backward_tc: bad size");
     if (N == 0) return 0;
-    NERF_REQUIRE(packed_t && acts && dsigma_pre && drgb_pre && dz_out, "nerf_mlp_backward_tc: null pointer");
-    NERF_REQUIRE(((uintptr_t)packed_t & 127) == 0 && ((uintptr_t)acts & 15) == 0 && ((uintptr_t)dz_out & 15) == 0,
+    NERF_REQUIRE(packed_t && masks && dsigma_pre && drgb_pre && dz_out, "nerf_mlp_backward_tc: null pointer");
+    NERF_REQUIRE(((uintptr_t)packed_t & 127) == 0 && ((uintptr_t)masks & 7) == 0 && ((uintptr_t)dz_out & 15) == 0,
                  "nerf_mlp_backward_tc: misaligned buffer");
     static thread_local bool attr_set = false;
     if (!attr_set) {
@@ -303,6 +294,6 @@ extern "C" int nerf_mlp_backward_tc(const void* packed_t, const void* acts, cons
     const int64_t tiles = (total + tb::kTileM - 1) / tb::kTileM;
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
     mlp_tc_bwd_kernel<<<grid, tb::kThreads, tb::kSmemBytes, (cudaStream_t)stream>>>(
-        (const uint8_t*)packed_t, (const __nv_bfloat16*)acts, dsigma_pre, drgb_pre, total, (__nv_bfloat16*)dz_out);
+        (const uint8_t*)packed_t, (const unsigned long long*)masks, dsigma_pre, drgb_pre, total, (__nv_bfloat16*)dz_out);
     return check_launch("nerf_mlp_backward_tc");
 }

@@ -58,6 +58,9 @@ constexpr int kActFeatures = 1920;   // saved bf16 activations per sample (train
 // the features, 128 B along the rows) that wgrad (contraction over rows) consumes.
 // dz has two extra chunks (features 1920..1935): [dsigma_pre, drgb_pre x3, 0 ...] in bf16, the A/B operand of the two
 // head weight gradients.
+// ReLU sign bits for the dgrad kernel: one 64-bit word per (row, 64-feature block), bit i = [activation 64b+i > 0];
+// word index ((row/128) * kMaskWords + b) * 128 + row%128, b = feature/64 (30 blocks: 28 hidden + 2 of rgb_fn.0's output).
+constexpr int kMaskWords = kActFeatures / 64;       // 30
 constexpr int kActChunks = kActFeatures / 8;        // 240
 constexpr int kDzFeatures = kActFeatures + 16;      // 1936
 constexpr int kDzChunks = kDzFeatures / 8;          // 242

@@ -177,6 +177,13 @@ class NeRFNetwork(LightningModule):
                      "coarse_weights": c["weights"], "coarse_sigma": aux["c_sigma"], "fine_sigma": aux["f_sigma"],
                      "coarse_rgb": aux["c_rgb"], "fine_rgb": aux["f_rgb"]}
 
+    def invalidate_packed_weights(self):
+        """Force a re-pack of the bf16 weight images on the next forward / backward (call after changing parameters
+        through anything that does not bump tensor versions)."""
+        for net in (self.coarse_network, self.fine_network):
+            net._packed_key = None
+            net._packed_t_key = None
+
     def _coarse_ts(self, o, d, u_c):
         N, C = u_c.shape
         t_base, step = nerf_helpers._strata(self.near, self.far, C, o.device)
@@ -188,7 +195,10 @@ class NeRFNetwork(LightningModule):
     def configure_optimizers(self):
         start_lr, end_lr, num_epochs = 5e-4, 5e-5, 1200
         gamma = (end_lr / start_lr) ** (1 / num_epochs)
-        optimizer = torch.optim.Adam(self.parameters(), lr=start_lr)
+        optimizer = torch.optim.Adam(self.parameters(), lr=start_lr, fused=all(p.is_cuda for p in self.parameters()))
+        # the fused multi-tensor update does not bump the parameters' version counters, which is what the packed
+        # bf16 weight images are keyed on: drop them explicitly after every step
+        optimizer.register_step_post_hook(lambda *args, **kwargs: self.invalidate_packed_weights())
         lr_decay = torch.optim.lr_scheduler.ExponentialLR(optimizer=optimizer, gamma=gamma)
         return {'optimizer': optimizer, 'lr_scheduler': lr_decay}
 

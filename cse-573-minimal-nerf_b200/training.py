@@ -41,18 +41,19 @@ def _pe(x, L):
 
 
 def mlp_forward_train(model, o, d, ts):
-    """Fused MLP in training form.  Returns sigma [N,S,1], rgb [N,S,3] and the saved bf16 activations in the tiled
-    chunk-major layout (ceil(N*S/128)*128 rows x 1920 features, flat)."""
+    """Fused MLP in training form.  Returns sigma [N,S,1], rgb [N,S,3] and saved = (bf16 activations in the tiled
+    chunk-major layout, ceil(N*S/128)*128 rows x 1920 features, flat; ReLU sign words for the dgrad kernel)."""
     N, S = ts.shape[0], ts.shape[1]
     sigma = torch.empty((N, S, 1), device=ts.device, dtype=F32)
     rgb = torch.empty((N, S, 3), device=ts.device, dtype=F32)
     acts = torch.empty((padded_rows(N * S) * ACT,), device=ts.device, dtype=BF)
+    masks = torch.empty((padded_rows(N * S) * (ACT // 64),), device=ts.device, dtype=torch.int64)   # ReLU sign words for dgrad
     packed = model.packed_weights()
     with nat.timed_kernel("mlp_tc_kernel(train)", N * S):
         nat.check(nat.lib().nerf_mlp_forward_tc_train(nat.ptr(packed), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S,
-                                                      nat.ptr(sigma), nat.ptr(rgb), nat.ptr(acts), nat.stream()),
+                                                      nat.ptr(sigma), nat.ptr(rgb), nat.ptr(acts), nat.ptr(masks), nat.stream()),
                   "nerf_mlp_forward_tc_train")
-    return sigma, rgb, acts
+    return sigma, rgb, (acts, masks)
 
 
 def composite_backward(sigma, rgb, ts, g_ray):
@@ -69,12 +70,13 @@ def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray):
     """Gradients of one network's 20 parameters (state_dict order) given dL/d(ray colour) [N,3]: all hand-written kernels -
     compositing backward, tcgen05 dgrad chain (mlp_tc_bwd.cu), tcgen05 wgrad + bias sums (wgrad_tc.cu)."""
     import ctypes
+    acts, masks = acts
     N, S = ts.shape[0], ts.shape[1]
     M = N * S
     dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
     dz_t = torch.empty((padded_rows(M) * DZ,), device=ts.device, dtype=BF)
     with nat.timed_kernel("mlp_tc_bwd_kernel", M):
-        nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(acts), nat.ptr(dsig), nat.ptr(drgb),
+        nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb),
                                                  N, S, nat.ptr(dz_t), nat.stream()), "nerf_mlp_backward_tc")
     params = model.ordered_params()
     flat = torch.zeros(sum(p.numel() for p in params), device=ts.device, dtype=F32)
@@ -92,12 +94,13 @@ def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray):
 def mlp_backward_library_wgrad(model, o, d, ts, sigma, rgb, acts, g_ray):
     """Same gradients with the hand-written dgrad kernel but the weight gradients as bf16 cuBLAS GEMMs on untiled copies
     (kept as an on-device cross-check of wgrad_tc.cu)."""
+    acts, masks = acts
     N, S = ts.shape[0], ts.shape[1]
     M = N * S
     dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
     dz_t = torch.empty((padded_rows(M) * DZ,), device=ts.device, dtype=BF)
     with nat.timed_kernel("mlp_tc_bwd_kernel", M):
-        nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(acts), nat.ptr(dsig), nat.ptr(drgb),
+        nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb),
                                                  N, S, nat.ptr(dz_t), nat.stream()), "nerf_mlp_backward_tc")
     acts, dz = untile(acts, M, ACT), untile(dz_t, M, DZ)        # interim: the library wgrad GEMMs want row-major operands
     feat, r, dr = acts[:, 1536:1792], acts[:, 1792:1920], dz[:, 1792:1920]
@@ -139,7 +142,7 @@ def mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray):
     hand-written dgrad kernel (tests/test_gpu_training.py)."""
     N, S = ts.shape[0], ts.shape[1]
     M = N * S
-    acts = untile(acts, M, ACT)
+    acts = untile(acts[0], M, ACT)
     dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
     P = [p.detach() for p in model.ordered_params()]
     W = [P[2 * i] for i in range(10)]

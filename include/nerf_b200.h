@@ -113,16 +113,18 @@ int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, cons
 /* Training form: also stores the bf16 activations each layer consumed (outputs of mlp.0, mlp.2, mlp.4, mlp.6,
  * feature_fn.0, feature_fn.2, feature_fn.4 at feature 256*k; rgb_fn.0 at 1792).  act_out: ceil(N*S/128)*128 rows x 1920
  * features, TILED CHUNK-MAJOR: element (row, f) at ((row/128 * 240 + f/8) * 128 + row%128) * 8 + f%8. */
+/* mask_out: ceil(N*S/128)*128 x 30 uint64 sign words, word ((row/128)*30 + f/64)*128 + row%128, bit i = [act(row, 64*(f/64)+i) > 0]:
+ * all the dgrad kernel needs from the activations. */
 int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
-                              int64_t N, int S, float* sigma, float* rgb, void* act_out, void* stream);
+                              int64_t N, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream);
 /* ---- backward of H8 (dgrad chain) on the tensor cores.  packed_t = nerf_pack_weights_t image (W^T stages, bf16).
- * acts: the forward's saved activations (tiled chunk-major, see above); dsigma_pre [N*S], drgb_pre [N*S,3] from
+ * masks: the forward's ReLU sign words (see above); dsigma_pre [N*S], drgb_pre [N*S,3] from
  * nerf_composite_backward.  dz_out: ceil(N*S/128)*128 rows x 1936 features bf16, tiled chunk-major with 242 chunks per
  * tile: gradient w.r.t. every layer's pre-activation at the same feature offsets as acts (mlp.0 .. feature_fn.4 at 256*k,
  * rgb_fn.0 at 1792) + a heads block [dsigma_pre, drgb_pre x3, 0..] at 1920; weight gradients are dz^T . (layer input). */
 size_t nerf_packed_t_bytes(void);
 int nerf_pack_weights_t(const float* const* params20_host, void* packed_t, void* stream);
-int nerf_mlp_backward_tc(const void* packed_t, const void* acts, const float* dsigma_pre, const float* drgb_pre,
+int nerf_mlp_backward_tc(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre,
                          int64_t N, int S, void* dz_out, void* stream);
 /* ---- weight / bias gradients of one network on the tensor cores: dW_l += dz_l^T . (input of layer l), db_l += sum dz_l.
  * acts, dz: the tiled chunk-major training tensors written by nerf_mlp_forward_tc_train / nerf_mlp_backward_tc;
