@@ -27,6 +27,7 @@ class JsonLogger:
 
     def log_hyperparams(self, args):
         self.fh.write(json.dumps({"hyperparams": {k: str(v) for k, v in vars(args).items()}}) + "\n")
+        self.fh.flush()
 
     def log_metrics(self, metrics, step):
         self.fh.write(json.dumps({"step": step, **metrics}) + "\n")
@@ -79,7 +80,7 @@ class Trainer:
         self.last_checkpoint = None
 
     def record(self, name, value):
-        self._metrics[name] = float(value) if torch.is_tensor(value) and value.numel() == 1 else value
+        self._metrics[name] = float(value.detach()) if torch.is_tensor(value) and value.numel() == 1 else value
 
     def checkpoint_dir(self):
         run = getattr(self.logger, "name", "run") if self.logger is not None else "run"
