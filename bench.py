@@ -128,14 +128,14 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     v = n / dt
     sample = f"one {n}-ray chunk of the {args.hw}x{args.hw} frame per step (no_grad), CPU oracle port of the reference"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "rays/sec render (device-timed)", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def workload_config(args):
@@ -230,7 +230,20 @@ def bench_train(args, rank, world, dev):
             "collective": "one NCCL all-reduce of the 924 680-float flat gradient buffer per step" if world > 1 else None}
 
 
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else libraries print (e.g. NCCL's version banner, which is a
+    C-level printf) has been routed to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                # fd 1 -> stderr for the rest of the process
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -249,7 +262,7 @@ def main():
         return
 
     import torch.distributed as dist
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    os.environ.pop("NCCL_DEBUG", None)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -372,7 +385,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

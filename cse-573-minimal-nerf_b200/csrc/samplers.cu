@@ -224,7 +224,75 @@ fine_sample_kernel(const float* __restrict__ o, const float* __restrict__ d, con
 }
 
 // -------------------------------------------------------------------------------------- K4 merge sort
-// One warp per ray, enumeration sort in shared memory: rank(e) = #{j : v_j < v_e or (v_j == v_e and j < e)}.
+// Fast path (A + B <= 256): one warp per ray, the ray's depths padded with +inf to 256 and sorted by a bitonic network held
+// in registers: element e = 32 j + lane lives in register j of that lane, so compare distances >= 32 are register-to-register
+// and distances < 32 are one __shfl_xor each.  Sorting values only - equal depths are interchangeable - so the result is the
+// same multiset order torch.sort produces.
+__device__ __forceinline__ void cmpx(float& a, float& b, bool up) {
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = up ? lo : hi;
+    b = up ? hi : lo;
+}
+
+__global__ void __launch_bounds__(kThreads)
+merge_sort256_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ ts_a, int A,
+                     const float* __restrict__ ts_b, int B, int64_t N, float* __restrict__ ts_sorted,
+                     float* __restrict__ samples_sorted) {
+    const int S = A + B;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t n = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); n < N; n += warps) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = 32 * j + lane;
+            v[j] = (e < A) ? ts_a[n * A + e] : (e < S ? ts_b[n * B + (e - A)] : __int_as_float(0x7f800000));   // nerf_model.py:117
+        }
+#pragma unroll
+        for (int k = 2; k <= 256; k <<= 1) {
+#pragma unroll
+            for (int dist = k >> 1; dist >= 1; dist >>= 1) {
+                if (dist >= 32) {
+                    const int dj = dist >> 5;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if ((j & dj) == 0) {
+                            const bool up = (((32 * j + lane) & k) == 0);
+                            cmpx(v[j], v[j | dj], up);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = 32 * j + lane;
+                        const float other = __shfl_xor_sync(kFull, v[j], dist);
+                        const bool up = ((e & k) == 0);
+                        const bool lower = ((lane & dist) == 0);          // this lane holds the lower-index element of the pair
+                        v[j] = (up == lower) ? fminf(v[j], other) : fmaxf(v[j], other);
+                    }
+                }
+            }
+        }
+        const float ox = o ? o[n * 3] : 0.f, oy = o ? o[n * 3 + 1] : 0.f, oz = o ? o[n * 3 + 2] : 0.f;
+        const float dx = d ? d[n * 3] : 0.f, dy = d ? d[n * 3 + 1] : 0.f, dz = d ? d[n * 3 + 2] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = 32 * j + lane;
+            if (e < S) {
+                const float t = v[j];
+                ts_sorted[n * S + e] = t;
+                if (samples_sorted) {
+                    float* p = samples_sorted + (n * S + e) * 3;
+                    p[0] = __fadd_rn(ox, __fmul_rn(t, dx));
+                    p[1] = __fadd_rn(oy, __fmul_rn(t, dy));
+                    p[2] = __fadd_rn(oz, __fmul_rn(t, dz));
+                }
+            }
+        }
+    }
+}
+
+// General path (A + B <= 1024): one warp per ray, enumeration sort in shared memory: rank(e) = #{j : v_j < v_e or (v_j == v_e and j < e)}.
 // Dynamic shared memory per warp: vals[S] then sorted[S].
 __global__ void __launch_bounds__(kThreads)
 merge_sort_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ ts_a, int A,
@@ -435,6 +503,11 @@ extern "C" int nerf_merge_sort(const float* o, const float* d, const float* ts_a
     if (N == 0) return 0;
     NERF_REQUIRE(ts_a && ts_b && ts_sorted, "nerf_merge_sort: null pointer");
     NERF_REQUIRE(!samples_sorted || (o && d), "nerf_merge_sort: samples_sorted needs o and d");
+    if (A + B <= 256) {
+        merge_sort256_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(o, d, ts_a, A, ts_b, B, N, ts_sorted,
+                                                                                            samples_sorted);
+        return check_launch("nerf_merge_sort");
+    }
     const size_t smem = (size_t)kWarpsPerBlock * 2 * (A + B) * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     merge_sort_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, smem, (cudaStream_t)stream>>>(

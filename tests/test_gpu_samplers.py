@@ -118,9 +118,13 @@ def test_merge_sort(golden, mods):
     b = torch.tensor([[3.0, 0.5]], device=DEV).view(1, 2, 1)
     _, ts = h.merge_samples(torch.zeros(1, 3, device=DEV), torch.ones(1, 3, device=DEV), a, b)
     assert ts.flatten().tolist() == [0.5, 1.0, 3.0, 3.0, 3.0, 5.0]
-    # the sorted depths the reference's forward produced (captured inside NeRFNetwork.forward)
-    for kind, seed in (("init", 3), ("dense", 4)):
-        pass   # covered end-to-end in test_gpu_network.py
+    # general path (A + B > 256, enumeration sort in shared memory) and odd sizes of the register bitonic path
+    for A, B in ((300, 77), (5, 2), (255, 1), (1, 31)):
+        ta = torch.rand(33, A, 1, device=DEV) * 4 + 2
+        tb = torch.sort(torch.rand(33, B, 1, device=DEV) * 4 + 2, dim=1).values
+        ta[:, :: 3] = tb[:, :1]                                           # plenty of exact ties
+        _, ts = h.merge_samples(torch.zeros(33, 3, device=DEV), torch.ones(33, 3, device=DEV), ta, tb, want_points=False)
+        assert torch.equal(ts, torch.sort(torch.cat([ta, tb], 1), dim=1).values)
 
 
 def test_sampler_properties_full_size(mods):
