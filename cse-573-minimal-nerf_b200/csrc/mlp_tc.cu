@@ -409,6 +409,8 @@ mlp_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_ra
 namespace nerf {
 int launch_mlp_tc2(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
                    int64_t total, int S, float* sigma, float* rgb, void* stream, long long* dbg);
+int launch_mlp_tc3(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
+                   int64_t total, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream, long long* dbg);
 }
 
 using namespace nerf;
@@ -418,6 +420,13 @@ using namespace nerf;
 // loop is latency-bound and the pair's cross-CTA signalling lengthens it more than the halved weight traffic saves.
 static bool use_pair_kernel() {
     static const bool v = [] { const char* e = getenv("NERF_TC_PAIR"); return e && e[0] == '1'; }();
+    return v;
+}
+
+// NERF_TC_ONE_TILE=1 selects the one-tile-per-CTA schedule of this file; the default is the two-tile schedule of
+// mlp_tc3.cu (shared weight stages, the dependency loop of one tile hidden behind the other tile's MMAs).
+static bool use_one_tile_kernel() {
+    static const bool v = [] { const char* e = getenv("NERF_TC_ONE_TILE"); return e && e[0] == '1'; }();
     return v;
 }
 
@@ -440,6 +449,7 @@ static int launch_mlp_tc(const void* packed, const float* o, const float* d, con
     const int64_t total = N * S;
     NERF_REQUIRE(!act_out || ((uintptr_t)act_out & 15) == 0, "nerf_mlp_forward_tc: act_out must be 16-byte aligned");
     if (use_pair_kernel() && !act_out) return launch_mlp_tc2(packed, o, d, ts, samples, total, S, sigma, rgb, stream, dbg);
+    if (!use_one_tile_kernel()) return launch_mlp_tc3(packed, o, d, ts, samples, total, S, sigma, rgb, act_out, mask_out, stream, dbg);
     const int64_t tiles = (total + tc::kTileM - 1) / tc::kTileM;
     int grid = (int)(tiles < num_sms() ? tiles : num_sms());
     if (dbg) {                                        // diagnostic runs only: NERF_TC_MAX_CTAS limits the grid

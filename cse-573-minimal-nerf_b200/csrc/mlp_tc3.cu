@@ -1,0 +1,641 @@
+// mlp_tc3.cu - K8, two-tile form: NeRFModel.forward (nerf_model.py:362-389) for TWO 128-sample tiles ("X" and "Y") per
+// CTA at a time.  Same arithmetic, weight image and TMEM-resident activations as mlp_tc.cu; what changes is the schedule:
+//
+//   * every weight stage fetched from L2 into the shared-memory ring is used by both tiles before it is released, so the
+//     L2 -> SM weight stream per sample is halved (mlp_tc.cu streams 0.92 MB per tile at ~36 B/clk/SM, close to the
+//     ~42 B/clk/SM the L2 can deliver to all 148 SMs at once);
+//   * the MMA -> epilogue -> MMA dependency of one tile (a layer needs the previous layer's ReLU'd output) is hidden
+//     behind the other tile's MMAs: the issue order per 256-wide half layer is  X.kb01 X.kb23 | Y.kb01 Y.kb23, each
+//     tile has its own epilogue warps, and a tile's epilogue has one full half-step of the other tile to finish.
+//
+// TMEM (512 columns): D_X 0..127, D_Y 128..255 (one fp32 accumulator of N = 128 per tile), A_X 256..383, A_Y 384..511
+// (bf16 activations, K = 256, the A operand of the next layer).  There is no room for a second A buffer per tile, so
+// the epilogue converts IN PLACE: the first half of a layer's output (features 0..127) is kept in registers until the
+// tile's second-half MMAs - the last readers of the old activations - have completed, then written over them.
+//
+// Measured facts this schedule is built on (tools/probe_tmem_contention.py, profiles/r01_notes.md): an M128 x N128 x K16
+// tcgen05.mma with A in TMEM retires every 71.6 clk (96 clk with A in shared memory), tcgen05.commit is free, TMEM loads
+// by the epilogue do not slow the MMAs down, but the MMA queue is only ~4 instructions deep: the issuing warp must come
+// back with the next group within ~290 clk or the tensor pipe idles.  The issue loop therefore works on 32-bit shared
+// addresses and precomputed descriptors only (no generic-pointer arithmetic, no local-memory traffic between groups).
+//
+// Warps (768 threads): 0,3 weight producers | 1 MMA issuer | 2 TMEM allocation | 4-11 epilogue of tile X |
+// 12-19 epilogue of tile Y | 20-23 PE producers (both tiles).  Register budgets are re-balanced with setmaxnreg.
+//
+// Steps per tile (16): mlp.0 h0,h1 | mlp.2/4/6, feature_fn.0/2/4 h0,h1 | rgb_fn.0 | rgb_fn.2 (density_fn.0: CUDA cores, see below).
+// Barriers per tile t: dfull[t] (MMA -> epilogue, accumulator complete), dfree[t] (accumulator read into registers),
+// alo[t] / ahi[t] (K-blocks 0,1 / 2,3 of the next A operand written), pex_full/empty[t], ped_full/empty[t].
+#include <stdlib.h>
+#include "mlp_tc_common.cuh"
+
+namespace nerf {
+
+namespace t3 {
+constexpr int kTileM = 128;
+constexpr int kSlots = 4;
+constexpr uint32_t kSlotBytes = 32768;
+constexpr int kThreads = 768;
+constexpr int kEpiWarps = 8;           // per tile
+constexpr int kPEWarps = 4;
+constexpr uint32_t kColD = 0, kColA = 256;      // + 128 * tile
+
+constexpr uint32_t kOffPE = 0;             // PE(x) tiles of X and Y: 2 x [128 x 64] bf16
+constexpr uint32_t kOffPEDir = 32768;      // PE(dir) tiles of X and Y
+constexpr uint32_t kOffRing = 65536;
+constexpr uint32_t kOffBias = kOffRing + kSlots * kSlotBytes;
+constexpr uint32_t kOffW7 = kOffBias + ((pk::kBiasFloats * 4 + 15) / 16) * 16;     // density_fn.0 weights, fp32 [256]
+constexpr uint32_t kOffSig = kOffW7 + 1024;                                          // sigma partial sums [2 tiles][2][128]
+constexpr uint32_t kOffBars = kOffSig + 2048;
+// barrier indices (8 bytes each)
+constexpr uint32_t kBarFull = 0, kBarEmpty = 4, kBarDFull = 8, kBarDFree = 10, kBarALo = 12, kBarAHi = 14, kBarPexFull = 16,
+                   kBarPexEmpty = 18, kBarPedFull = 20, kBarPedEmpty = 22, kNumBars = 24;
+constexpr uint32_t kOffTmemHolder = kOffBars + kNumBars * 8;
+constexpr uint32_t kOffDetail = kOffTmemHolder + 16;                                 // PROFILE builds: 96 x int64
+constexpr uint32_t kSmemBytes = kOffDetail + 96 * 8 + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+// setmaxnreg moves registers inside the CTA's own pool (768 threads x 80 at launch): what the two small warpgroups give
+// back is exactly what the four epilogue warpgroups take
+constexpr int kRegsLaunch = 80, kRegsMisc = 56, kRegsEpi = 96, kRegsPE = 40;
+static_assert(kRegsMisc + 4 * kRegsEpi + kRegsPE <= 6 * kRegsLaunch, "register pool budget");
+}  // namespace t3
+
+// Stages of this kernel: c_merged without density_fn.0.  sigma is a 256-long dot product per sample; the epilogue of
+// feature_fn.4 takes it on the CUDA cores from the bf16 feat values it has in registers (same operands as the N = 16
+// MMA of mlp_tc.cu, fp32 accumulation), which removes one step, its accumulator hand-over and an 8 KB stage per tile.
+constexpr int kMergedStages3 = kMergedStages - 1;
+constexpr MergedTable make_merged_table3() {
+    MergedTable m = make_merged_table(), t = m;
+    t.s[31] = m.s[32];                                  // rgb_fn.2 follows rgb_fn.0 directly
+    t.s[32] = StageRef{0u, 0u};
+    return t;
+}
+static __constant__ MergedTable c_merged3 = make_merged_table3();
+constexpr uint32_t kDensityStageOffset = make_merged_table().s[31].offset;     // 4 blocks of [16 x 64] bf16, row 0 = w7
+
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {     // TMEM side effects of this warp are done
+    umma::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive_u32(bar);
+}
+
+// 32 accumulator columns (registers) -> + bias, (ReLU), 16 registers of bf16 pairs
+__device__ __forceinline__ void pack32(const uint32_t (&v)[32], const float* __restrict__ bias, bool relu, uint32_t* p) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b4 = *(const float4*)(bias + 4 * j);
+        const float x0 = __uint_as_float(v[4 * j + 0]) + b4.x, x1 = __uint_as_float(v[4 * j + 1]) + b4.y;
+        const float x2 = __uint_as_float(v[4 * j + 2]) + b4.z, x3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+        p[2 * j + 0] = relu ? umma::pack_bf16_relu(x0, x1) : umma::pack_bf16(x0, x1);
+        p[2 * j + 1] = relu ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
+    }
+}
+
+// 64 accumulator columns of this thread's row -> + bias, (ReLU), bf16 pairs.  The accumulator is released (dfree)
+// as soon as the values are in registers.
+__device__ __forceinline__ void load_pack64(uint32_t d_addr, const float* __restrict__ bias, bool relu, uint32_t dfree_bar,
+                                            int lane, uint32_t (&p)[32]) {
+    uint32_t v0[32], v1[32];
+    umma::tmem_ld32(d_addr, v0);
+    umma::tmem_ld32(d_addr + 32, v1);
+    umma::tmem_wait_ld();
+    warp_arrive(dfree_bar, lane);
+    pack32(v0, bias, relu, p);
+    pack32(v1, bias + 32, relu, p + 16);
+}
+
+// Second half of a layer.  The held first-half output `p_lo` may now overwrite A columns [a_addr, +32) (every reader of
+// the old activations has completed); its store is overlapped with the load of the first 32 accumulator columns.
+__device__ __forceinline__ void store_lo_load_pack64(uint32_t a_addr, const uint32_t (&p_lo)[32], uint32_t alo_bar, uint32_t d_addr,
+                                                     const float* __restrict__ bias, bool relu, uint32_t dfree_bar, int lane,
+                                                     uint32_t (&p)[32]) {
+    uint32_t v0[32];
+    umma::tmem_ld32(d_addr, v0);
+    {
+        uint32_t a[16], b[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { a[j] = p_lo[j]; b[j] = p_lo[16 + j]; }
+        umma::tmem_st16(a_addr, a);
+        umma::tmem_st16(a_addr + 16, b);
+    }
+    umma::tmem_wait_st();
+    warp_arrive(alo_bar, lane);
+    uint32_t v1[32];
+    umma::tmem_ld32(d_addr + 32, v1);
+    umma::tmem_wait_ld();
+    warp_arrive(dfree_bar, lane);
+    pack32(v0, bias, relu, p);
+    pack32(v1, bias + 32, relu, p + 16);
+}
+
+// 32 packed registers (64 bf16) -> 32 TMEM columns of this thread's lane, then signal `bar` (one arrive per warp).
+__device__ __forceinline__ void store_a32(uint32_t a_addr, const uint32_t (&p)[32], uint32_t bar, int lane) {
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { lo[j] = p[j]; hi[j] = p[16 + j]; }
+    umma::tmem_st16(a_addr, lo);
+    umma::tmem_st16(a_addr + 16, hi);
+    umma::tmem_wait_st();
+    warp_arrive(bar, lane);
+}
+
+// Row `r` of a [128 x 64] bf16 K-major 128B-swizzled PE tile, four frequencies (12 registers = three 16-byte chunks) at a
+// time so that the producer warps stay within a small register budget.  Layout per frequency as encode_row.
+template <int L>
+__device__ __forceinline__ void encode_store_row(uint8_t* tile, int r, const float (&x)[3]) {
+    uint8_t* rowp = tile + r * 128;
+    const int sw = r & 7;
+#pragma unroll
+    for (int g = 0; g < 8; g += 3) {              // chunk groups {0,1,2}, {3,4,5}, {6,7}
+        uint32_t v[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) v[j] = 0u;
+#pragma unroll
+        for (int fi = 0; fi < 4; ++fi) {
+            const int i = (g / 3) * 4 + fi;
+            if (i < L) {
+                const float f = tcm::kPiF * (float)(1 << i);
+                float s[3], c[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) fast_sincos(__fmul_rn(f, x[k]), s[k], c[k]);
+                v[3 * fi + 0] = umma::pack_bf16(c[0], c[1]);
+                v[3 * fi + 1] = umma::pack_bf16(c[2], s[0]);
+                v[3 * fi + 2] = umma::pack_bf16(s[1], s[2]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (g + c < 8) *(uint4*)(rowp + (((g + c) ^ sw) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+}
+
+// sum of 64 bf16 values (32 packed registers) times 64 fp32 weights, fp32 accumulation
+__device__ __forceinline__ float dot_bf16x64(const uint32_t (&p)[32], const float* __restrict__ w, float acc) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float4 w4 = *(const float4*)(w + 4 * j);
+        acc = fmaf(__uint_as_float(p[2 * j] << 16), w4.x, acc);
+        acc = fmaf(__uint_as_float(p[2 * j] & 0xFFFF0000u), w4.y, acc);
+        acc = fmaf(__uint_as_float(p[2 * j + 1] << 16), w4.z, acc);
+        acc = fmaf(__uint_as_float(p[2 * j + 1] & 0xFFFF0000u), w4.w, acc);
+    }
+    return acc;
+}
+
+// training: keep what the next layer consumes (post-activation bf16, tiled chunk-major, pack_layout.cuh) and the 64-bit
+// word of ReLU sign bits the dgrad kernel masks with.
+__device__ __forceinline__ void save_act64(__nv_bfloat16* __restrict__ act_out, unsigned long long* __restrict__ mask_out,
+                                           int64_t row, int feature, const uint32_t (&p)[32]) {
+    uint4* chunk = (uint4*)(act_out + pk::tiled_offset(row, feature, pk::kActChunks));
+    unsigned long long mbits = 0ull;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) chunk[j * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        mbits |= (unsigned long long)((p[j] & 0x00007FFFu) != 0u) << (2 * j);
+        mbits |= (unsigned long long)((p[j] & 0x7FFF0000u) != 0u) << (2 * j + 1);
+    }
+    mask_out[((row >> 7) * pk::kMaskWords + (feature >> 6)) * 128 + (row & 127)] = mbits;
+}
+
+// The MMA-issuing warp's state and primitives.  Tile indices are template parameters and every address is a 32-bit
+// shared-memory / TMEM address held in a register, so nothing but a handful of integer instructions sits between two
+// groups of tcgen05.mma.
+// PROFILE counters: prof[1] wait weights, [2] wait dfree, [3] wait alo/ahi, [4] wait PE; detail (shared memory, 96 x
+// int64): [0,32) weight wait per stage, [32,64) dfree wait per (tile, step), [64,96) alo/ahi wait per (tile, step).
+template <bool PROFILE>
+struct MmaIssuer {
+    static constexpr uint32_t kI128 = umma::make_idesc_bf16(128, 128);
+    static constexpr uint32_t kI16 = umma::make_idesc_bf16(128, 16);
+    uint32_t bars, tmem;
+    uint64_t ring_desc;                             // descriptor of ring slot 0; slot s / K block at byte offset o: + (s*32768 + o) >> 4
+    bool leader;
+    uint32_t cnt;                                   // weight stages opened
+    uint32_t n_dfree0, n_dfree1, n_alo0, n_alo1, n_ahi0, n_ahi1, acc0, acc1;
+    long long prof[5];
+    uint32_t detail, stage_id, step0, step1;
+
+    __device__ __forceinline__ void init(uint32_t bars_addr, uint32_t ring_addr, uint32_t tmem_base, bool is_leader, uint32_t detail_addr) {
+        bars = bars_addr; tmem = tmem_base; leader = is_leader;
+        ring_desc = umma::make_desc_k_sw128(ring_addr);
+        cnt = 0; n_dfree0 = n_dfree1 = n_alo0 = n_alo1 = n_ahi0 = n_ahi1 = acc0 = acc1 = 0;
+        detail = detail_addr; stage_id = step0 = step1 = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) prof[i] = 0;
+    }
+    __device__ __forceinline__ uint32_t bar(uint32_t idx) const { return bars + 8u * idx; }
+    __device__ __forceinline__ void wait(uint32_t bar_addr, uint32_t parity, int slot, int detail_idx = -1) {
+        if (PROFILE) {
+            const long long t0 = clock64();
+            umma::mbar_wait_u32(bar_addr, parity);
+            const long long dt = clock64() - t0;
+            prof[slot] += dt;
+            if (detail_idx >= 0 && leader) {
+                long long old;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(old) : "r"(detail + 8u * (uint32_t)detail_idx));
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(detail + 8u * (uint32_t)detail_idx), "l"(old + dt));
+            }
+        } else {
+            umma::mbar_wait_u32(bar_addr, parity);
+        }
+        umma::tc_fence_after();
+    }
+    // next weight stage present in shared memory; returns its descriptor offset (slot * 32768 >> 4)
+    __device__ __forceinline__ uint32_t open() {
+        const uint32_t slot = cnt & (t3::kSlots - 1);
+        wait(bar(t3::kBarFull + slot), (cnt >> 2) & 1u, 1, (int)(stage_id & 31u));
+        ++cnt; ++stage_id;
+        return slot * (t3::kSlotBytes >> 4);
+    }
+    // the stage opened `back` opens ago is free once the MMAs issued so far have completed
+    __device__ __forceinline__ void release(uint32_t back) {
+        const uint32_t slot = (cnt - 1u - back) & (t3::kSlots - 1);
+        if (leader) umma::mma_commit_u32(bar(t3::kBarEmpty + slot));
+        __syncwarp();
+    }
+    __device__ __forceinline__ void commit(uint32_t idx) {
+        if (leader) umma::mma_commit_u32(bar(idx));
+        __syncwarp();
+    }
+    __device__ __forceinline__ void wait_pe(uint32_t idx, uint32_t parity) { wait(bar(idx), parity, 4); }
+    template <int T> __device__ __forceinline__ void begin_step() {     // the tile's accumulator has been read by its epilogue
+        uint32_t& n = T ? n_dfree1 : n_dfree0;
+        uint32_t& st = T ? step1 : step0;
+        wait(bar(t3::kBarDFree + T), (n & 1u) ^ 1u, 2, 32 + T * 16 + (int)(st & 15u));
+        ++n; ++st;
+        (T ? acc1 : acc0) = 0;
+    }
+    template <int T> __device__ __forceinline__ void end_step() { commit(t3::kBarDFull + T); }
+    template <int T> __device__ __forceinline__ void need_lo() {
+        uint32_t& n = T ? n_alo1 : n_alo0;
+        wait(bar(t3::kBarALo + T), n & 1u, 3, 64 + T * 16 + (int)(((T ? step1 : step0) - 1u) & 15u));
+        ++n;
+    }
+    template <int T> __device__ __forceinline__ void need_hi() {
+        uint32_t& n = T ? n_ahi1 : n_ahi0;
+        wait(bar(t3::kBarAHi + T), n & 1u, 3, 64 + T * 16 + (int)(((T ? step1 : step0) - 1u) & 15u));
+        ++n;
+    }
+    // NKB K=64 blocks of TILE_BYTES each in the stage at descriptor offset `b_off`; A = TMEM columns a_col.. of tile T
+    template <int T, int NKB, uint32_t TILE_BYTES, uint32_t IDESC>
+    __device__ __forceinline__ void issue_ts(uint32_t a_col, uint32_t b_off) {
+        uint32_t& acc = T ? acc1 : acc0;
+        if (leader) {
+            const uint32_t d = tmem + t3::kColD + 128u * T;
+            const uint32_t a = tmem + t3::kColA + 128u * T + a_col;
+            const uint64_t bdesc = ring_desc + b_off;
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma::mma_ts(d, a + 32u * kb + 8u * k, bdesc + (uint64_t)(kb * (TILE_BYTES >> 4) + 2 * k), IDESC, (kb | k) ? 1u : acc);
+            }
+        }
+        __syncwarp();
+        acc = 1;
+    }
+    // one K block (NK16 K=16 slices) with A from a shared-memory PE tile
+    template <int T, int NK16>
+    __device__ __forceinline__ void issue_ss(uint64_t a_desc, uint32_t b_off) {
+        uint32_t& acc = T ? acc1 : acc0;
+        if (leader) {
+            const uint32_t d = tmem + t3::kColD + 128u * T;
+            const uint64_t bdesc = ring_desc + b_off;
+#pragma unroll
+            for (int k = 0; k < NK16; ++k) umma::mma_ss(d, a_desc + 2u * k, bdesc + 2u * k, kI128, k ? 1u : acc);
+        }
+        __syncwarp();
+        acc = 1;
+    }
+    // a K = 256 layer half (or rgb_fn.0) for both tiles: [PE stage] kb01 kb23 of X, then of Y on the same stages
+    template <bool FIRST_HALF, int PE_K16>
+    __device__ __forceinline__ void layer_half(uint64_t descA0, uint64_t descA1, uint32_t pe_done_idx) {
+        uint32_t bP = 0;
+        if (PE_K16 > 0) bP = open();
+        const uint32_t b01 = open();
+        begin_step<0>();
+        if (PE_K16 > 0) {
+            issue_ss<0, PE_K16 ? PE_K16 : 1>(descA0, bP);
+            if (pe_done_idx) commit(pe_done_idx);
+        }
+        if (FIRST_HALF) need_lo<0>();
+        issue_ts<0, 2, 16384, kI128>(0, b01);
+        const uint32_t b23 = open();
+        if (FIRST_HALF) need_hi<0>();
+        issue_ts<0, 2, 16384, kI128>(64, b23);
+        end_step<0>();
+        begin_step<1>();
+        if (PE_K16 > 0) {
+            issue_ss<1, PE_K16 ? PE_K16 : 1>(descA1, bP);
+            if (pe_done_idx) commit(pe_done_idx + 1);
+            release(2);
+        }
+        if (FIRST_HALF) need_lo<1>();
+        issue_ts<1, 2, 16384, kI128>(0, b01);
+        release(1);
+        if (FIRST_HALF) need_hi<1>();
+        issue_ts<1, 2, 16384, kI128>(64, b23);
+        release(0);
+        end_step<1>();
+    }
+};
+
+// dbg counters (PROFILE), per CTA x 16: 0 MMA warp total, 1 wait weights, 2 wait dfree, 3 wait alo/ahi, 4 wait PE,
+// 5 producer wait empty, 6 epilogue X total, 7 epilogue X wait dfull, 8 pairs; dbg[148*16 ...] = CTA 0's wait detail
+template <bool PROFILE>
+__global__ void __launch_bounds__(t3::kThreads, 1)
+mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_rays, const float* __restrict__ d_rays,
+               const float* __restrict__ ts, const float* __restrict__ samples, int64_t total, int S,
+               float* __restrict__ sigma_out, float* __restrict__ rgb_out, __nv_bfloat16* __restrict__ act_out,
+               unsigned long long* __restrict__ mask_out, long long* __restrict__ dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = umma::smem_u32(smem);
+    const uint32_t bars = sbase + t3::kOffBars;
+    float* sBias = (float*)(smem + t3::kOffBias);
+    float* sW7 = (float*)(smem + t3::kOffW7);
+    float* sSig = (float*)(smem + t3::kOffSig);
+    uint32_t* tmem_holder = (uint32_t*)(smem + t3::kOffTmemHolder);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t num_tiles = (total + t3::kTileM - 1) / t3::kTileM;
+    const int64_t num_pairs = (num_tiles + 1) / 2;
+
+    if (tid == 0) {
+        uint64_t* b = (uint64_t*)(smem + t3::kOffBars);
+        for (int i = 0; i < t3::kSlots; ++i) { umma::mbar_init(&b[t3::kBarFull + i], 1); umma::mbar_init(&b[t3::kBarEmpty + i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&b[t3::kBarDFull + i], 1);
+            umma::mbar_init(&b[t3::kBarDFree + i], t3::kEpiWarps);
+            umma::mbar_init(&b[t3::kBarALo + i], t3::kEpiWarps);
+            umma::mbar_init(&b[t3::kBarAHi + i], t3::kEpiWarps);
+            umma::mbar_init(&b[t3::kBarPexFull + i], t3::kPEWarps);
+            umma::mbar_init(&b[t3::kBarPexEmpty + i], 1);
+            umma::mbar_init(&b[t3::kBarPedFull + i], t3::kPEWarps);
+            umma::mbar_init(&b[t3::kBarPedEmpty + i], 1);
+        }
+        umma::fence_mbar_init();
+    }
+    if (warp == 2) umma::tmem_alloc(tmem_holder, 512);
+    {   // biases: resident for the whole kernel
+        const float* gb = (const float*)(packed + pk::kLayout.bias_offset);
+        for (int i = tid; i < pk::kBiasFloats; i += t3::kThreads) sBias[i] = gb[i];
+        // density_fn.0.weight as the packer rounded it to bf16: row 0 of the four [16 x 64] blocks (row 0 is not swizzled)
+        if (tid < 256) {
+            const __nv_bfloat16* w7 = (const __nv_bfloat16*)(packed + kDensityStageOffset + (tid >> 6) * pk::kStageBytesSmall);
+            sW7[tid] = __bfloat162float(w7[tid & 63]);
+        }
+        if (PROFILE && tid < 96) ((long long*)(smem + t3::kOffDetail))[tid] = 0;
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+
+    if (warp < 4) {
+        reg_dec<t3::kRegsMisc>();
+        if (warp == 0 || warp == 3) {
+            // -------------------------------------------------------------- weight producers (alternate stages)
+            const bool leader = umma::elect_one();
+            const uint32_t me = (warp == 0) ? 0u : 1u;
+            const uint32_t ring = sbase + t3::kOffRing;
+            long long t_wait = 0;
+            uint32_t cnt = 0;
+            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+                for (int s = 0; s < kMergedStages3; ++s, ++cnt) {
+                    if ((cnt & 1u) != me) continue;
+                    const uint32_t slot = cnt & (t3::kSlots - 1), ph = (cnt >> 2) & 1u;
+                    const long long t0 = PROFILE ? clock64() : 0;
+                    umma::mbar_wait_u32(bars + 8u * (t3::kBarEmpty + slot), ph ^ 1u);
+                    if (PROFILE) t_wait += clock64() - t0;
+                    if (leader) {
+                        const StageRef st = c_merged3.s[s];
+                        umma::mbar_arrive_expect_tx_u32(bars + 8u * (t3::kBarFull + slot), st.bytes);
+                        umma::bulk_g2s_u32(ring + slot * t3::kSlotBytes, packed + st.offset, st.bytes, bars + 8u * (t3::kBarFull + slot));
+                    }
+                    __syncwarp();
+                }
+            }
+            if (PROFILE && lane == 0 && warp == 0) dbg[blockIdx.x * 16 + 5] = t_wait;
+        } else if (warp == 1) {
+            // -------------------------------------------------------------- MMA issuer (warp-uniform, one lane issues)
+            MmaIssuer<PROFILE> m;
+            m.init(bars, sbase + t3::kOffRing, tmem, umma::elect_one(), sbase + t3::kOffDetail);
+            const uint64_t descPE0 = umma::make_desc_k_sw128(sbase + t3::kOffPE);
+            const uint64_t descPE1 = umma::make_desc_k_sw128(sbase + t3::kOffPE + 16384);
+            const uint64_t descPD0 = umma::make_desc_k_sw128(sbase + t3::kOffPEDir);
+            const uint64_t descPD1 = umma::make_desc_k_sw128(sbase + t3::kOffPEDir + 16384);
+            uint32_t it = 0;
+            const long long t_begin = PROFILE ? clock64() : 0;
+            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
+                // ---- mlp.0: A = PE(x) tile, one 16 KB stage per N half
+                m.wait_pe(t3::kBarPexFull + 0, it & 1u);
+                m.wait_pe(t3::kBarPexFull + 1, it & 1u);
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t b = m.open();
+                    m.template begin_step<0>();
+                    m.template issue_ss<0, 4>(descPE0, b);
+                    m.template end_step<0>();
+                    m.template begin_step<1>();
+                    m.template issue_ss<1, 4>(descPE1, b);
+                    m.template end_step<1>();
+                    m.release(0);
+                }
+                // ---- mlp.2/4/6, feature_fn.0 (PE(x) K block first; its second half is the last reader of PE(x)), feature_fn.2/4
+#pragma unroll 1
+                for (int l = 1; l <= 6; ++l) {
+                    if (l == 4) {
+                        m.template layer_half<true, 4>(descPE0, descPE1, 0);
+                        m.template layer_half<false, 4>(descPE0, descPE1, t3::kBarPexEmpty);
+                    } else {
+                        m.template layer_half<true, 0>(0, 0, 0);
+                        m.template layer_half<false, 0>(0, 0, 0);
+                    }
+                }
+                // ---- rgb_fn.0: PE(dir) K block + feat -> 128 columns
+                m.wait_pe(t3::kBarPedFull + 0, it & 1u);
+                m.wait_pe(t3::kBarPedFull + 1, it & 1u);
+                m.template layer_half<true, 2>(descPD0, descPD1, t3::kBarPedEmpty);
+                // ---- rgb_fn.2: r (A columns 0..63) -> 16 columns
+                {
+                    const uint32_t b = m.open();
+                    m.template begin_step<0>();
+                    m.template need_lo<0>();
+                    m.template issue_ts<0, 2, 2048, MmaIssuer<PROFILE>::kI16>(0, b);
+                    m.template end_step<0>();
+                    m.template begin_step<1>();
+                    m.template need_lo<1>();
+                    m.template issue_ts<1, 2, 2048, MmaIssuer<PROFILE>::kI16>(0, b);
+                    m.template end_step<1>();
+                    m.release(0);
+                }
+            }
+            if (PROFILE && lane == 0) {
+                dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
+                for (int i = 1; i < 5; ++i) dbg[blockIdx.x * 16 + i] = m.prof[i];
+                dbg[blockIdx.x * 16 + 8] = it;
+            }
+            __syncwarp();
+            if (PROFILE && blockIdx.x == 0) for (int i = lane; i < 96; i += 32) dbg[148 * 16 + i] = ((long long*)(smem + t3::kOffDetail))[i];
+        }
+    } else if (warp >= 20) {
+        // ------------------------------------------------------------------ PE producers (128 threads, thread = row)
+        reg_dec<t3::kRegsPE>();
+        const int r = (warp - 20) * 32 + lane;
+        uint32_t it = 0;
+        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const int64_t row = (pair * 2 + t) * t3::kTileM + r;
+                float x[3] = {0.f, 0.f, 0.f};
+                if (row < total) {
+                    if (samples) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) x[k] = samples[row * 3 + k];
+                    } else {
+                        const int64_t n = row / S;
+                        const float tt = ts[row];                     // d * t + o (nerf_helpers.py:55)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) x[k] = __fadd_rn(__fmul_rn(__ldg(d_rays + n * 3 + k), tt), __ldg(o_rays + n * 3 + k));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) x[k] = __fdiv_rn(x[k], tcm::kPiF);           // nerf_model.py:377
+                }
+                umma::mbar_wait_u32(bars + 8u * (t3::kBarPexEmpty + t), (it & 1u) ^ 1u);   // feature_fn.0 of the previous pair is done with it
+                encode_store_row<10>(smem + t3::kOffPE + t * 16384, r, x);
+                umma::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive_u32(bars + 8u * (t3::kBarPexFull + t));
+            }
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const int64_t row = (pair * 2 + t) * t3::kTileM + r;
+                float u[3] = {0.f, 0.f, 0.f};
+                if (row < total) {
+                    const int64_t n = row / S;
+                    const float dx = __ldg(d_rays + n * 3), dy = __ldg(d_rays + n * 3 + 1), dz = __ldg(d_rays + n * 3 + 2);
+                    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);                    // nerf_model.py:373
+                    u[0] = __fdiv_rn(dx, nrm); u[1] = __fdiv_rn(dy, nrm); u[2] = __fdiv_rn(dz, nrm);
+                }
+                umma::mbar_wait_u32(bars + 8u * (t3::kBarPedEmpty + t), (it & 1u) ^ 1u);   // rgb_fn.0 of the previous pair is done with it
+                encode_store_row<4>(smem + t3::kOffPEDir + t * 16384, r, u);
+                umma::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive_u32(bars + 8u * (t3::kBarPedFull + t));
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: warps 4-11 tile X, 12-19 tile Y
+        reg_inc<t3::kRegsEpi>();
+        const int t = (warp >= 12) ? 1 : 0;
+        const int q = warp & 3;                          // TMEM lane quarter this warp may touch
+        const int wh = ((warp - 4) >> 2) & 1;            // column half handled by this warp
+        const int r = q * 32 + lane;                     // row (sample) inside the tile
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(wh * 64);
+        const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(wh * 32);
+        const uint32_t bar_dfull = bars + 8u * (t3::kBarDFull + t), bar_dfree = bars + 8u * (t3::kBarDFree + t);
+        const uint32_t bar_alo = bars + 8u * (t3::kBarALo + t), bar_ahi = bars + 8u * (t3::kBarAHi + t);
+        uint32_t nd = 0;                                 // accumulators consumed
+        long long t_wait = 0;
+        const long long t_begin = PROFILE ? clock64() : 0;
+        auto wait_d = [&]() {
+            const long long t0 = PROFILE ? clock64() : 0;
+            umma::mbar_wait_u32(bar_dfull, nd & 1u);
+            if (PROFILE) t_wait += clock64() - t0;
+            umma::tc_fence_after();
+            ++nd;
+        };
+
+        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            const int64_t tile = pair * 2 + t;
+            const int64_t row = tile * t3::kTileM + r;
+            const bool save = (act_out != nullptr) && (tile < num_tiles);
+            // ---- 7 hidden layers: h0 is held in registers until h1's MMAs (the last readers of the old A) are done
+            float sig_part = 0.f;
+#pragma unroll 1
+            for (int layer = 0; layer < 7; ++layer) {
+                const bool relu = (layer != 6);                       // feature_fn.4 is linear (nerf_model.py:347)
+                const float* bias = sBias + layer * 256 + wh * 64;
+                uint32_t p_lo[32];
+                wait_d();
+                load_pack64(d_addr, bias, relu, bar_dfree, lane, p_lo);
+                if (save) save_act64(act_out, mask_out, row, layer * 256 + wh * 64, p_lo);
+                if (layer == 6) sig_part = dot_bf16x64(p_lo, sW7 + wh * 64, sig_part);
+                wait_d();
+                uint32_t p_hi[32];
+                store_lo_load_pack64(a_addr, p_lo, bar_alo, d_addr, bias + 128, relu, bar_dfree, lane, p_hi);   // features 0..127 -> A 0..63
+                store_a32(a_addr + 64, p_hi, bar_ahi, lane);          // features 128..255 -> A columns 64..127
+                if (save) save_act64(act_out, mask_out, row, layer * 256 + 128 + wh * 64, p_hi);
+                if (layer == 6) sig_part = dot_bf16x64(p_hi, sW7 + 128 + wh * 64, sig_part);
+            }
+            // density_fn.0 (nerf_model.py:350-353): this warp's 128 of the 256 products; the wh = 0 warp of the same rows adds
+            // the two partial sums at the last step (ordered behind this write by the alo arrive below and the MMA commit)
+            sSig[(t * 2 + wh) * 128 + r] = sig_part;
+            // ---- rgb_fn.0: r = relu(. + b) overwrites feat (every reader of feat has completed)
+            {
+                uint32_t p[32];
+                wait_d();
+                load_pack64(d_addr, sBias + pk::kBiasR0 + wh * 64, true, bar_dfree, lane, p);
+                store_a32(a_addr, p, bar_alo, lane);                  // r features 0..127 -> A columns 0..63
+                if (save) save_act64(act_out, mask_out, row, 1792 + wh * 64, p);
+            }
+            // ---- rgb_fn.2: columns 0..2 -> sigmoid(. + b) (nerf_model.py:358-359); sigma = relu(feat . w7 + b7)
+            {
+                wait_d();
+                uint32_t v[4] = {0u, 0u, 0u, 0u};
+                float sg = 0.f;
+                if (wh == 0) {
+                    umma::tmem_ld4(tmem + lane_base + t3::kColD + 128u * (uint32_t)t, v);
+                    sg = sSig[(t * 2 + 0) * 128 + r] + sSig[(t * 2 + 1) * 128 + r];
+                    umma::tmem_wait_ld();
+                }
+                warp_arrive(bar_dfree, lane);
+                if (wh == 0 && row < total) {
+                    sigma_out[row] = fmaxf(sg + sBias[pk::kBiasSigma], 0.f);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float x = __uint_as_float(v[k]) + sBias[pk::kBiasRgb + k];
+                        rgb_out[row * 3 + k] = 1.0f / (1.0f + __expf(-x));
+                    }
+                }
+            }
+        }
+        if (PROFILE && tid == 128) { dbg[blockIdx.x * 16 + 6] = clock64() - t_begin; dbg[blockIdx.x * 16 + 7] = t_wait; }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) umma::tmem_dealloc(tmem, 512);
+}
+
+int launch_mlp_tc3(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
+                   int64_t total, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream, long long* dbg) {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        if (e != cudaSuccess) { set_error("nerf_mlp_forward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
+        attr_set = true;
+    }
+    const int64_t tiles = (total + t3::kTileM - 1) / t3::kTileM;
+    const int64_t pairs = (tiles + 1) / 2;
+    int grid = (int)(pairs < num_sms() ? pairs : num_sms());
+    if (dbg) {                                        // diagnostic runs only: NERF_TC_MAX_CTAS limits the grid
+        const char* e = getenv("NERF_TC_MAX_CTAS");
+        if (e && atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
+    }
+    if (dbg)
+        mlp_tc3_kernel<true><<<grid, t3::kThreads, t3::kSmemBytes, (cudaStream_t)stream>>>(
+            (const uint8_t*)packed, o, d, ts, samples, total, S, sigma, rgb, (__nv_bfloat16*)act_out, (unsigned long long*)mask_out, dbg);
+    else
+        mlp_tc3_kernel<false><<<grid, t3::kThreads, t3::kSmemBytes, (cudaStream_t)stream>>>(
+            (const uint8_t*)packed, o, d, ts, samples, total, S, sigma, rgb, (__nv_bfloat16*)act_out, (unsigned long long*)mask_out, nullptr);
+    return check_launch("nerf_mlp_forward_tc");
+}
+
+}  // namespace nerf

@@ -176,6 +176,50 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
+// ---- 32-bit shared-address variants: hot loops keep barrier / ring addresses as plain u32 so that no generic -> shared
+// conversion (and no re-materialisation of the aligned dynamic-smem base) lands between two tcgen05.mma groups.
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A wait that lasts longer than ~2 s of SM clocks is a protocol bug: trap instead of hanging the GPU.  (No printf here:
+// a real call in the slow path makes ptxas spill the caller's registers around every wait; build with
+// -DNERF_DEBUG_BARRIERS to get the barrier address printed.)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_u32(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_u32(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+#ifdef NERF_DEBUG_BARRIERS
+            printf("nerf_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gmem_src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_commit_u32(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // ------------------------------------------------------------------ CTA-pair (cta_group::2) / cluster variants
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

@@ -172,6 +172,98 @@ extern "C" int nerf_debug_tmem_bw(int nwarps, int iters, int mode, long long* ou
     return nerf::check_launch("nerf_debug_tmem_bw");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// TMEM contention probe: warp 0 issues `n_mma` back-to-back tcgen05.mma (M128 x N x K16, bf16) into the accumulator at
+// column d_col (A from TMEM column a_col, or from shared memory when a_col < 0) while `nw` other warps loop over
+// tcgen05.ld 32x32b.x32 (+ optional st x16) on columns [ld_col, ld_col + ld_span) of their lane quarter until the MMAs
+// have completed.  out[0] = cycles from first issue to completion of the last MMA, out[1] = bytes loaded by all ld warps
+// in that window, out[2] = bytes stored.
+namespace nerf {
+__global__ void __launch_bounds__(1024, 1)
+tmem_contention_probe_kernel(int n_mma, int N, int d_col, int a_col, int nw, int ld_mode, int ld_col, int ld_span, int commit_every,
+                             long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint32_t holder;
+    __shared__ uint64_t done_bar, dummy_bar;
+    __shared__ volatile int stop_flag;
+    __shared__ unsigned long long ld_bytes, st_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u;   // bf16 pairs, finite
+    if (threadIdx.x == 0) { umma::mbar_init(&done_bar, 1); umma::mbar_init(&dummy_bar, 1u << 19); umma::fence_mbar_init(); stop_flag = 0; ld_bytes = 0; st_bytes = 0; }
+    if (warp == 0) umma::tmem_alloc(&holder, 512);
+    umma::fence_proxy_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = holder;
+    if (warp == 0) {
+        const bool leader = umma::elect_one();
+        const uint32_t idesc = umma::make_idesc_bf16(128, (uint32_t)N);
+        const uint64_t adesc = umma::make_desc_k_sw128(umma::smem_u32(smem));
+        const uint64_t bdesc = umma::make_desc_k_sw128(umma::smem_u32(smem + 16384));
+        const long long t0 = clock64();
+        if (leader) {
+            int since = 0;
+            for (int i = 0; i < n_mma; ++i) {
+                const uint32_t k = (uint32_t)(i & 3);
+                if (a_col >= 0) umma::mma_ts(tmem + (uint32_t)d_col, tmem + (uint32_t)a_col + 8u * (uint32_t)(i & 15), bdesc + 2u * k, idesc, 1u);
+                else umma::mma_ss(tmem + (uint32_t)d_col, adesc + 2u * k, bdesc + 2u * k, idesc, 1u);
+                if (commit_every > 0 && ++since == commit_every) { umma::mma_commit(&dummy_bar); since = 0; }
+            }
+            umma::mma_commit(&done_bar);
+        }
+        __syncwarp();
+        const long long t_issue = clock64();
+        umma::mbar_wait(&done_bar, 0);
+        const long long t1 = clock64();
+        stop_flag = 1;
+        if (lane == 0) { out[0] = t1 - t0; out[3] = t_issue - t0; }
+    } else if (warp >= 4 && warp < 4 + nw && ld_mode != 0) {
+        const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t acc = 0;
+        unsigned long long nld = 0, nst = 0;
+        int i = warp >> 2;
+        while (!stop_flag) {
+            const uint32_t col = (uint32_t)ld_col + (uint32_t)((i * 32) % ld_span);
+            ++i;
+            uint32_t v[32];
+            umma::tmem_ld32(base + col, v);
+            umma::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc ^= v[j];
+            nld += 4096;
+            if (ld_mode == 2) {
+                uint32_t p[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) p[j] = (acc & 0x3c003c00u) + j;
+                umma::tmem_st16(base + 448 + (col & 31), p);        // scratch columns 448..511
+                umma::tmem_wait_st();
+                nst += 2048;
+            }
+        }
+        if (acc == 0x12345678) out[7] = acc;
+        if (lane == 0) { atomicAdd(&ld_bytes, nld); atomicAdd(&st_bytes, nst); }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) { out[1] = (long long)ld_bytes; out[2] = (long long)st_bytes; }
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+}  // namespace nerf
+
+extern "C" int nerf_debug_tmem_contention(int n_mma, int N, int d_col, int a_col, int nw, int ld_mode, int ld_col, int ld_span,
+                                          int commit_every, long long* out, void* stream) {
+    using namespace nerf;
+    NERF_REQUIRE(nw >= 0 && nw <= 28 && N >= 16 && N <= 256 && d_col >= 0 && d_col + N <= 512 && ld_span >= 32, "tmem_contention: bad args");
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(tmem_contention_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr = true; }
+    tmem_contention_probe_kernel<<<1, (4 + (nw > 0 ? nw : 0)) * 32, 65536, (cudaStream_t)stream>>>(n_mma, N, d_col, a_col, nw, ld_mode,
+                                                                                                ld_col, ld_span, commit_every, out);
+    return check_launch("nerf_debug_tmem_contention");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Copy-engine streaming probe: one producer lane streams `nstages` x `bytes` from an L2-resident buffer through a
 // `slots`-deep shared-memory ring; a consumer warp releases every slot as soon as it is full.  mode 0: cp.async.bulk

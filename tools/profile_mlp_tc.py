@@ -1,6 +1,7 @@
 """Per-CTA cycle counters of the fused tcgen05 MLP kernel (diagnostic build of the same kernel).
 usage: python tools/profile_mlp_tc.py [N] [S]"""
 import ctypes
+import os
 import sys
 from pathlib import Path
 
@@ -27,7 +28,7 @@ rgb = torch.empty(N, S, 3, device=dev)
 fn = nat.lib().nerf_debug_mlp_tc_profile
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p] * 4
-dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+dbg = torch.zeros(148 * 16 + 128, dtype=torch.int64, device=dev)
 import os
 G = int(os.environ.get("NERF_TC_MAX_CTAS", "148"))
 for it in range(3):
@@ -38,13 +39,35 @@ for it in range(3):
     t1.record()
     torch.cuda.synchronize()
 ms = t0.elapsed_time(t1)
-c = dbg.double().cpu()[:G]
+detail = dbg[148 * 16:].double().cpu()
+c = dbg[:148 * 16].view(148, 16).double().cpu()[:G]
 tiles = c[:, 8].clamp(min=1)
+one_tile = os.environ.get("NERF_TC_ONE_TILE") == "1"
+names3 = ["mma_total", "mma_wait_full(weights)", "mma_wait_dfree(acc read)", "mma_wait_alo/ahi(epilogue)", "mma_wait_pe",
+          "producer_wait_empty", "epiX_total", "epiX_wait_dfull", "pairs", "mma_issue_ts(+backpressure)", "epiX_ld+wait",
+          "epiX_pack", "epiX_st+wait+arrive", "mma_commits"]
 names = ["mma_total", "mma_wait_full(weights)", "mma_wait_edone(epilogue)", "mma_wait_pe", "producer_wait_empty", "epi_total",
          "epi_wait_dfull", "epi_pe_time", "tiles", "epi_seg_ld+wait", "epi_seg_math1", "epi_seg_wait_st", "epi_seg_fence+arrive", "epi_seg_st1", "epi_seg_math2(+act store)", "epi_seg_st2"]
+if not one_tile:
+    names = names3
+    tiles = tiles * 2          # counter 8 holds tile PAIRS for the two-tile kernel
 print(f"N={N} S={S}: {ms:.3f} ms, {N*S*920832/ms/1e9:.1f} TFLOP/s, tiles/CTA {tiles.mean():.1f}")
 for i, n in enumerate(names):
     if i == 8: continue
+    if i >= c.shape[1]: break
     per_tile = (c[:, i] / tiles)
     print(f"  {n:28s} per tile: mean {per_tile.mean():9.0f} clk  min {per_tile.min():9.0f}  max {per_tile.max():9.0f}")
 print("  (tensor-pipe floor per tile: 14.7k clk)")
+
+if not one_tile:
+    pairs0 = float(dbg[8].item())
+    d = detail / max(pairs0, 1)
+    print("CTA 0, clk per pair: weight-stage waits by stage index:")
+    print("  " + " ".join(f"{v:5.0f}" for v in d[:32].tolist()))
+    print("dfree waits by step, tile X / tile Y:")
+    print("  X " + " ".join(f"{v:5.0f}" for v in d[32:48].tolist()))
+    print("  Y " + " ".join(f"{v:5.0f}" for v in d[48:64].tolist()))
+    print("alo/ahi waits by step, tile X / tile Y:")
+    print("  X " + " ".join(f"{v:5.0f}" for v in d[64:80].tolist()))
+    print("  Y " + " ".join(f"{v:5.0f}" for v in d[80:96].tolist()))
+    print(f"layer_half total per pair (13 calls): {d[95].item():.0f} clk")
