@@ -48,7 +48,7 @@ constexpr uint32_t kOffSig = kOffW7 + 1024;                                     
 constexpr uint32_t kOffBars = kOffSig + 2048;
 // barrier indices (8 bytes each)
 constexpr uint32_t kBarFull = 0, kBarEmpty = 4, kBarDFull = 8, kBarDFree = 10, kBarALo = 12, kBarAHi = 14, kBarPexFull = 16,
-                   kBarPexEmpty = 18, kBarPedFull = 20, kBarPedEmpty = 22, kNumBars = 24;
+                   kBarPexEmpty = 18, kBarPedFull = 20, kBarPedEmpty = 22, kBarTurn = 24, kNumBars = 26;
 constexpr uint32_t kOffTmemHolder = kOffBars + kNumBars * 8;
 constexpr uint32_t kOffDetail = kOffTmemHolder + 16;                                 // PROFILE builds: 96 x int64
 constexpr uint32_t kSmemBytes = kOffDetail + 96 * 8 + 1024;
@@ -56,7 +56,7 @@ static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 // setmaxnreg moves registers inside the CTA's own pool (768 threads x 80 at launch): what the two small warpgroups give
 // back is exactly what the four epilogue warpgroups take
-constexpr int kRegsLaunch = 80, kRegsMisc = 56, kRegsEpi = 96, kRegsPE = 40;
+constexpr int kRegsLaunch = 80, kRegsMisc = 64, kRegsEpi = 96, kRegsPE = 32;
 static_assert(kRegsMisc + 4 * kRegsEpi + kRegsPE <= 6 * kRegsLaunch, "register pool budget");
 }  // namespace t3
 
@@ -109,9 +109,11 @@ __device__ __forceinline__ void load_pack64(uint32_t d_addr, const float* __rest
 
 // Second half of a layer.  The held first-half output `p_lo` may now overwrite A columns [a_addr, +32) (every reader of
 // the old activations has completed); its store is overlapped with the load of the first 32 accumulator columns.
+template <bool PROFILE>
 __device__ __forceinline__ void store_lo_load_pack64(uint32_t a_addr, const uint32_t (&p_lo)[32], uint32_t alo_bar, uint32_t d_addr,
                                                      const float* __restrict__ bias, bool relu, uint32_t dfree_bar, int lane,
-                                                     uint32_t (&p)[32]) {
+                                                     uint32_t (&p)[32], long long* tp) {
+    const long long t0 = PROFILE ? clock64() : 0;
     uint32_t v0[32];
     umma::tmem_ld32(d_addr, v0);
     {
@@ -121,12 +123,14 @@ __device__ __forceinline__ void store_lo_load_pack64(uint32_t a_addr, const uint
         umma::tmem_st16(a_addr, a);
         umma::tmem_st16(a_addr + 16, b);
     }
+    uint32_t v1[32];
+    umma::tmem_ld32(d_addr + 32, v1);          // in flight together with the stores (their source registers were read at issue)
     umma::tmem_wait_st();
     warp_arrive(alo_bar, lane);
-    uint32_t v1[32];
-    umma::tmem_ld32(d_addr + 32, v1);
+    if (PROFILE) tp[0] += clock64() - t0;
     umma::tmem_wait_ld();
     warp_arrive(dfree_bar, lane);
+    if (PROFILE) { asm volatile("" ::"r"(v0[31]), "r"(v1[31])); tp[1] += clock64() - t0; }
     pack32(v0, bias, relu, p);
     pack32(v1, bias + 32, relu, p + 16);
 }
@@ -201,145 +205,181 @@ __device__ __forceinline__ void save_act64(__nv_bfloat16* __restrict__ act_out, 
     mask_out[((row >> 7) * pk::kMaskWords + (feature >> 6)) * 128 + (row & 127)] = mbits;
 }
 
-// The MMA-issuing warp's state and primitives.  Tile indices are template parameters and every address is a 32-bit
-// shared-memory / TMEM address held in a register, so nothing but a handful of integer instructions sits between two
-// groups of tcgen05.mma.
-// PROFILE counters: prof[1] wait weights, [2] wait dfree, [3] wait alo/ahi, [4] wait PE; detail (shared memory, 96 x
-// int64): [0,32) weight wait per stage, [32,64) dfree wait per (tile, step), [64,96) alo/ahi wait per (tile, step).
-template <bool PROFILE>
-struct MmaIssuer {
+// One MMA-issuing warp PER TILE (warp 1: tile X, warp 2: tile Y).  Each runs the plain one-tile program - open stage,
+// wait for its own tile's dependencies, issue 8 MMAs, release the stage - and the two instruction streams meet in the
+// tensor pipe's queue: while one warp is between groups (barrier waits, bookkeeping; a single warp needs 150-300 clk for
+// that and the queue only covers ~290 clk) the other warp's MMAs keep the pipe busy.  A weight stage is released when
+// BOTH warps have committed it (empty barriers count 2), so every stage is still fetched once per tile pair.
+// Every address is a 32-bit shared-memory / TMEM address held in a register.
+// PROFILE counters: prof[1] wait weights, [2] wait dfree, [3] wait alo/ahi, [4] wait PE, [0] time inside issue blocks.
+template <int T, bool PROFILE>
+struct MmaTile {
     static constexpr uint32_t kI128 = umma::make_idesc_bf16(128, 128);
     static constexpr uint32_t kI16 = umma::make_idesc_bf16(128, 16);
     uint32_t bars, tmem;
     uint64_t ring_desc;                             // descriptor of ring slot 0; slot s / K block at byte offset o: + (s*32768 + o) >> 4
     bool leader;
     uint32_t cnt;                                   // weight stages opened
-    uint32_t n_dfree0, n_dfree1, n_alo0, n_alo1, n_ahi0, n_ahi1, acc0, acc1;
+    uint32_t n_dfree, n_ahi, n_alo, n_step;
     long long prof[5];
-    uint32_t detail, stage_id, step0, step1;
 
-    __device__ __forceinline__ void init(uint32_t bars_addr, uint32_t ring_addr, uint32_t tmem_base, bool is_leader, uint32_t detail_addr) {
+    __device__ __forceinline__ void init(uint32_t bars_addr, uint32_t ring_addr, uint32_t tmem_base, bool is_leader) {
         bars = bars_addr; tmem = tmem_base; leader = is_leader;
         ring_desc = umma::make_desc_k_sw128(ring_addr);
-        cnt = 0; n_dfree0 = n_dfree1 = n_alo0 = n_alo1 = n_ahi0 = n_ahi1 = acc0 = acc1 = 0;
-        detail = detail_addr; stage_id = step0 = step1 = 0;
+        cnt = 0; n_dfree = n_ahi = n_alo = n_step = 0;
 #pragma unroll
         for (int i = 0; i < 5; ++i) prof[i] = 0;
     }
     __device__ __forceinline__ uint32_t bar(uint32_t idx) const { return bars + 8u * idx; }
-    __device__ __forceinline__ void wait(uint32_t bar_addr, uint32_t parity, int slot, int detail_idx = -1) {
+    __device__ __forceinline__ void wait(uint32_t bar_addr, uint32_t parity, int slot) {
         if (PROFILE) {
             const long long t0 = clock64();
             umma::mbar_wait_u32(bar_addr, parity);
-            const long long dt = clock64() - t0;
-            prof[slot] += dt;
-            if (detail_idx >= 0 && leader) {
-                long long old;
-                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(old) : "r"(detail + 8u * (uint32_t)detail_idx));
-                asm volatile("st.shared.b64 [%0], %1;" ::"r"(detail + 8u * (uint32_t)detail_idx), "l"(old + dt));
-            }
+            prof[slot] += clock64() - t0;
         } else {
             umma::mbar_wait_u32(bar_addr, parity);
         }
-        umma::tc_fence_after();
     }
+    __device__ __forceinline__ void fence() { umma::tc_fence_after(); }     // once after a run of waits, before the MMAs
     // next weight stage present in shared memory; returns its descriptor offset (slot * 32768 >> 4)
     __device__ __forceinline__ uint32_t open() {
         const uint32_t slot = cnt & (t3::kSlots - 1);
-        wait(bar(t3::kBarFull + slot), (cnt >> 2) & 1u, 1, (int)(stage_id & 31u));
-        ++cnt; ++stage_id;
+        wait(bar(t3::kBarFull + slot), (cnt >> 2) & 1u, 1);
+        ++cnt;
         return slot * (t3::kSlotBytes >> 4);
     }
-    // the stage opened `back` opens ago is free once the MMAs issued so far have completed
-    __device__ __forceinline__ void release(uint32_t back) {
-        const uint32_t slot = (cnt - 1u - back) & (t3::kSlots - 1);
-        if (leader) umma::mma_commit_u32(bar(t3::kBarEmpty + slot));
-        __syncwarp();
+    __device__ __forceinline__ uint32_t empty_bar(uint32_t back) const { return bar(t3::kBarEmpty + ((cnt - 1u - back) & (t3::kSlots - 1))); }
+    __device__ __forceinline__ void wait_pe(uint32_t idx, uint32_t parity) { wait(bar(idx + T), parity, 4); }
+    __device__ __forceinline__ void begin_step() {      // the tile's accumulator has been read by its epilogue
+        wait(bar(t3::kBarDFree + T), (n_dfree & 1u) ^ 1u, 2);
+        ++n_dfree;
     }
-    __device__ __forceinline__ void commit(uint32_t idx) {
-        if (leader) umma::mma_commit_u32(bar(idx));
-        __syncwarp();
+    // Ping-pong between the two issuing warps: step n of tile X is queued before step n of tile Y, which is queued before
+    // step n+1 of tile X.  Left alone the two warps fall into lockstep (both tiles in the same phase, both waiting for their
+    // epilogues at the same time); with the turn token one tile's MMAs always cover the other tile's epilogue latency.
+    __device__ __forceinline__ void my_turn() {
+        if (T == 0) wait(bar(t3::kBarTurn + 1), (n_step & 1u) ^ 1u, 2);      // Y has queued step n-1
+        else wait(bar(t3::kBarTurn + 0), n_step & 1u, 2);                     // X has queued step n
+        ++n_step;
     }
-    __device__ __forceinline__ void wait_pe(uint32_t idx, uint32_t parity) { wait(bar(idx), parity, 4); }
-    template <int T> __device__ __forceinline__ void begin_step() {     // the tile's accumulator has been read by its epilogue
-        uint32_t& n = T ? n_dfree1 : n_dfree0;
-        uint32_t& st = T ? step1 : step0;
-        wait(bar(t3::kBarDFree + T), (n & 1u) ^ 1u, 2, 32 + T * 16 + (int)(st & 15u));
-        ++n; ++st;
-        (T ? acc1 : acc0) = 0;
-    }
-    template <int T> __device__ __forceinline__ void end_step() { commit(t3::kBarDFull + T); }
-    template <int T> __device__ __forceinline__ void need_lo() {
-        uint32_t& n = T ? n_alo1 : n_alo0;
-        wait(bar(t3::kBarALo + T), n & 1u, 3, 64 + T * 16 + (int)(((T ? step1 : step0) - 1u) & 15u));
-        ++n;
-    }
-    template <int T> __device__ __forceinline__ void need_hi() {
-        uint32_t& n = T ? n_ahi1 : n_ahi0;
-        wait(bar(t3::kBarAHi + T), n & 1u, 3, 64 + T * 16 + (int)(((T ? step1 : step0) - 1u) & 15u));
-        ++n;
-    }
-    // NKB K=64 blocks of TILE_BYTES each in the stage at descriptor offset `b_off`; A = TMEM columns a_col.. of tile T
-    template <int T, int NKB, uint32_t TILE_BYTES, uint32_t IDESC>
-    __device__ __forceinline__ void issue_ts(uint32_t a_col, uint32_t b_off) {
-        uint32_t& acc = T ? acc1 : acc0;
-        if (leader) {
-            const uint32_t d = tmem + t3::kColD + 128u * T;
-            const uint32_t a = tmem + t3::kColA + 128u * T + a_col;
-            const uint64_t bdesc = ring_desc + b_off;
+    __device__ __forceinline__ void pass_turn() { umma::mbar_arrive_u32(bar(t3::kBarTurn + T)); }   // leader lane, after its MMAs
+    // the same epilogue task signals alo BEFORE dfree: after begin_step() the first-half operand is known to be written
+    __device__ __forceinline__ void lo_implied() { ++n_alo; }
+    __device__ __forceinline__ void need_lo() { wait(bar(t3::kBarALo + T), n_alo & 1u, 3); ++n_alo; }
+    __device__ __forceinline__ void need_hi() { wait(bar(t3::kBarAHi + T), n_ahi & 1u, 3); ++n_ahi; }
+    // ---- unguarded pieces (callers hold the leader lane)
+    __device__ __forceinline__ void mma8(uint32_t a_col, uint32_t b_off, uint32_t first_acc) {     // two K=64 blocks of a 32 KB stage
+        const uint32_t d = tmem + t3::kColD + 128u * T;
+        const uint32_t a = tmem + t3::kColA + 128u * T + a_col;
+        const uint64_t bdesc = ring_desc + b_off;
 #pragma unroll
-            for (int kb = 0; kb < NKB; ++kb) {
+        for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma::mma_ts(d, a + 32u * kb + 8u * k, bdesc + (uint64_t)(kb * (TILE_BYTES >> 4) + 2 * k), IDESC, (kb | k) ? 1u : acc);
-            }
+            for (int k = 0; k < 4; ++k)
+                umma::mma_ts(d, a + 32u * kb + 8u * k, bdesc + (uint64_t)(kb * 1024 + 2 * k), kI128, (kb | k) ? 1u : first_acc);
         }
-        __syncwarp();
-        acc = 1;
     }
-    // one K block (NK16 K=16 slices) with A from a shared-memory PE tile
-    template <int T, int NK16>
-    __device__ __forceinline__ void issue_ss(uint64_t a_desc, uint32_t b_off) {
-        uint32_t& acc = T ? acc1 : acc0;
-        if (leader) {
-            const uint32_t d = tmem + t3::kColD + 128u * T;
-            const uint64_t bdesc = ring_desc + b_off;
+    template <int NK16> __device__ __forceinline__ void mma_pe(uint64_t a_desc, uint32_t b_off) {   // A = shared-memory PE tile
+        const uint32_t d = tmem + t3::kColD + 128u * T;
+        const uint64_t bdesc = ring_desc + b_off;
 #pragma unroll
-            for (int k = 0; k < NK16; ++k) umma::mma_ss(d, a_desc + 2u * k, bdesc + 2u * k, kI128, k ? 1u : acc);
-        }
-        __syncwarp();
-        acc = 1;
+        for (int k = 0; k < NK16; ++k) umma::mma_ss(d, a_desc + 2u * k, bdesc + 2u * k, kI128, k ? 1u : 0u);
     }
-    // a K = 256 layer half (or rgb_fn.0) for both tiles: [PE stage] kb01 kb23 of X, then of Y on the same stages
+    template <class F> __device__ __forceinline__ void issue(F&& f) {       // one group of MMAs + commits by the leader lane
+        long long t0 = 0;
+        if (PROFILE) t0 = clock64();
+        if (leader) f();
+        __syncwarp();
+        if (PROFILE) prof[0] += clock64() - t0;
+    }
+    // mlp.0 half: one 16 KB stage, A = PE(x)
+    __device__ __forceinline__ void first_layer_half(uint64_t descPE) {
+        const uint32_t b = open();
+        begin_step();
+        my_turn();
+        fence();
+        issue([&] {
+            mma_pe<4>(descPE, b);
+            umma::mma_commit_u32(empty_bar(0));
+            umma::mma_commit_u32(bar(t3::kBarDFull + T));
+            pass_turn();
+        });
+    }
+    // a K = 256 layer half (or rgb_fn.0): [PE stage] kb01 kb23.  A second half has no new A operand to wait for and issues
+    // its 16 MMAs back to back.
     template <bool FIRST_HALF, int PE_K16>
-    __device__ __forceinline__ void layer_half(uint64_t descA0, uint64_t descA1, uint32_t pe_done_idx) {
+    __device__ __forceinline__ void layer_half(uint64_t descA, uint32_t pe_done_idx) {
+        constexpr bool PE = PE_K16 > 0;
+        constexpr int NK = PE ? PE_K16 : 1;
         uint32_t bP = 0;
-        if (PE_K16 > 0) bP = open();
+        if (PE) bP = open();
         const uint32_t b01 = open();
-        begin_step<0>();
-        if (PE_K16 > 0) {
-            issue_ss<0, PE_K16 ? PE_K16 : 1>(descA0, bP);
-            if (pe_done_idx) commit(pe_done_idx);
-        }
-        if (FIRST_HALF) need_lo<0>();
-        issue_ts<0, 2, 16384, kI128>(0, b01);
         const uint32_t b23 = open();
-        if (FIRST_HALF) need_hi<0>();
-        issue_ts<0, 2, 16384, kI128>(64, b23);
-        end_step<0>();
-        begin_step<1>();
-        if (PE_K16 > 0) {
-            issue_ss<1, PE_K16 ? PE_K16 : 1>(descA1, bP);
-            if (pe_done_idx) commit(pe_done_idx + 1);
-            release(2);
+        const uint32_t e_p = empty_bar(2), e_01 = empty_bar(1), e_23 = empty_bar(0);
+        begin_step();
+        if (FIRST_HALF) lo_implied();
+        my_turn();
+        fence();
+        issue([&] {
+            if (PE) {
+                mma_pe<NK>(descA, bP);
+                if (pe_done_idx) umma::mma_commit_u32(bar(pe_done_idx + T));
+                umma::mma_commit_u32(e_p);
+            }
+            mma8(0, b01, PE ? 1u : 0u);
+            umma::mma_commit_u32(e_01);
+            if (!FIRST_HALF) { mma8(64, b23, 1u); umma::mma_commit_u32(e_23); umma::mma_commit_u32(bar(t3::kBarDFull + T)); pass_turn(); }
+        });
+        if (FIRST_HALF) {               // K blocks 2,3 of the new operand are written ~500 clk after K blocks 0,1
+            need_hi();
+            fence();
+            issue([&] { mma8(64, b23, 1u); umma::mma_commit_u32(e_23); umma::mma_commit_u32(bar(t3::kBarDFull + T)); pass_turn(); });
         }
-        if (FIRST_HALF) need_lo<1>();
-        issue_ts<1, 2, 16384, kI128>(0, b01);
-        release(1);
-        if (FIRST_HALF) need_hi<1>();
-        issue_ts<1, 2, 16384, kI128>(64, b23);
-        release(0);
-        end_step<1>();
+    }
+    // rgb_fn.2: r (A columns 0..63) -> 16 columns, one 4 KB stage
+    __device__ __forceinline__ void last_step() {
+        const uint32_t b = open();
+        begin_step();
+        need_lo();
+        my_turn();
+        fence();
+        issue([&] {
+            const uint32_t d = tmem + t3::kColD + 128u * T;
+            const uint32_t a = tmem + t3::kColA + 128u * T;
+            const uint64_t bdesc = ring_desc + b;
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma::mma_ts(d, a + 32u * kb + 8u * k, bdesc + (uint64_t)(kb * 128 + 2 * k), kI16, (kb | k) ? 1u : 0u);
+            }
+            umma::mma_commit_u32(empty_bar(0));
+            umma::mma_commit_u32(bar(t3::kBarDFull + T));
+            pass_turn();
+        });
+    }
+    // the whole per-CTA program of tile T
+    __device__ __forceinline__ void run(uint32_t sbase, int64_t num_pairs) {
+        const uint64_t descPE = umma::make_desc_k_sw128(sbase + t3::kOffPE + T * 16384);
+        const uint64_t descPD = umma::make_desc_k_sw128(sbase + t3::kOffPEDir + T * 16384);
+        uint32_t it = 0;
+        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
+            wait_pe(t3::kBarPexFull, it & 1u);
+            first_layer_half(descPE);                                  // mlp.0
+            first_layer_half(descPE);
+#pragma unroll 1
+            for (int l = 1; l <= 6; ++l) {                             // mlp.2/4/6, feature_fn.0 (PE(x) K block first), feature_fn.2/4
+                if (l == 4) {
+                    layer_half<true, 4>(descPE, 0);
+                    layer_half<false, 4>(descPE, t3::kBarPexEmpty);    // last reader of PE(x)
+                } else {
+                    layer_half<true, 0>(0, 0);
+                    layer_half<false, 0>(0, 0);
+                }
+            }
+            wait_pe(t3::kBarPedFull, it & 1u);
+            layer_half<true, 2>(descPD, t3::kBarPedEmpty);             // rgb_fn.0: PE(dir) K block + feat
+            last_step();                                               // rgb_fn.2
+        }
     }
 };
 
@@ -366,7 +406,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
 
     if (tid == 0) {
         uint64_t* b = (uint64_t*)(smem + t3::kOffBars);
-        for (int i = 0; i < t3::kSlots; ++i) { umma::mbar_init(&b[t3::kBarFull + i], 1); umma::mbar_init(&b[t3::kBarEmpty + i], 1); }
+        for (int i = 0; i < t3::kSlots; ++i) { umma::mbar_init(&b[t3::kBarFull + i], 1); umma::mbar_init(&b[t3::kBarEmpty + i], 2); }
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&b[t3::kBarDFull + i], 1);
             umma::mbar_init(&b[t3::kBarDFree + i], t3::kEpiWarps);
@@ -376,6 +416,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             umma::mbar_init(&b[t3::kBarPexEmpty + i], 1);
             umma::mbar_init(&b[t3::kBarPedFull + i], t3::kPEWarps);
             umma::mbar_init(&b[t3::kBarPedEmpty + i], 1);
+            umma::mbar_init(&b[t3::kBarTurn + i], 1);
         }
         umma::fence_mbar_init();
     }
@@ -420,67 +461,25 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 }
             }
             if (PROFILE && lane == 0 && warp == 0) dbg[blockIdx.x * 16 + 5] = t_wait;
-        } else if (warp == 1) {
-            // -------------------------------------------------------------- MMA issuer (warp-uniform, one lane issues)
-            MmaIssuer<PROFILE> m;
-            m.init(bars, sbase + t3::kOffRing, tmem, umma::elect_one(), sbase + t3::kOffDetail);
-            const uint64_t descPE0 = umma::make_desc_k_sw128(sbase + t3::kOffPE);
-            const uint64_t descPE1 = umma::make_desc_k_sw128(sbase + t3::kOffPE + 16384);
-            const uint64_t descPD0 = umma::make_desc_k_sw128(sbase + t3::kOffPEDir);
-            const uint64_t descPD1 = umma::make_desc_k_sw128(sbase + t3::kOffPEDir + 16384);
-            uint32_t it = 0;
+        } else {
+            // -------------------------------------------------------------- MMA issuers: warp 1 tile X, warp 2 tile Y
+            const bool elected = umma::elect_one();
             const long long t_begin = PROFILE ? clock64() : 0;
-            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
-                // ---- mlp.0: A = PE(x) tile, one 16 KB stage per N half
-                m.wait_pe(t3::kBarPexFull + 0, it & 1u);
-                m.wait_pe(t3::kBarPexFull + 1, it & 1u);
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t b = m.open();
-                    m.template begin_step<0>();
-                    m.template issue_ss<0, 4>(descPE0, b);
-                    m.template end_step<0>();
-                    m.template begin_step<1>();
-                    m.template issue_ss<1, 4>(descPE1, b);
-                    m.template end_step<1>();
-                    m.release(0);
+            if (warp == 1) {
+                MmaTile<0, PROFILE> m;
+                m.init(bars, sbase + t3::kOffRing, tmem, elected);
+                m.run(sbase, num_pairs);
+                if (PROFILE && elected) {
+                    dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
+                    for (int i = 1; i < 5; ++i) dbg[blockIdx.x * 16 + i] = m.prof[i];
+                    dbg[blockIdx.x * 16 + 9] = m.prof[0];
+                    dbg[blockIdx.x * 16 + 8] = (num_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
                 }
-                // ---- mlp.2/4/6, feature_fn.0 (PE(x) K block first; its second half is the last reader of PE(x)), feature_fn.2/4
-#pragma unroll 1
-                for (int l = 1; l <= 6; ++l) {
-                    if (l == 4) {
-                        m.template layer_half<true, 4>(descPE0, descPE1, 0);
-                        m.template layer_half<false, 4>(descPE0, descPE1, t3::kBarPexEmpty);
-                    } else {
-                        m.template layer_half<true, 0>(0, 0, 0);
-                        m.template layer_half<false, 0>(0, 0, 0);
-                    }
-                }
-                // ---- rgb_fn.0: PE(dir) K block + feat -> 128 columns
-                m.wait_pe(t3::kBarPedFull + 0, it & 1u);
-                m.wait_pe(t3::kBarPedFull + 1, it & 1u);
-                m.template layer_half<true, 2>(descPD0, descPD1, t3::kBarPedEmpty);
-                // ---- rgb_fn.2: r (A columns 0..63) -> 16 columns
-                {
-                    const uint32_t b = m.open();
-                    m.template begin_step<0>();
-                    m.template need_lo<0>();
-                    m.template issue_ts<0, 2, 2048, MmaIssuer<PROFILE>::kI16>(0, b);
-                    m.template end_step<0>();
-                    m.template begin_step<1>();
-                    m.template need_lo<1>();
-                    m.template issue_ts<1, 2, 2048, MmaIssuer<PROFILE>::kI16>(0, b);
-                    m.template end_step<1>();
-                    m.release(0);
-                }
+            } else {
+                MmaTile<1, PROFILE> m;
+                m.init(bars, sbase + t3::kOffRing, tmem, elected);
+                m.run(sbase, num_pairs);
             }
-            if (PROFILE && lane == 0) {
-                dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
-                for (int i = 1; i < 5; ++i) dbg[blockIdx.x * 16 + i] = m.prof[i];
-                dbg[blockIdx.x * 16 + 8] = it;
-            }
-            __syncwarp();
-            if (PROFILE && blockIdx.x == 0) for (int i = lane; i < 96; i += 32) dbg[148 * 16 + i] = ((long long*)(smem + t3::kOffDetail))[i];
         }
     } else if (warp >= 20) {
         // ------------------------------------------------------------------ PE producers (128 threads, thread = row)
@@ -542,6 +541,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
         const uint32_t bar_alo = bars + 8u * (t3::kBarALo + t), bar_ahi = bars + 8u * (t3::kBarAHi + t);
         uint32_t nd = 0;                                 // accumulators consumed
         long long t_wait = 0;
+        long long tp[4] = {0, 0, 0, 0};
         const long long t_begin = PROFILE ? clock64() : 0;
         auto wait_d = [&]() {
             const long long t0 = PROFILE ? clock64() : 0;
@@ -563,13 +563,17 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 const float* bias = sBias + layer * 256 + wh * 64;
                 uint32_t p_lo[32];
                 wait_d();
+                const long long t_h0 = PROFILE ? clock64() : 0;
                 load_pack64(d_addr, bias, relu, bar_dfree, lane, p_lo);
+                if (PROFILE) { asm volatile("" ::"r"(p_lo[0]), "r"(p_lo[31])); tp[3] += clock64() - t_h0; }
                 if (save) save_act64(act_out, mask_out, row, layer * 256 + wh * 64, p_lo);
                 if (layer == 6) sig_part = dot_bf16x64(p_lo, sW7 + wh * 64, sig_part);
                 wait_d();
                 uint32_t p_hi[32];
-                store_lo_load_pack64(a_addr, p_lo, bar_alo, d_addr, bias + 128, relu, bar_dfree, lane, p_hi);   // features 0..127 -> A 0..63
+                const long long t_h1 = PROFILE ? clock64() : 0;
+                store_lo_load_pack64<PROFILE>(a_addr, p_lo, bar_alo, d_addr, bias + 128, relu, bar_dfree, lane, p_hi, tp);   // features 0..127 -> A 0..63
                 store_a32(a_addr + 64, p_hi, bar_ahi, lane);          // features 128..255 -> A columns 64..127
+                if (PROFILE) tp[2] += clock64() - t_h1;
                 if (save) save_act64(act_out, mask_out, row, layer * 256 + 128 + wh * 64, p_hi);
                 if (layer == 6) sig_part = dot_bf16x64(p_hi, sW7 + 128 + wh * 64, sig_part);
             }
@@ -605,7 +609,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 }
             }
         }
-        if (PROFILE && tid == 128) { dbg[blockIdx.x * 16 + 6] = clock64() - t_begin; dbg[blockIdx.x * 16 + 7] = t_wait; }
+        if (PROFILE && tid == 128) { dbg[blockIdx.x * 16 + 6] = clock64() - t_begin; dbg[blockIdx.x * 16 + 7] = t_wait; for (int i = 0; i < 4; ++i) dbg[blockIdx.x * 16 + 10 + i] = tp[i]; }
     }
     umma::tc_fence_before();
     __syncthreads();

@@ -182,7 +182,7 @@ extern "C" int nerf_debug_tmem_bw(int nwarps, int iters, int mode, long long* ou
 namespace nerf {
 __global__ void __launch_bounds__(1024, 1)
 tmem_contention_probe_kernel(int n_mma, int N, int d_col, int a_col, int nw, int ld_mode, int ld_col, int ld_span, int commit_every,
-                             long long* out) {
+                             int alt_every, long long* out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint32_t holder;
@@ -205,11 +205,15 @@ tmem_contention_probe_kernel(int n_mma, int N, int d_col, int a_col, int nw, int
         const uint64_t bdesc = umma::make_desc_k_sw128(umma::smem_u32(smem + 16384));
         const long long t0 = clock64();
         if (leader) {
-            int since = 0;
+            int since = 0, run_len = 0;
+            uint32_t sel = 0;
             for (int i = 0; i < n_mma; ++i) {
                 const uint32_t k = (uint32_t)(i & 3);
-                if (a_col >= 0) umma::mma_ts(tmem + (uint32_t)d_col, tmem + (uint32_t)a_col + 8u * (uint32_t)(i & 15), bdesc + 2u * k, idesc, 1u);
-                else umma::mma_ss(tmem + (uint32_t)d_col, adesc + 2u * k, bdesc + 2u * k, idesc, 1u);
+                // alt_every > 0: switch accumulator (and A region) between two tiles every alt_every MMAs, as the two-tile kernel does
+                uint32_t fresh = 1u;                                                           // first MMA of a run overwrites
+                if (alt_every > 0 && ++run_len == alt_every) { run_len = 0; sel ^= 1u; fresh = 0u; }
+                if (a_col >= 0) umma::mma_ts(tmem + (uint32_t)d_col + 128u * sel, tmem + (uint32_t)a_col + 128u * sel + 8u * (uint32_t)(i & 15), bdesc + 2u * k, idesc, fresh);
+                else umma::mma_ss(tmem + (uint32_t)d_col + 128u * sel, adesc + 2u * k, bdesc + 2u * k, idesc, fresh);
                 if (commit_every > 0 && ++since == commit_every) { umma::mma_commit(&dummy_bar); since = 0; }
             }
             umma::mma_commit(&done_bar);
@@ -254,13 +258,13 @@ tmem_contention_probe_kernel(int n_mma, int N, int d_col, int a_col, int nw, int
 }  // namespace nerf
 
 extern "C" int nerf_debug_tmem_contention(int n_mma, int N, int d_col, int a_col, int nw, int ld_mode, int ld_col, int ld_span,
-                                          int commit_every, long long* out, void* stream) {
+                                          int commit_every, int alt_every, long long* out, void* stream) {
     using namespace nerf;
     NERF_REQUIRE(nw >= 0 && nw <= 28 && N >= 16 && N <= 256 && d_col >= 0 && d_col + N <= 512 && ld_span >= 32, "tmem_contention: bad args");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(tmem_contention_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr = true; }
     tmem_contention_probe_kernel<<<1, (4 + (nw > 0 ? nw : 0)) * 32, 65536, (cudaStream_t)stream>>>(n_mma, N, d_col, a_col, nw, ld_mode,
-                                                                                                ld_col, ld_span, commit_every, out);
+                                                                                                ld_col, ld_span, commit_every, alt_every, out);
     return check_launch("nerf_debug_tmem_contention");
 }
 

@@ -8,14 +8,14 @@ import torch
 import _native as nat
 fn = nat.lib().nerf_debug_tmem_contention
 fn.restype = ctypes.c_int
-fn.argtypes = [ctypes.c_int] * 9 + [ctypes.c_void_p, ctypes.c_void_p]
+fn.argtypes = [ctypes.c_int] * 10 + [ctypes.c_void_p, ctypes.c_void_p]
 out = torch.zeros(8, dtype=torch.int64, device="cuda")
 NM = 4000
 
-def run(N, d_col, a_col, nw, mode, ld_col, ld_span, commit_every=0, nm=NM):
+def run(N, d_col, a_col, nw, mode, ld_col, ld_span, commit_every=0, nm=NM, alt_every=0):
     for _ in range(2):
         out.zero_()
-        nat.check(fn(nm, N, d_col, a_col, nw, mode, ld_col, ld_span, commit_every, nat.ptr(out), None), "probe")
+        nat.check(fn(nm, N, d_col, a_col, nw, mode, ld_col, ld_span, commit_every, alt_every, nat.ptr(out), None), "probe")
         torch.cuda.synchronize()
     cyc, ldb, stb, iss = (out[i].item() for i in range(4))
     return cyc / nm, ldb / cyc, stb / cyc, iss / nm
@@ -29,6 +29,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "queue":
     for ce in (0, 32, 16, 8, 4, 2, 1):
         c, _, _, i = run(128, 0, 256, 0, 0, 0, 32, ce)
         print(f"  {ce:4d} {c:8.1f}")
+    print("accumulator switching: alt_every  clk/MMA (N=128, A in TMEM; 16 epilogue-like ld+st warps running)")
+    for ae in (0, 64, 16, 8, 4, 1):
+        c, _, _, i = run(128, 0, 256, 0, 0, 0, 32, 0, NM, ae)
+        c2, l2, s2, _ = run(128, 0, 256, 16, 2, 0, 256, 0, NM, ae)
+        print(f"  {ae:4d} {c:8.1f}   with 16 ld+st warps: {c2:8.1f} (ld {l2:.0f} B/clk, st {s2:.0f} B/clk)")
     sys.exit(0)
 
 print("N d_col a_src   ld_warps mode  ld_cols      clk/MMA  issue clk/MMA  ld B/clk  st B/clk")

@@ -33,6 +33,7 @@ import os
 G = int(os.environ.get("NERF_TC_MAX_CTAS", "148"))
 for it in range(3):
     dbg.zero_()
+    dbg[148 * 16 + 120] = int(os.environ.get('NERF_PROF_FLAGS', '0'))
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     nat.check(fn(nat.ptr(packed), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, nat.ptr(sigma), nat.ptr(rgb), nat.ptr(dbg), nat.stream()), "profile")
@@ -44,8 +45,8 @@ c = dbg[:148 * 16].view(148, 16).double().cpu()[:G]
 tiles = c[:, 8].clamp(min=1)
 one_tile = os.environ.get("NERF_TC_ONE_TILE") == "1"
 names3 = ["mma_total", "mma_wait_full(weights)", "mma_wait_dfree(acc read)", "mma_wait_alo/ahi(epilogue)", "mma_wait_pe",
-          "producer_wait_empty", "epiX_total", "epiX_wait_dfull", "pairs", "mma_issue_ts(+backpressure)", "epiX_ld+wait",
-          "epiX_pack", "epiX_st+wait+arrive", "mma_commits"]
+          "producer_wait_empty", "epiX_total", "epiX_wait_dfull", "pairs", "mma_in_issue_blocks(layer_half)", "epiX_h1: dfull->alo (x7)",
+          "epiX_h1: dfull->dfree (x7)", "epiX_h1: dfull->ahi (x7)", "epiX_h0: dfull->packed (x7)"]
 names = ["mma_total", "mma_wait_full(weights)", "mma_wait_edone(epilogue)", "mma_wait_pe", "producer_wait_empty", "epi_total",
          "epi_wait_dfull", "epi_pe_time", "tiles", "epi_seg_ld+wait", "epi_seg_math1", "epi_seg_wait_st", "epi_seg_fence+arrive", "epi_seg_st1", "epi_seg_math2(+act store)", "epi_seg_st2"]
 if not one_tile:
