@@ -35,7 +35,7 @@ constexpr int kTileM = 128;
 constexpr int kSlots = 4;
 constexpr uint32_t kSlotBytes = 32768;
 constexpr int kThreads = 768;
-constexpr int kEpiWarps = 8;           // per tile
+constexpr int kEpiWarps = 16;          // every epilogue warp takes part in every task
 constexpr int kPEWarps = 4;
 constexpr uint32_t kColD = 0, kColA = 256;      // + 128 * tile
 
@@ -44,8 +44,8 @@ constexpr uint32_t kOffPEDir = 32768;      // PE(dir) tiles of X and Y
 constexpr uint32_t kOffRing = 65536;
 constexpr uint32_t kOffBias = kOffRing + kSlots * kSlotBytes;
 constexpr uint32_t kOffW7 = kOffBias + ((pk::kBiasFloats * 4 + 15) / 16) * 16;     // density_fn.0 weights, fp32 [256]
-constexpr uint32_t kOffSig = kOffW7 + 1024;                                          // sigma partial sums [2 tiles][2][128]
-constexpr uint32_t kOffBars = kOffSig + 2048;
+constexpr uint32_t kOffSig = kOffW7 + 1024;                                          // sigma partial sums [2 tiles][4][128]
+constexpr uint32_t kOffBars = kOffSig + 4096;
 // barrier indices (8 bytes each)
 constexpr uint32_t kBarFull = 0, kBarEmpty = 4, kBarDFull = 8, kBarDFree = 10, kBarALo = 12, kBarAHi = 14, kBarPexFull = 16,
                    kBarPexEmpty = 18, kBarPedFull = 20, kBarPedEmpty = 22, kBarTurn = 24, kNumBars = 26;
@@ -187,6 +187,34 @@ __device__ __forceinline__ float dot_bf16x64(const uint32_t (&p)[32], const floa
         acc = fmaf(__uint_as_float(p[2 * j + 1] & 0xFFFF0000u), w4.w, acc);
     }
     return acc;
+}
+
+__device__ __forceinline__ float dot_bf16x32(const uint32_t (&p)[16], const float* __restrict__ w, float acc) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 w4 = *(const float4*)(w + 4 * j);
+        acc = fmaf(__uint_as_float(p[2 * j] << 16), w4.x, acc);
+        acc = fmaf(__uint_as_float(p[2 * j] & 0xFFFF0000u), w4.y, acc);
+        acc = fmaf(__uint_as_float(p[2 * j + 1] << 16), w4.z, acc);
+        acc = fmaf(__uint_as_float(p[2 * j + 1] & 0xFFFF0000u), w4.w, acc);
+    }
+    return acc;
+}
+
+// training, 32 features of one row: bf16 activations (four 16-byte chunks) + the matching half of the 64-bit sign word
+__device__ __forceinline__ void save_act32(__nv_bfloat16* __restrict__ act_out, unsigned long long* __restrict__ mask_out,
+                                           int64_t row, int feature, const uint32_t (&p)[16]) {
+    uint4* chunk = (uint4*)(act_out + pk::tiled_offset(row, feature, pk::kActChunks));
+    uint32_t mbits = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) chunk[j * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        mbits |= (uint32_t)((p[j] & 0x00007FFFu) != 0u) << (2 * j);
+        mbits |= (uint32_t)((p[j] & 0x7FFF0000u) != 0u) << (2 * j + 1);
+    }
+    uint32_t* words = (uint32_t*)mask_out;           // little-endian: features 0..31 of the block are the low half
+    words[(((row >> 7) * pk::kMaskWords + (feature >> 6)) * 128 + (row & 127)) * 2 + ((feature >> 5) & 1)] = mbits;
 }
 
 // training: keep what the next layer consumes (post-activation bf16, tiled chunk-major, pack_layout.cuh) and the 64-bit
@@ -528,78 +556,108 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: warps 4-11 tile X, 12-19 tile Y
+        // ------------------------------------------------------------------ epilogue: all 16 warps work on every task
+        // (tile t, step): the TMEM -> register path delivers ~13 B/clk per warp whatever else is going on, so a task's
+        // latency is set by how many warps share it.  Thread = (row r, 32 of the 128 accumulator columns).
         reg_inc<t3::kRegsEpi>();
-        const int t = (warp >= 12) ? 1 : 0;
         const int q = warp & 3;                          // TMEM lane quarter this warp may touch
-        const int wh = ((warp - 4) >> 2) & 1;            // column half handled by this warp
+        const int cq = (warp - 4) >> 2;                  // column quarter (32 accumulator columns, 32 features)
         const int r = q * 32 + lane;                     // row (sample) inside the tile
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(wh * 64);
-        const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(wh * 32);
-        const uint32_t bar_dfull = bars + 8u * (t3::kBarDFull + t), bar_dfree = bars + 8u * (t3::kBarDFree + t);
-        const uint32_t bar_alo = bars + 8u * (t3::kBarALo + t), bar_ahi = bars + 8u * (t3::kBarAHi + t);
-        uint32_t nd = 0;                                 // accumulators consumed
+        uint32_t nd[2] = {0, 0};                         // accumulators consumed per tile
         long long t_wait = 0;
         long long tp[4] = {0, 0, 0, 0};
         const long long t_begin = PROFILE ? clock64() : 0;
-        auto wait_d = [&]() {
+        auto wait_d = [&](int t) {
             const long long t0 = PROFILE ? clock64() : 0;
-            umma::mbar_wait_u32(bar_dfull, nd & 1u);
+            umma::mbar_wait_u32(bars + 8u * (t3::kBarDFull + t), nd[t] & 1u);
             if (PROFILE) t_wait += clock64() - t0;
             umma::tc_fence_after();
-            ++nd;
+            ++nd[t];
         };
 
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-            const int64_t tile = pair * 2 + t;
-            const int64_t row = tile * t3::kTileM + r;
-            const bool save = (act_out != nullptr) && (tile < num_tiles);
-            // ---- 7 hidden layers: h0 is held in registers until h1's MMAs (the last readers of the old A) are done
-            float sig_part = 0.f;
+            const int64_t row0 = pair * 2 * t3::kTileM + r;          // this thread's row in tile X (tile Y: + 128)
+            const bool save0 = (act_out != nullptr), save1 = (act_out != nullptr) && (pair * 2 + 1 < num_tiles);
+            float sig_part[2] = {0.f, 0.f};
 #pragma unroll 1
             for (int layer = 0; layer < 7; ++layer) {
                 const bool relu = (layer != 6);                       // feature_fn.4 is linear (nerf_model.py:347)
-                const float* bias = sBias + layer * 256 + wh * 64;
-                uint32_t p_lo[32];
-                wait_d();
-                const long long t_h0 = PROFILE ? clock64() : 0;
-                load_pack64(d_addr, bias, relu, bar_dfree, lane, p_lo);
-                if (PROFILE) { asm volatile("" ::"r"(p_lo[0]), "r"(p_lo[31])); tp[3] += clock64() - t_h0; }
-                if (save) save_act64(act_out, mask_out, row, layer * 256 + wh * 64, p_lo);
-                if (layer == 6) sig_part = dot_bf16x64(p_lo, sW7 + wh * 64, sig_part);
-                wait_d();
-                uint32_t p_hi[32];
-                const long long t_h1 = PROFILE ? clock64() : 0;
-                store_lo_load_pack64<PROFILE>(a_addr, p_lo, bar_alo, d_addr, bias + 128, relu, bar_dfree, lane, p_hi, tp);   // features 0..127 -> A 0..63
-                store_a32(a_addr + 64, p_hi, bar_ahi, lane);          // features 128..255 -> A columns 64..127
-                if (PROFILE) tp[2] += clock64() - t_h1;
-                if (save) save_act64(act_out, mask_out, row, layer * 256 + 128 + wh * 64, p_hi);
-                if (layer == 6) sig_part = dot_bf16x64(p_hi, sW7 + 128 + wh * 64, sig_part);
+                const float* bias = sBias + layer * 256 + cq * 32;
+                uint32_t hold[2][16];                                 // first-half outputs of X and Y, kept until the tile's second half
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {                         // ---- first halves: X then Y
+                    const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
+                    wait_d(t);
+                    const long long t_h0 = PROFILE ? clock64() : 0;
+                    uint32_t v[32];
+                    umma::tmem_ld32(d_addr, v);
+                    umma::tmem_wait_ld();
+                    warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
+                    pack32(v, bias, relu, hold[t]);
+                    if (PROFILE && t == 0) { asm volatile("" ::"r"(hold[0][0]), "r"(hold[0][15])); tp[3] += clock64() - t_h0; }
+                    if (t == 0 ? save0 : save1) save_act32(act_out, mask_out, row0 + t * 128, layer * 256 + cq * 32, hold[t]);
+                    if (layer == 6) sig_part[t] = dot_bf16x32(hold[t], sW7 + cq * 32, sig_part[t]);
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {                         // ---- second halves: the held half goes in place first
+                    const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
+                    const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(cq * 16);
+                    wait_d(t);
+                    const long long t_h1 = PROFILE ? clock64() : 0;
+                    uint32_t v[32];
+                    umma::tmem_ld32(d_addr, v);
+                    umma::tmem_st16(a_addr, hold[t]);                 // features 0..127 -> A columns 0..63
+                    umma::tmem_wait_st();
+                    warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
+                    if (PROFILE && t == 0) tp[0] += clock64() - t_h1;
+                    umma::tmem_wait_ld();
+                    warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
+                    if (PROFILE && t == 0) { asm volatile("" ::"r"(v[31])); tp[1] += clock64() - t_h1; }
+                    uint32_t p[16];
+                    pack32(v, bias + 128, relu, p);
+                    umma::tmem_st16(a_addr + 64, p);                  // features 128..255 -> A columns 64..127
+                    umma::tmem_wait_st();
+                    warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
+                    if (PROFILE && t == 0) tp[2] += clock64() - t_h1;
+                    if (t == 0 ? save0 : save1) save_act32(act_out, mask_out, row0 + t * 128, layer * 256 + 128 + cq * 32, p);
+                    if (layer == 6) sig_part[t] = dot_bf16x32(p, sW7 + 128 + cq * 32, sig_part[t]);
+                }
             }
-            // density_fn.0 (nerf_model.py:350-353): this warp's 128 of the 256 products; the wh = 0 warp of the same rows adds
-            // the two partial sums at the last step (ordered behind this write by the alo arrive below and the MMA commit)
-            sSig[(t * 2 + wh) * 128 + r] = sig_part;
+            // density_fn.0 (nerf_model.py:350-353): this warp's 64 of the 256 products; the cq = 0 warp of the same rows adds
+            // the four partial sums at the last step (ordered behind this write by the alo arrive below and the MMA commit)
+#pragma unroll
+            for (int t = 0; t < 2; ++t) sSig[(t * 4 + cq) * 128 + r] = sig_part[t];
             // ---- rgb_fn.0: r = relu(. + b) overwrites feat (every reader of feat has completed)
-            {
-                uint32_t p[32];
-                wait_d();
-                load_pack64(d_addr, sBias + pk::kBiasR0 + wh * 64, true, bar_dfree, lane, p);
-                store_a32(a_addr, p, bar_alo, lane);                  // r features 0..127 -> A columns 0..63
-                if (save) save_act64(act_out, mask_out, row, 1792 + wh * 64, p);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
+                const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(cq * 16);
+                wait_d(t);
+                uint32_t v[32], p[16];
+                umma::tmem_ld32(d_addr, v);
+                umma::tmem_wait_ld();
+                warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
+                pack32(v, sBias + pk::kBiasR0 + cq * 32, true, p);
+                umma::tmem_st16(a_addr, p);                           // r features 0..127 -> A columns 0..63
+                umma::tmem_wait_st();
+                warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
+                if (t == 0 ? save0 : save1) save_act32(act_out, mask_out, row0 + t * 128, 1792 + cq * 32, p);
             }
             // ---- rgb_fn.2: columns 0..2 -> sigmoid(. + b) (nerf_model.py:358-359); sigma = relu(feat . w7 + b7)
-            {
-                wait_d();
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int64_t row = row0 + t * 128;
+                wait_d(t);
                 uint32_t v[4] = {0u, 0u, 0u, 0u};
                 float sg = 0.f;
-                if (wh == 0) {
+                if (cq == 0) {
                     umma::tmem_ld4(tmem + lane_base + t3::kColD + 128u * (uint32_t)t, v);
-                    sg = sSig[(t * 2 + 0) * 128 + r] + sSig[(t * 2 + 1) * 128 + r];
+                    sg = (sSig[(t * 4 + 0) * 128 + r] + sSig[(t * 4 + 1) * 128 + r]) + (sSig[(t * 4 + 2) * 128 + r] + sSig[(t * 4 + 3) * 128 + r]);
                     umma::tmem_wait_ld();
                 }
-                warp_arrive(bar_dfree, lane);
-                if (wh == 0 && row < total) {
+                warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
+                if (cq == 0 && row < total) {
                     sigma_out[row] = fmaxf(sg + sBias[pk::kBiasSigma], 0.f);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
