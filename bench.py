@@ -335,7 +335,7 @@ def main():
     tf = ROOT / "profiles" / "mlp_tc_traffic.json"
     if tf.exists():
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "mlp_tc_kernel", "achieved": achieved, "peak": pk["tflops_sustained"],
+    roofline = {"bound": "tensor", "kernel": "mlp_tc3_kernel", "achieved": achieved, "peak": pk["tflops_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
                 "peak_source": f"{pk['source']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); "
                                f"burst {pk['tflops_burst']}",

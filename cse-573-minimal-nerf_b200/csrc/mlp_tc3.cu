@@ -5,8 +5,7 @@
 //     L2 -> SM weight stream per sample is halved (mlp_tc.cu streams 0.92 MB per tile at ~36 B/clk/SM, close to the
 //     ~42 B/clk/SM the L2 can deliver to all 148 SMs at once);
 //   * the MMA -> epilogue -> MMA dependency of one tile (a layer needs the previous layer's ReLU'd output) is hidden
-//     behind the other tile's MMAs: the issue order per 256-wide half layer is  X.kb01 X.kb23 | Y.kb01 Y.kb23, each
-//     tile has its own epilogue warps, and a tile's epilogue has one full half-step of the other tile to finish.
+//     behind the other tile's MMAs: steps alternate X, Y, X, Y (turn token between the two issuing warps).
 //
 // TMEM (512 columns): D_X 0..127, D_Y 128..255 (one fp32 accumulator of N = 128 per tile), A_X 256..383, A_Y 384..511
 // (bf16 activations, K = 256, the A operand of the next layer).  There is no room for a second A buffer per tile, so
@@ -14,17 +13,18 @@
 // tile's second-half MMAs - the last readers of the old activations - have completed, then written over them.
 //
 // Measured facts this schedule is built on (tools/probe_tmem_contention.py, profiles/r01_notes.md): an M128 x N128 x K16
-// tcgen05.mma with A in TMEM retires every 71.6 clk (96 clk with A in shared memory), tcgen05.commit is free, TMEM loads
+// tcgen05.mma with A in TMEM retires every ~72 clk (96 clk with A in shared memory), tcgen05.commit is free, TMEM loads
 // by the epilogue do not slow the MMAs down, but the MMA queue is only ~4 instructions deep: the issuing warp must come
-// back with the next group within ~290 clk or the tensor pipe idles.  The issue loop therefore works on 32-bit shared
-// addresses and precomputed descriptors only (no generic-pointer arithmetic, no local-memory traffic between groups).
+// back with the next group within ~290 clk or the tensor pipe idles, and the TMEM -> register path delivers ~13 B/clk per
+// warp.  Hence: 32-bit shared addresses and precomputed descriptors on the issue path, one issuing warp per tile, and all
+// 16 epilogue warps on every task.
 //
-// Warps (768 threads): 0,3 weight producers | 1 MMA issuer | 2 TMEM allocation | 4-11 epilogue of tile X |
-// 12-19 epilogue of tile Y | 20-23 PE producers (both tiles).  Register budgets are re-balanced with setmaxnreg.
+// Warps (768 threads): 0,3 weight producers | 1 MMA issuer of tile X | 2 TMEM allocation + MMA issuer of tile Y |
+// 4-19 epilogue (both tiles) | 20-23 PE producers (both tiles).  Register budgets are re-balanced with setmaxnreg.
 //
 // Steps per tile (16): mlp.0 h0,h1 | mlp.2/4/6, feature_fn.0/2/4 h0,h1 | rgb_fn.0 | rgb_fn.2 (density_fn.0: CUDA cores, see below).
 // Barriers per tile t: dfull[t] (MMA -> epilogue, accumulator complete), dfree[t] (accumulator read into registers),
-// alo[t] / ahi[t] (K-blocks 0,1 / 2,3 of the next A operand written), pex_full/empty[t], ped_full/empty[t].
+// alo[t] / ahi[t] (K-blocks 0,1 / 2,3 of the next A operand written), pex_full/empty[t], ped_full/empty[t], turn[t].
 #include <stdlib.h>
 #include "mlp_tc_common.cuh"
 
