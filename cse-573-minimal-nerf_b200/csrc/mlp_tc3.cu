@@ -26,61 +26,36 @@
 // Barriers per tile t: dfull[t] (MMA -> epilogue, accumulator complete), dfree[t] (accumulator read into registers),
 // alo[t] / ahi[t] (K-blocks 0,1 / 2,3 of the next A operand written), pex_full/empty[t], ped_full/empty[t], turn[t].
 #include <stdlib.h>
-#include "mlp_tc_common.cuh"
+#include "mlp_tc3_common.cuh"
 
 namespace nerf {
 
-namespace t3 {
-constexpr int kTileM = 128;
-constexpr int kSlots = 4;
-constexpr uint32_t kSlotBytes = 32768;
-constexpr int kThreads = 768;
-constexpr int kEpiWarps = 16;          // every epilogue warp takes part in every task
-constexpr int kPEWarps = 4;
-constexpr uint32_t kColD = 0, kColA = 256;      // + 128 * tile
 
-constexpr uint32_t kOffPE = 0;             // PE(x) tiles of X and Y: 2 x [128 x 64] bf16
-constexpr uint32_t kOffPEDir = 32768;      // PE(dir) tiles of X and Y
-constexpr uint32_t kOffRing = 65536;
-constexpr uint32_t kOffBias = kOffRing + kSlots * kSlotBytes;
-constexpr uint32_t kOffW7 = kOffBias + ((pk::kBiasFloats * 4 + 15) / 16) * 16;     // density_fn.0 weights, fp32 [256]
-constexpr uint32_t kOffSig = kOffW7 + 1024;                                          // sigma partial sums [2 tiles][4][128]
-constexpr uint32_t kOffBars = kOffSig + 4096;
-// barrier indices (8 bytes each)
-constexpr uint32_t kBarFull = 0, kBarEmpty = 4, kBarDFull = 8, kBarDFree = 10, kBarALo = 12, kBarAHi = 14, kBarPexFull = 16,
-                   kBarPexEmpty = 18, kBarPedFull = 20, kBarPedEmpty = 22, kBarTurn = 24, kNumBars = 26;
-constexpr uint32_t kOffTmemHolder = kOffBars + kNumBars * 8;
-constexpr uint32_t kOffDetail = kOffTmemHolder + 16;                                 // PROFILE builds: 96 x int64
-constexpr uint32_t kSmemBytes = kOffDetail + 96 * 8 + 1024;
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-
-// setmaxnreg moves registers inside the CTA's own pool (768 threads x 80 at launch): what the two small warpgroups give
-// back is exactly what the four epilogue warpgroups take
-constexpr int kRegsLaunch = 80, kRegsMisc = 64, kRegsEpi = 96, kRegsPE = 32;
-static_assert(kRegsMisc + 4 * kRegsEpi + kRegsPE <= 6 * kRegsLaunch, "register pool budget");
-}  // namespace t3
-
-// Stages of this kernel: c_merged without density_fn.0.  sigma is a 256-long dot product per sample; the epilogue of
-// feature_fn.4 takes it on the CUDA cores from the bf16 feat values it has in registers (same operands as the N = 16
-// MMA of mlp_tc.cu, fp32 accumulation), which removes one step, its accumulator hand-over and an 8 KB stage per tile.
-constexpr int kMergedStages3 = kMergedStages - 1;
-constexpr MergedTable make_merged_table3() {
-    MergedTable m = make_merged_table(), t = m;
-    t.s[31] = m.s[32];                                  // rgb_fn.2 follows rgb_fn.0 directly
-    t.s[32] = StageRef{0u, 0u};
+// Stages of this kernel: the 63 K = 64 weight blocks of the packed image in consumption order (one ring slot each) without
+// density_fn.0's four, and rgb_fn.2's two 2 KB blocks fetched as one request.  sigma is a 256-long dot product per sample;
+// the epilogue of feature_fn.4 takes it on the CUDA cores from the bf16 feat values it has in registers (same operands as
+// the N = 16 MMA of mlp_tc.cu, fp32 accumulation), which removes one step and its accumulator hand-over per tile.
+constexpr int kStages3 = pk::kStages - 4 - 1;          // 58
+struct StageTable3 { StageRef s[kStages3]; };
+constexpr StageTable3 make_stage_table3() {
+    StageTable3 t{};
+    int m = 0;
+    for (int i = 0; i < pk::kStages; ++i) {
+        if (pk::kLayout.st[i].param == 7) continue;                       // density_fn.0
+        if (pk::kLayout.st[i].param == 9 && pk::kLayout.st[i].k0 != 0) {  // second block of rgb_fn.2: part of the previous request
+            t.s[m - 1].bytes += (uint32_t)pk::kLayout.st[i].rows * 128u;
+            continue;
+        }
+        t.s[m].offset = pk::kLayout.st[i].offset;
+        t.s[m].bytes = (uint32_t)pk::kLayout.st[i].rows * 128u;
+        ++m;
+    }
     return t;
 }
-static __constant__ MergedTable c_merged3 = make_merged_table3();
+static __constant__ StageTable3 c_stages3 = make_stage_table3();
+static_assert(make_stage_table3().s[kStages3 - 1].bytes == 2u * pk::kStageBytesSmall && make_stage_table3().s[kStages3 - 2].bytes == 16384u,
+              "stage table of the two-tile kernel");
 constexpr uint32_t kDensityStageOffset = make_merged_table().s[31].offset;     // 4 blocks of [16 x 64] bf16, row 0 = w7
-
-template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
-template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
-
-__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {     // TMEM side effects of this warp are done
-    umma::tc_fence_before();
-    __syncwarp();
-    if (lane == 0) umma::mbar_arrive_u32(bar);
-}
 
 // 32 accumulator columns (registers) -> + bias, (ReLU), 16 registers of bf16 pairs
 __device__ __forceinline__ void pack32(const uint32_t (&v)[32], const float* __restrict__ bias, bool relu, uint32_t* p) {
@@ -233,184 +208,6 @@ __device__ __forceinline__ void save_act64(__nv_bfloat16* __restrict__ act_out, 
     mask_out[((row >> 7) * pk::kMaskWords + (feature >> 6)) * 128 + (row & 127)] = mbits;
 }
 
-// One MMA-issuing warp PER TILE (warp 1: tile X, warp 2: tile Y).  Each runs the plain one-tile program - open stage,
-// wait for its own tile's dependencies, issue 8 MMAs, release the stage - and the two instruction streams meet in the
-// tensor pipe's queue: while one warp is between groups (barrier waits, bookkeeping; a single warp needs 150-300 clk for
-// that and the queue only covers ~290 clk) the other warp's MMAs keep the pipe busy.  A weight stage is released when
-// BOTH warps have committed it (empty barriers count 2), so every stage is still fetched once per tile pair.
-// Every address is a 32-bit shared-memory / TMEM address held in a register.
-// PROFILE counters: prof[1] wait weights, [2] wait dfree, [3] wait alo/ahi, [4] wait PE, [0] time inside issue blocks.
-template <int T, bool PROFILE>
-struct MmaTile {
-    static constexpr uint32_t kI128 = umma::make_idesc_bf16(128, 128);
-    static constexpr uint32_t kI16 = umma::make_idesc_bf16(128, 16);
-    uint32_t bars, tmem;
-    uint64_t ring_desc;                             // descriptor of ring slot 0; slot s / K block at byte offset o: + (s*32768 + o) >> 4
-    bool leader;
-    uint32_t cnt;                                   // weight stages opened
-    uint32_t n_dfree, n_ahi, n_alo, n_step;
-    long long prof[5];
-
-    __device__ __forceinline__ void init(uint32_t bars_addr, uint32_t ring_addr, uint32_t tmem_base, bool is_leader) {
-        bars = bars_addr; tmem = tmem_base; leader = is_leader;
-        ring_desc = umma::make_desc_k_sw128(ring_addr);
-        cnt = 0; n_dfree = n_ahi = n_alo = n_step = 0;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) prof[i] = 0;
-    }
-    __device__ __forceinline__ uint32_t bar(uint32_t idx) const { return bars + 8u * idx; }
-    __device__ __forceinline__ void wait(uint32_t bar_addr, uint32_t parity, int slot) {
-        if (PROFILE) {
-            const long long t0 = clock64();
-            umma::mbar_wait_u32(bar_addr, parity);
-            prof[slot] += clock64() - t0;
-        } else {
-            umma::mbar_wait_u32(bar_addr, parity);
-        }
-    }
-    __device__ __forceinline__ void fence() { umma::tc_fence_after(); }     // once after a run of waits, before the MMAs
-    // next weight stage present in shared memory; returns its descriptor offset (slot * 32768 >> 4)
-    __device__ __forceinline__ uint32_t open() {
-        const uint32_t slot = cnt & (t3::kSlots - 1);
-        wait(bar(t3::kBarFull + slot), (cnt >> 2) & 1u, 1);
-        ++cnt;
-        return slot * (t3::kSlotBytes >> 4);
-    }
-    __device__ __forceinline__ uint32_t empty_bar(uint32_t back) const { return bar(t3::kBarEmpty + ((cnt - 1u - back) & (t3::kSlots - 1))); }
-    __device__ __forceinline__ void wait_pe(uint32_t idx, uint32_t parity) { wait(bar(idx + T), parity, 4); }
-    __device__ __forceinline__ void begin_step() {      // the tile's accumulator has been read by its epilogue
-        wait(bar(t3::kBarDFree + T), (n_dfree & 1u) ^ 1u, 2);
-        ++n_dfree;
-    }
-    // Ping-pong between the two issuing warps: step n of tile X is queued before step n of tile Y, which is queued before
-    // step n+1 of tile X.  Left alone the two warps fall into lockstep (both tiles in the same phase, both waiting for their
-    // epilogues at the same time); with the turn token one tile's MMAs always cover the other tile's epilogue latency.
-    __device__ __forceinline__ void my_turn() {
-        if (T == 0) wait(bar(t3::kBarTurn + 1), (n_step & 1u) ^ 1u, 2);      // Y has queued step n-1
-        else wait(bar(t3::kBarTurn + 0), n_step & 1u, 2);                     // X has queued step n
-        ++n_step;
-    }
-    __device__ __forceinline__ void pass_turn() { umma::mbar_arrive_u32(bar(t3::kBarTurn + T)); }   // leader lane, after its MMAs
-    // the same epilogue task signals alo BEFORE dfree: after begin_step() the first-half operand is known to be written
-    __device__ __forceinline__ void lo_implied() { ++n_alo; }
-    __device__ __forceinline__ void need_lo() { wait(bar(t3::kBarALo + T), n_alo & 1u, 3); ++n_alo; }
-    __device__ __forceinline__ void need_hi() { wait(bar(t3::kBarAHi + T), n_ahi & 1u, 3); ++n_ahi; }
-    // ---- unguarded pieces (callers hold the leader lane)
-    __device__ __forceinline__ void mma8(uint32_t a_col, uint32_t b_off, uint32_t first_acc) {     // two K=64 blocks of a 32 KB stage
-        const uint32_t d = tmem + t3::kColD + 128u * T;
-        const uint32_t a = tmem + t3::kColA + 128u * T + a_col;
-        const uint64_t bdesc = ring_desc + b_off;
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma::mma_ts(d, a + 32u * kb + 8u * k, bdesc + (uint64_t)(kb * 1024 + 2 * k), kI128, (kb | k) ? 1u : first_acc);
-        }
-    }
-    template <int NK16> __device__ __forceinline__ void mma_pe(uint64_t a_desc, uint32_t b_off) {   // A = shared-memory PE tile
-        const uint32_t d = tmem + t3::kColD + 128u * T;
-        const uint64_t bdesc = ring_desc + b_off;
-#pragma unroll
-        for (int k = 0; k < NK16; ++k) umma::mma_ss(d, a_desc + 2u * k, bdesc + 2u * k, kI128, k ? 1u : 0u);
-    }
-    template <class F> __device__ __forceinline__ void issue(F&& f) {       // one group of MMAs + commits by the leader lane
-        long long t0 = 0;
-        if (PROFILE) t0 = clock64();
-        if (leader) f();
-        __syncwarp();
-        if (PROFILE) prof[0] += clock64() - t0;
-    }
-    // mlp.0 half: one 16 KB stage, A = PE(x)
-    __device__ __forceinline__ void first_layer_half(uint64_t descPE) {
-        const uint32_t b = open();
-        begin_step();
-        my_turn();
-        fence();
-        issue([&] {
-            mma_pe<4>(descPE, b);
-            umma::mma_commit_u32(empty_bar(0));
-            umma::mma_commit_u32(bar(t3::kBarDFull + T));
-            pass_turn();
-        });
-    }
-    // a K = 256 layer half (or rgb_fn.0): [PE stage] kb01 kb23.  A second half has no new A operand to wait for and issues
-    // its 16 MMAs back to back.
-    template <bool FIRST_HALF, int PE_K16>
-    __device__ __forceinline__ void layer_half(uint64_t descA, uint32_t pe_done_idx) {
-        constexpr bool PE = PE_K16 > 0;
-        constexpr int NK = PE ? PE_K16 : 1;
-        uint32_t bP = 0;
-        if (PE) bP = open();
-        const uint32_t b01 = open();
-        const uint32_t b23 = open();
-        const uint32_t e_p = empty_bar(2), e_01 = empty_bar(1), e_23 = empty_bar(0);
-        begin_step();
-        if (FIRST_HALF) lo_implied();
-        my_turn();
-        fence();
-        issue([&] {
-            if (PE) {
-                mma_pe<NK>(descA, bP);
-                if (pe_done_idx) umma::mma_commit_u32(bar(pe_done_idx + T));
-                umma::mma_commit_u32(e_p);
-            }
-            mma8(0, b01, PE ? 1u : 0u);
-            umma::mma_commit_u32(e_01);
-            if (!FIRST_HALF) { mma8(64, b23, 1u); umma::mma_commit_u32(e_23); umma::mma_commit_u32(bar(t3::kBarDFull + T)); pass_turn(); }
-        });
-        if (FIRST_HALF) {               // K blocks 2,3 of the new operand are written ~500 clk after K blocks 0,1
-            need_hi();
-            fence();
-            issue([&] { mma8(64, b23, 1u); umma::mma_commit_u32(e_23); umma::mma_commit_u32(bar(t3::kBarDFull + T)); pass_turn(); });
-        }
-    }
-    // rgb_fn.2: r (A columns 0..63) -> 16 columns, one 4 KB stage
-    __device__ __forceinline__ void last_step() {
-        const uint32_t b = open();
-        begin_step();
-        need_lo();
-        my_turn();
-        fence();
-        issue([&] {
-            const uint32_t d = tmem + t3::kColD + 128u * T;
-            const uint32_t a = tmem + t3::kColA + 128u * T;
-            const uint64_t bdesc = ring_desc + b;
-#pragma unroll
-            for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma::mma_ts(d, a + 32u * kb + 8u * k, bdesc + (uint64_t)(kb * 128 + 2 * k), kI16, (kb | k) ? 1u : 0u);
-            }
-            umma::mma_commit_u32(empty_bar(0));
-            umma::mma_commit_u32(bar(t3::kBarDFull + T));
-            pass_turn();
-        });
-    }
-    // the whole per-CTA program of tile T
-    __device__ __forceinline__ void run(uint32_t sbase, int64_t num_pairs) {
-        const uint64_t descPE = umma::make_desc_k_sw128(sbase + t3::kOffPE + T * 16384);
-        const uint64_t descPD = umma::make_desc_k_sw128(sbase + t3::kOffPEDir + T * 16384);
-        uint32_t it = 0;
-        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
-            wait_pe(t3::kBarPexFull, it & 1u);
-            first_layer_half(descPE);                                  // mlp.0
-            first_layer_half(descPE);
-#pragma unroll 1
-            for (int l = 1; l <= 6; ++l) {                             // mlp.2/4/6, feature_fn.0 (PE(x) K block first), feature_fn.2/4
-                if (l == 4) {
-                    layer_half<true, 4>(descPE, 0);
-                    layer_half<false, 4>(descPE, t3::kBarPexEmpty);    // last reader of PE(x)
-                } else {
-                    layer_half<true, 0>(0, 0);
-                    layer_half<false, 0>(0, 0);
-                }
-            }
-            wait_pe(t3::kBarPedFull, it & 1u);
-            layer_half<true, 2>(descPD, t3::kBarPedEmpty);             // rgb_fn.0: PE(dir) K block + feat
-            last_step();                                               // rgb_fn.2
-        }
-    }
-};
-
 // dbg counters (PROFILE), per CTA x 16: 0 MMA warp total, 1 wait weights, 2 wait dfree, 3 wait alo/ahi, 4 wait PE,
 // 5 producer wait empty, 6 epilogue X total, 7 epilogue X wait dfull, 8 pairs; dbg[148*16 ...] = CTA 0's wait detail
 template <bool PROFILE>
@@ -474,14 +271,14 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             long long t_wait = 0;
             uint32_t cnt = 0;
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-                for (int s = 0; s < kMergedStages3; ++s, ++cnt) {
+                for (int s = 0; s < kStages3; ++s, ++cnt) {
                     if ((cnt & 1u) != me) continue;
-                    const uint32_t slot = cnt & (t3::kSlots - 1), ph = (cnt >> 2) & 1u;
+                    const uint32_t slot = cnt & (t3::kSlots - 1), ph = (cnt >> 3) & 1u;
                     const long long t0 = PROFILE ? clock64() : 0;
                     umma::mbar_wait_u32(bars + 8u * (t3::kBarEmpty + slot), ph ^ 1u);
                     if (PROFILE) t_wait += clock64() - t0;
                     if (leader) {
-                        const StageRef st = c_merged3.s[s];
+                        const StageRef st = c_stages3.s[s];
                         umma::mbar_arrive_expect_tx_u32(bars + 8u * (t3::kBarFull + slot), st.bytes);
                         umma::bulk_g2s_u32(ring + slot * t3::kSlotBytes, packed + st.offset, st.bytes, bars + 8u * (t3::kBarFull + slot));
                     }
@@ -496,7 +293,10 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             if (warp == 1) {
                 MmaTile<0, PROFILE> m;
                 m.init(bars, sbase + t3::kOffRing, tmem, elected);
+                if (PROFILE) m.detail = sbase + t3::kOffDetail;
                 m.run(sbase, num_pairs);
+                __syncwarp();
+                if (PROFILE && blockIdx.x == 0) for (int i = lane; i < 64; i += 32) dbg[148 * 16 + i] = ((long long*)(smem + t3::kOffDetail))[i];
                 if (PROFILE && elected) {
                     dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
                     for (int i = 1; i < 5; ++i) dbg[blockIdx.x * 16 + i] = m.prof[i];

@@ -10,6 +10,7 @@
 //   plus a 16-wide heads block [dsigma_pre, drgb_pre, 0..] at features 1920..1935.
 // ReLU masks are the 64-bit sign words the forward kernel wrote per (row, 64-feature block): 8 B instead of 128 B per step.
 // mlp.0's dgrad (d PE) is not needed: the inputs carry no gradient.
+#include <stdlib.h>
 #include "mlp_tc_common.cuh"
 
 namespace nerf {
@@ -275,6 +276,10 @@ mlp_tc_bwd_kernel(const uint8_t* __restrict__ packed_t, const unsigned long long
 
 }  // namespace nerf
 
+namespace nerf {
+int launch_mlp_tc_bwd3(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre, int64_t total,
+                       void* dz_out, void* stream);
+}
 using namespace nerf;
 
 extern "C" int nerf_mlp_backward_tc(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre,
@@ -284,6 +289,9 @@ extern "C" int nerf_mlp_backward_tc(const void* packed_t, const void* masks, con
     NERF_REQUIRE(packed_t && masks && dsigma_pre && drgb_pre && dz_out, "nerf_mlp_backward_tc: null pointer");
     NERF_REQUIRE(((uintptr_t)packed_t & 127) == 0 && ((uintptr_t)masks & 7) == 0 && ((uintptr_t)dz_out & 15) == 0,
                  "nerf_mlp_backward_tc: misaligned buffer");
+    // NERF_TC_ONE_TILE=1 selects the one-tile-per-CTA schedule of this file; the default is the two-tile schedule (mlp_tc_bwd3.cu)
+    static const bool one_tile = [] { const char* e = getenv("NERF_TC_ONE_TILE"); return e && e[0] == '1'; }();
+    if (!one_tile) return launch_mlp_tc_bwd3(packed_t, masks, dsigma_pre, drgb_pre, N * S, dz_out, stream);
     static thread_local bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::kSmemBytes);

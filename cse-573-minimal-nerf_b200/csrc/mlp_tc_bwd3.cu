@@ -1,0 +1,263 @@
+// mlp_tc_bwd3.cu - dgrad chain of one NeRFModel (autograd of nerf_model.py:362-389), two 128-sample tiles per CTA: the
+// schedule of mlp_tc3.cu (shared W^T stages, one MMA-issuing warp per tile with a turn token, in-place TMEM operands, all
+// 16 epilogue warps on every task) applied to the arithmetic of mlp_tc_bwd.cu:
+//   per tile, given the gradients w.r.t. the head pre-activations (from composite_backward_kernel)
+//     dr   = (drgb_pre . W9) * [r > 0]                         CUDA cores, producer warps 20-23 -> smem A tile (K = 128)
+//     dz6  = dr . W8[:, :256] + dsigma_pre (x) w7              steps 0,1   (A = dr tile in shared memory, SS)
+//     dz5  = (dz6 . W6) * [h5 > 0]                             steps 2,3   (A = previous dz in TMEM, TS; B = W^T stages)
+//     dz4 .. dz0 likewise through feature_fn.2, feature_fn.0 (h columns), mlp.6, mlp.4, mlp.2     steps 4..13
+//   every dz is written to global (bf16, tiled chunk-major, pack_layout.cuh) for wgrad, plus the 16-wide heads block.
+// ReLU masks are the sign words the forward kernel wrote per (row, 64-feature block), read here as 32-bit halves.
+// mlp.0's dgrad (d PE) is not needed: the inputs carry no gradient.
+#include "mlp_tc3_common.cuh"
+
+namespace nerf {
+
+namespace b3 {
+constexpr uint32_t kOffDr = 0;                                    // dr tiles of X and Y: 2 x 2 K-blocks x [128 x 64] bf16
+constexpr uint32_t kOffRing = t3::kOffRing;                       // 65536
+constexpr uint32_t kOffConst = kOffRing + t3::kSlots * t3::kSlotBytes;      // fp32 W9 [3][128], w7 [256]
+constexpr uint32_t kOffBars = kOffConst + pk::kConstFloatsT * 4;
+constexpr uint32_t kOffTmemHolder = kOffBars + t3::kNumBars * 8;
+constexpr uint32_t kSmemBytes = kOffTmemHolder + 16 + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr int kStagesT = pk::kStagesT;                            // 52 requests of 16 KB per tile pair
+}  // namespace b3
+
+__global__ void __launch_bounds__(t3::kThreads, 1)
+mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restrict__ masks32, const float* __restrict__ dsigma_pre,
+                   const float* __restrict__ drgb_pre, int64_t total, __nv_bfloat16* __restrict__ dz_out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = umma::smem_u32(smem);
+    const uint32_t bars = sbase + b3::kOffBars;
+    float* sConst = (float*)(smem + b3::kOffConst);        // [0,384) W9[c][k], [384,640) w7[k]
+    uint32_t* tmem_holder = (uint32_t*)(smem + b3::kOffTmemHolder);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t num_tiles = (total + t3::kTileM - 1) / t3::kTileM;
+    const int64_t num_pairs = (num_tiles + 1) / 2;
+
+    if (tid == 0) {
+        uint64_t* b = (uint64_t*)(smem + b3::kOffBars);
+        for (int i = 0; i < t3::kSlots; ++i) { umma::mbar_init(&b[t3::kBarFull + i], 1); umma::mbar_init(&b[t3::kBarEmpty + i], 2); }
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&b[t3::kBarDFull + i], 1);
+            umma::mbar_init(&b[t3::kBarDFree + i], t3::kEpiWarps);
+            umma::mbar_init(&b[t3::kBarALo + i], t3::kEpiWarps);
+            umma::mbar_init(&b[t3::kBarAHi + i], t3::kEpiWarps);
+            umma::mbar_init(&b[t3::kBarPexFull + i], t3::kPEWarps);     // dr tile written
+            umma::mbar_init(&b[t3::kBarPexEmpty + i], 1);               // dr tile no longer read
+            umma::mbar_init(&b[t3::kBarTurn + i], 1);
+        }
+        umma::fence_mbar_init();
+    }
+    if (warp == 2) umma::tmem_alloc(tmem_holder, 512);
+    {
+        const float* gc = (const float*)(packed_t + pk::kLayoutT.const_offset);
+        for (int i = tid; i < pk::kConstFloatsT; i += t3::kThreads) sConst[i] = gc[i];
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+
+    if (warp < 4) {
+        reg_dec<t3::kRegsMisc>();
+        if (warp == 0 || warp == 3) {
+            // -------------------------------------------------------------- W^T stage producers (alternate 32 KB requests)
+            const bool leader = umma::elect_one();
+            const uint32_t me = (warp == 0) ? 0u : 1u;
+            const uint32_t ring = sbase + b3::kOffRing;
+            uint32_t cnt = 0;
+            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+                for (int s = 0; s < b3::kStagesT; ++s, ++cnt) {
+                    if ((cnt & 1u) != me) continue;
+                    const uint32_t slot = cnt & (t3::kSlots - 1), ph = (cnt >> 3) & 1u;
+                    umma::mbar_wait_u32(bars + 8u * (t3::kBarEmpty + slot), ph ^ 1u);
+                    if (leader) {
+                        umma::mbar_arrive_expect_tx_u32(bars + 8u * (t3::kBarFull + slot), t3::kSlotBytes);
+                        umma::bulk_g2s_u32(ring + slot * t3::kSlotBytes, packed_t + (size_t)s * t3::kSlotBytes, t3::kSlotBytes,
+                                           bars + 8u * (t3::kBarFull + slot));
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            // -------------------------------------------------------------- MMA issuers: warp 1 tile X, warp 2 tile Y
+            const bool elected = umma::elect_one();
+            if (warp == 1) {
+                MmaTile<0, false> m;
+                m.init(bars, sbase + b3::kOffRing, tmem, elected);
+                m.run_bwd(sbase + b3::kOffDr, num_pairs);
+            } else {
+                MmaTile<1, false> m;
+                m.init(bars, sbase + b3::kOffRing, tmem, elected);
+                m.run_bwd(sbase + b3::kOffDr, num_pairs);
+            }
+        }
+    } else if (warp >= 20) {
+        // ------------------------------------------------------------------ dr producers: thread = row, 16-byte chunks of 8 features
+        reg_dec<t3::kRegsPE>();
+        const int r = (warp - 20) * 32 + lane;
+        const float* W9 = sConst;
+        uint32_t it = 0;
+        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const int64_t tile = pair * 2 + t;
+                const int64_t row = tile * t3::kTileM + r;
+                const bool valid = row < total;
+                const bool store = tile < num_tiles;              // dz_out holds whole tiles only
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+                if (valid) { g0 = drgb_pre[row * 3]; g1 = drgb_pre[row * 3 + 1]; g2 = drgb_pre[row * 3 + 2]; }
+                umma::mbar_wait_u32(bars + 8u * (t3::kBarPexEmpty + t), (it & 1u) ^ 1u);
+                uint8_t* tile_smem = smem + b3::kOffDr + t * 32768;
+#pragma unroll 1
+                for (int c = 0; c < 16; ++c) {                    // chunk c = features 8c .. 8c+7 of r (rgb_fn.0's ReLU output)
+                    // sign bits written by the forward kernel: 32-bit half (c >> 2) & 1 of block 28 + (c >> 3)
+                    uint32_t mb = 0u;
+                    if (store) mb = masks32[(((row >> 7) * pk::kMaskWords + 28 + (c >> 3)) * 128 + (row & 127)) * 2 + ((c >> 2) & 1)];
+                    mb >>= (c & 3) * 8;
+                    uint32_t v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = c * 8 + 2 * j;
+                        float a = g0 * W9[k] + g1 * W9[128 + k] + g2 * W9[256 + k];            // nerf_model.py:358 backward
+                        float b = g0 * W9[k + 1] + g1 * W9[128 + k + 1] + g2 * W9[256 + k + 1];
+                        if (!((mb >> (2 * j)) & 1u)) a = 0.f;
+                        if (!((mb >> (2 * j + 1)) & 1u)) b = 0.f;
+                        v[j] = umma::pack_bf16(a, b);
+                    }
+                    const uint4 q4 = make_uint4(v[0], v[1], v[2], v[3]);
+                    const int kb = c >> 3, cc = c & 7;            // K block, chunk inside its 128-byte row
+                    *(uint4*)(tile_smem + kb * 16384 + r * 128 + ((cc ^ (r & 7)) << 4)) = q4;
+                    if (store) *(uint4*)(dz_out + pk::tiled_offset(row, 1792 + c * 8, pk::kDzChunks)) = q4;
+                }
+                if (store) {   // heads block (features 1920..1935): [dsigma_pre, drgb_pre x3, 0 ...] in bf16 for the head weight gradients
+                    const float dsg = valid ? dsigma_pre[row] : 0.f;
+                    uint4* dst = (uint4*)(dz_out + pk::tiled_offset(row, 1920, pk::kDzChunks));
+                    dst[0] = make_uint4(umma::pack_bf16(dsg, g0), umma::pack_bf16(g1, g2), 0u, 0u);
+                    dst[128] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                umma::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive_u32(bars + 8u * (t3::kBarPexFull + t));
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: all 16 warps on every task
+        reg_inc<t3::kRegsEpi>();
+        const int q = warp & 3;                          // TMEM lane quarter this warp may touch
+        const int cq = (warp - 4) >> 2;                  // column quarter (32 accumulator columns, 32 features)
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const float* w7 = sConst + 384;
+        uint32_t nd[2] = {0, 0};
+        auto wait_d = [&](int t) {
+            umma::mbar_wait_u32(bars + 8u * (t3::kBarDFull + t), nd[t] & 1u);
+            umma::tc_fence_after();
+            ++nd[t];
+        };
+        // 32 accumulator columns -> (+ dsigma (x) w7 | ReLU mask) -> 16 registers of bf16 pairs
+        auto finish = [&](const uint32_t (&v)[32], bool first, float dsg, uint32_t mb, int col0, uint32_t* p) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+                if (first) {                                // + dsigma_pre (x) w7  (density head, nerf_model.py:351)
+                    a = fmaf(dsg, w7[col0 + 2 * i], a);
+                    b = fmaf(dsg, w7[col0 + 2 * i + 1], b);
+                } else {
+                    if (!((mb >> (2 * i)) & 1u)) a = 0.f;
+                    if (!((mb >> (2 * i + 1)) & 1u)) b = 0.f;
+                }
+                p[i] = umma::pack_bf16(a, b);
+            }
+        };
+        auto store_dz = [&](int64_t row, int feature, const uint32_t* p) {
+            uint4* dst = (uint4*)(dz_out + pk::tiled_offset(row, feature, pk::kDzChunks));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i * 128] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+        };
+
+        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            const int64_t row0 = pair * 2 * t3::kTileM + r;
+            const bool st0 = true, st1 = (pair * 2 + 1 < num_tiles);
+            float dsg[2];
+            dsg[0] = (row0 < total) ? dsigma_pre[row0] : 0.f;
+            dsg[1] = (row0 + 128 < total) ? dsigma_pre[row0 + 128] : 0.f;
+#pragma unroll 1
+            for (int L = 0; L < 7; ++L) {
+                const int j = 6 - L;                        // output: dz_j (gradient w.r.t. the pre-activation of layer j)
+                const bool first = (L == 0);
+                uint32_t hold[2][16];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {               // ---- first halves (features cq*32 ..): X then Y
+                    const int64_t row = row0 + t * 128;
+                    const bool st = t == 0 ? st0 : st1;
+                    const int col0 = cq * 32;
+                    // ReLU mask source: saved output of layer j (post-ReLU), except dz6 (feature_fn.4 is linear)
+                    uint32_t mb = 0u;
+                    if (!first && st) mb = masks32[(((row >> 7) * pk::kMaskWords + ((j * 256 + col0) >> 6)) * 128 + (row & 127)) * 2 + (cq & 1)];
+                    const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
+                    wait_d(t);
+                    uint32_t v[32];
+                    umma::tmem_ld32(d_addr, v);
+                    umma::tmem_wait_ld();
+                    warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
+                    finish(v, first, dsg[t], mb, col0, hold[t]);
+                    if (st) store_dz(row, j * 256 + col0, hold[t]);
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {               // ---- second halves (features 128 + cq*32 ..)
+                    const int64_t row = row0 + t * 128;
+                    const bool st = t == 0 ? st0 : st1;
+                    const int col0 = 128 + cq * 32;
+                    uint32_t mb = 0u;
+                    if (!first && st) mb = masks32[(((row >> 7) * pk::kMaskWords + ((j * 256 + col0) >> 6)) * 128 + (row & 127)) * 2 + (cq & 1)];
+                    const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
+                    const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(cq * 16);
+                    wait_d(t);
+                    uint32_t v[32];
+                    umma::tmem_ld32(d_addr, v);
+                    if (j > 0) {                            // dz_j is the A operand of the next dgrad GEMM: held half in place first
+                        umma::tmem_st16(a_addr, hold[t]);
+                        umma::tmem_wait_st();
+                        warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
+                    }
+                    umma::tmem_wait_ld();
+                    warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
+                    uint32_t p[16];
+                    finish(v, first, dsg[t], mb, col0, p);
+                    if (j > 0) {
+                        umma::tmem_st16(a_addr + 64, p);
+                        umma::tmem_wait_st();
+                        warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
+                    }
+                    if (st) store_dz(row, j * 256 + col0, p);     // rows past `total` carry zeros (their dsigma / drgb are zero)
+                }
+            }
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) umma::tmem_dealloc(tmem, 512);
+}
+
+int launch_mlp_tc_bwd3(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre, int64_t total,
+                       void* dz_out, void* stream) {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b3::kSmemBytes);
+        if (e != cudaSuccess) { set_error("nerf_mlp_backward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
+        attr_set = true;
+    }
+    const int64_t tiles = (total + t3::kTileM - 1) / t3::kTileM;
+    const int64_t pairs = (tiles + 1) / 2;
+    const int grid = (int)(pairs < num_sms() ? pairs : num_sms());
+    mlp_tc_bwd3_kernel<<<grid, t3::kThreads, b3::kSmemBytes, (cudaStream_t)stream>>>(
+        (const uint8_t*)packed_t, (const uint32_t*)masks, dsigma_pre, drgb_pre, total, (__nv_bfloat16*)dz_out);
+    return check_launch("nerf_mlp_backward_tc");
+}
+
+}  // namespace nerf

@@ -64,7 +64,7 @@ if not one_tile:
     pairs0 = float(dbg[8].item())
     d = detail / max(pairs0, 1)
     print("CTA 0, clk per pair: weight-stage waits by stage index:")
-    print("  " + " ".join(f"{v:5.0f}" for v in d[:32].tolist()))
+    print("  " + " ".join(f"{v:4.0f}" for v in d[:58].tolist()))
     print("dfree waits by step, tile X / tile Y:")
     print("  X " + " ".join(f"{v:5.0f}" for v in d[32:48].tolist()))
     print("  Y " + " ".join(f"{v:5.0f}" for v in d[48:64].tolist()))
