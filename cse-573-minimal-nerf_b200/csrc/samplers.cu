@@ -97,20 +97,33 @@ composite_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb,
     for (int64_t n = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); n < N; n += warps) {
         const float* sg = sigma + n * S;
         const float* tp = ts_or_deltas + n * S;
+        const float* cp = rgb + n * S * 3;
         float running = 0.f;       // sum_{j<i} -sigma_j delta_j, nerf_helpers.py:86-89
         float cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f;
+        // software pipeline: the next chunk's sigma / t / rgb are in flight while this chunk's serial running sum is taken
+        float s_n = 0.f, t_n = 0.f, c0_n = 0.f, c1_n = 0.f, c2_n = 0.f;
+        auto fetch = [&](int base) {
+            const int i = base + lane;
+            const bool in = i < S;
+            s_n = in ? __ldg(sg + i) : 0.f;
+            t_n = in ? __ldg(tp + i) : 0.f;
+            if (KIND == 1 && in) { c0_n = __ldg(cp + i * 3); c1_n = __ldg(cp + i * 3 + 1); c2_n = __ldg(cp + i * 3 + 2); }
+        };
+        fetch(0);
         for (int base = 0; base < S; base += kWarp) {
             const int i = base + lane;
             const bool in = i < S;
-            const float s = in ? sg[i] : 0.f;
+            const float s = s_n, tv = t_n, c0 = c0_n, c1 = c1_n, c2 = c2_n;
+            if (base + kWarp < S) fetch(base + kWarp);
             float t = 0.f, dl = 0.f;
             if (KIND == 1) {
-                t = in ? tp[i] : 0.f;
+                t = tv;
                 float tn = __shfl_down_sync(kFull, t, 1);
-                if (lane == 31 && i + 1 < S) tn = tp[i + 1];
+                const float t_first_next = __shfl_sync(kFull, t_n, 0);      // first depth of the next chunk (already fetched)
+                if (lane == 31 && i + 1 < S) tn = t_first_next;
                 dl = (i == S - 1) ? 1e10f : __fsub_rn(tn, t);             // nerf_helpers.py:71-72
             } else {
-                dl = in ? tp[i] : 0.f;
+                dl = tv;
             }
             const float x = in ? __fmul_rn(__fmul_rn(-1.0f, s), dl) : 0.f;   // -1 * density * deltas
             const float excl = chunk_exclusive_scan(x, running, lane);
@@ -120,8 +133,7 @@ composite_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb,
                 if (weights_out) weights_out[n * S + i] = w;
                 if (KIND == 1) {
                     if (deltas_out) deltas_out[n * S + i] = dl;
-                    const float* c = rgb + (n * S + i) * 3;
-                    cr = fmaf(w, c[0], cr); cg = fmaf(w, c[1], cg); cb = fmaf(w, c[2], cb);
+                    cr = fmaf(w, c0, cr); cg = fmaf(w, c1, cg); cb = fmaf(w, c2, cb);
                     dsum = fmaf(w, t, dsum); asum += w;
                     st_sq = fmaf(s, s, st_sq); st_nz += (s != 0.f) ? 1.f : 0.f;
                 }
@@ -147,6 +159,108 @@ composite_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb,
             for (int k = 0; k < kWarpsPerBlock; ++k) { a += red[0][k]; b += red[1][k]; }
             atomicAdd(stats2 + 0, a);
             atomicAdd(stats2 + 1, b);
+            // the last block to arrive publishes the norm the reference logs (nerf_model.py:105,124): stats[2] = sqrt(stats[0])
+            __threadfence();
+            const unsigned ticket = atomicAdd((unsigned*)(stats2 + 3), 1u);
+            if (ticket == gridDim.x - 1) {
+                __threadfence();
+                stats2[2] = sqrtf(atomicAdd(stats2 + 0, 0.f));
+            }
+        }
+    }
+}
+
+// Thread-per-ray form of the full composite (KIND 1 above), used by nerf_composite.  The running sum is sequential in the
+// sample index (the reference's CPU cumsum order), which a warp-per-ray kernel can only emulate with a 32-step shuffle chain
+// per 32 samples: ~8 warp instructions per sample, issue-bound at a third of the HBM roofline.  Here a block stages a
+// [64 rays x 32 samples] tile of sigma / t / rgb through shared memory with coalesced 128-byte rows, then every thread walks
+// ITS ray's 32 samples in order: the same arithmetic in the same order, ~1.5 warp instructions per sample.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+constexpr int kCompRays = 64;          // rays (= threads) per block
+constexpr int kCompPad = 33;           // row stride of the staged tiles (bank-conflict free column walks)
+__global__ void __launch_bounds__(kCompRays)
+composite_rays_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ ts, int64_t N, int S,
+                      float* __restrict__ deltas_out, float* __restrict__ weights_out, float* __restrict__ ray_rgb,
+                      float* __restrict__ depth, float* __restrict__ acc, float* __restrict__ stats2) {
+    __shared__ float sS[kCompRays * kCompPad], sT[kCompRays * (kCompPad + 1)], sC[kCompRays * 3 * 32 + kCompRays];      // weights overwrite sS in place
+    const int tid = threadIdx.x;
+    float st_sq = 0.f, st_nz = 0.f;
+    for (int64_t n0 = (int64_t)blockIdx.x * kCompRays; n0 < N; n0 += (int64_t)gridDim.x * kCompRays) {
+        const int rays = (int)((N - n0 < kCompRays) ? (N - n0) : kCompRays);
+        const int64_t n = n0 + tid;
+        float running = 0.f;       // sum_{j<i} -sigma_j delta_j, nerf_helpers.py:86-89
+        float cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f;
+        for (int base = 0; base < S; base += 32) {
+            const int len = (S - base < 32) ? (S - base) : 32;
+            // ---- stage the tile with cp.async (the whole 42 KB tile is in flight at once): consecutive threads read
+            // consecutive samples of one ray (128-byte rows)
+            for (int rr = tid >> 5; rr < rays; rr += kCompRays / 32) {      // one ray per warp iteration, no index divisions
+                const int lane = tid & 31;
+                const int64_t off = (n0 + rr) * S + base;
+                if (lane < len) cp_async4(sS + rr * kCompPad + lane, sigma + off + lane);
+                if (lane < len) cp_async4(sT + rr * (kCompPad + 1) + lane, ts + off + lane);
+                if (lane == 0 && base + 32 < S) cp_async4(sT + rr * (kCompPad + 1) + 32, ts + off + 32);   // delta of the chunk's last sample
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = lane + 32 * k;
+                    if (i < len * 3) cp_async4(sC + rr * 97 + i, rgb + off * 3 + i);
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            if (tid < rays) {
+                float* ps = sS + tid * kCompPad;
+                const float* pt = sT + tid * (kCompPad + 1);
+                const float* pc = sC + tid * 97;
+                float* pw = ps;
+                for (int i = 0; i < len; ++i) {
+                    const float s = ps[i], t = pt[i];
+                    const float dl = (base + i == S - 1) ? 1e10f : __fsub_rn(pt[i + 1], t);      // nerf_helpers.py:71-72
+                    const float x = __fmul_rn(__fmul_rn(-1.0f, s), dl);                            // -1 * density * deltas
+                    const float trans = expf(running);                                             // nerf_helpers.py:89
+                    const float w = __fmul_rn(__fsub_rn(1.0f, expf(x)), trans);                    // nerf_helpers.py:90
+                    running = __fadd_rn(running, x);
+                    pw[i] = w;
+                    if (deltas_out) deltas_out[n * S + base + i] = dl;
+                    cr = fmaf(w, pc[3 * i], cr); cg = fmaf(w, pc[3 * i + 1], cg); cb = fmaf(w, pc[3 * i + 2], cb);
+                    dsum = fmaf(w, t, dsum); asum += w;
+                    st_sq = fmaf(s, s, st_sq); st_nz += (s != 0.f) ? 1.f : 0.f;
+                }
+            }
+            __syncthreads();
+            if (weights_out) {
+                for (int e = tid; e < rays * 32; e += kCompRays) {
+                    const int rr = e >> 5, i = e & 31;
+                    if (i < len) weights_out[(n0 + rr) * S + base + i] = sS[rr * kCompPad + i];
+                }
+            }
+            __syncthreads();           // the next chunk's staging overwrites the tiles
+        }
+        if (tid < rays) {
+            if (ray_rgb) { ray_rgb[n * 3 + 0] = cr; ray_rgb[n * 3 + 1] = cg; ray_rgb[n * 3 + 2] = cb; }
+            if (depth) depth[n] = dsum;
+            if (acc) acc[n] = asum;
+        }
+    }
+    if (stats2) {
+        st_sq = warp_sum(st_sq); st_nz = warp_sum(st_nz);
+        __shared__ float red[2][kCompRays / 32];
+        if ((tid & 31) == 0) { red[0][tid >> 5] = st_sq; red[1][tid >> 5] = st_nz; }
+        __syncthreads();
+        if (tid == 0) {
+            float a = 0.f, b = 0.f;
+            for (int k = 0; k < kCompRays / 32; ++k) { a += red[0][k]; b += red[1][k]; }
+            atomicAdd(stats2 + 0, a);
+            atomicAdd(stats2 + 1, b);
+            // the last block to arrive publishes the norm the reference logs (nerf_model.py:105,124): stats[2] = sqrt(stats[0])
+            __threadfence();
+            const unsigned ticket = atomicAdd((unsigned*)(stats2 + 3), 1u);
+            if (ticket == gridDim.x - 1) {
+                __threadfence();
+                stats2[2] = sqrtf(atomicAdd(stats2 + 0, 0.f));
+            }
         }
     }
 }
@@ -479,8 +593,14 @@ extern "C" int nerf_composite(const float* sigma, const float* rgb, const float*
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_composite: bad size");
     if (N == 0) return 0;
     NERF_REQUIRE(sigma && rgb && ts, "nerf_composite: null pointer");
-    composite_kernel<1><<<grid_for(N, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(
-        sigma, rgb, ts, N, S, deltas, weights, ray_rgb, depth, acc, stats2);
+    // one thread per ray needs tens of thousands of rays to fill the GPU (a ray is a serial chain of S steps); a 4096-ray
+    // render / training chunk is served better by one warp per ray
+    if (N >= 32768)
+        composite_rays_kernel<<<grid_for(N, kCompRays), kCompRays, 0, (cudaStream_t)stream>>>(
+            sigma, rgb, ts, N, S, deltas, weights, ray_rgb, depth, acc, stats2);
+    else
+        composite_kernel<1><<<grid_for(N, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(
+            sigma, rgb, ts, N, S, deltas, weights, ray_rgb, depth, acc, stats2);
     return check_launch("nerf_composite");
 }
 

@@ -91,7 +91,8 @@ def estimate_ray_color(weights, rgb):
 
 def composite(density, rgb, ts, want_weights=True):
     """deltas + weights + ray colour + depth + opacity in one launch (what NeRFNetwork.forward needs).
-    Returns dict(weights [N,S,1], rgb [N,3], depth [N], acc [N], stats [2] = (sum sigma^2, count sigma != 0))."""
+    Returns dict(weights [N,S,1], rgb [N,3], depth [N], acc [N], stats [2] = (sum sigma^2, count sigma != 0),
+    norm = sqrt(sum sigma^2), a 0-d view written by the same launch)."""
     sg, c, t = nat.dev(density, "density"), nat.dev(rgb, "rgb"), nat.dev(ts, "ts")
     N, S = sg.shape[0], sg.shape[1]
     dv = sg.device
@@ -99,10 +100,10 @@ def composite(density, rgb, ts, want_weights=True):
     col = torch.empty((N, 3), device=dv, dtype=torch.float32)
     depth = torch.empty((N,), device=dv, dtype=torch.float32)
     acc = torch.empty((N,), device=dv, dtype=torch.float32)
-    stats = torch.zeros((2,), device=dv, dtype=torch.float32)
+    stats = torch.zeros((4,), device=dv, dtype=torch.float32)
     nat.check(nat.lib().nerf_composite(nat.ptr(sg), nat.ptr(c), nat.ptr(t), N, S, None, nat.ptr(w), nat.ptr(col),
                                        nat.ptr(depth), nat.ptr(acc), nat.ptr(stats), nat.stream()), "nerf_composite")
-    return {"weights": w, "rgb": col, "depth": depth, "acc": acc, "stats": stats}
+    return {"weights": w, "rgb": col, "depth": depth, "acc": acc, "stats": stats[:2], "norm": stats[2]}
 
 
 def inverse_transform_sampling(o_rays, d_rays, weights, ts, num_samples, near=2.0, far=6.0, rand=None,

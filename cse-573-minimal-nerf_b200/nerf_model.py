@@ -169,9 +169,9 @@ class NeRFNetwork(LightningModule):
     def _publish(self, aux):
         """The four density statistics the reference logs inside forward (nerf_model.py:105-106,124-125) + extras."""
         c, f = aux["c"], aux["f"]
-        self.log('coarse_density_norms', torch.sqrt(c["stats"][0]), batch_size=1)
+        self.log('coarse_density_norms', c["norm"], batch_size=1)
         self.log('coarse_density_non_zeros', c["stats"][1], batch_size=1)
-        self.log('fine_density_norms', torch.sqrt(f["stats"][0]), batch_size=1)
+        self.log('fine_density_norms', f["norm"], batch_size=1)
         self.log('fine_density_non_zeros', f["stats"][1], batch_size=1)
         self.last = {"depth": f["depth"], "acc": f["acc"], "ts": aux["ts"], "coarse_ts": aux["c_ts"],
                      "coarse_weights": c["weights"], "coarse_sigma": aux["c_sigma"], "fine_sigma": aux["f_sigma"],

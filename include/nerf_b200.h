@@ -59,8 +59,9 @@ int nerf_ray_color(const float* weights, const float* rgb, int64_t N, int S, flo
 
 /* ---- H2+H3+H4 in one pass (what NeRFNetwork.forward does at nerf_model.py:109-111 and :128-130).
  * sigma [N,S], rgb [N,S,3], ts [N,S].  Every output may be NULL: deltas [N,S], weights [N,S],
- * ray_rgb [N,3], depth [N] (sum w*t), acc [N] (sum w).  stats2 (nullable, [2], ACCUMULATED with atomics):
- * sum sigma^2 and count(sigma != 0) - the two density statistics logged at nerf_model.py:105-106. */
+ * ray_rgb [N,3], depth [N] (sum w*t), acc [N] (sum w).  stats2 (nullable, [4], zero-initialised by the caller, ACCUMULATED with atomics):
+ * [0] sum sigma^2, [1] count(sigma != 0) - the two density statistics logged at nerf_model.py:105-106 -, [2] sqrt([0]) written
+ * by the last block of the launch, [3] internal block counter. */
 int nerf_composite(const float* sigma, const float* rgb, const float* ts, int64_t N, int S,
                    float* deltas, float* weights, float* ray_rgb, float* depth, float* acc,
                    float* stats2, void* stream);

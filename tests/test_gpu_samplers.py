@@ -178,3 +178,25 @@ def test_mlp_fp32(golden, mods):
     small = m.NeRFModel(position_dim=6, direction_dim=2, precision="fp32").to(DEV)
     sg, rgb = small(torch.rand(4, 4, 3, device=DEV), torch.rand(4, 3, device=DEV))
     assert sg.shape == (4, 4, 1) and rgb.shape == (4, 4, 3) and (sg >= 0).all() and ((rgb > 0) & (rgb < 1)).all()
+
+
+def test_compositing_large_batch_kernel(mods):
+    """nerf_composite switches to the thread-per-ray kernel (tiles staged through shared memory) from 32768 rays on: the
+    running sum and the weights are taken in the same order as in the warp-per-ray kernel, so a 40000-ray batch must match
+    its two halves bit for bit in the weights; the per-ray sums (colour, depth, opacity) are added in sample order instead
+    of lane-partials + tree and agree to a few ulp; the density statistics to rounding."""
+    _, h, _ = mods
+    N = 40000
+    for S in (64, 192, 37):
+        gen = torch.Generator(device=DEV).manual_seed(100 + S)
+        ts = torch.sort(2 + 4 * torch.rand(N, S, 1, device=DEV, generator=gen), dim=1).values.contiguous()
+        sg = torch.relu(torch.randn(N, S, 1, device=DEV, generator=gen) * 3 - 2)
+        sg[::7] = 0
+        rgb = torch.rand(N, S, 3, device=DEV, generator=gen)
+        full = h.composite(sg, rgb, ts)
+        halves = [h.composite(sg[a:b].contiguous(), rgb[a:b].contiguous(), ts[a:b].contiguous()) for a, b in ((0, N // 2), (N // 2, N))]
+        assert torch.equal(full["weights"], torch.cat([x["weights"] for x in halves])), S
+        for key in ("rgb", "depth", "acc"):
+            torch.testing.assert_close(full[key], torch.cat([x[key] for x in halves]), atol=2e-6, rtol=2e-6)
+        torch.testing.assert_close(full["stats"], halves[0]["stats"] + halves[1]["stats"], rtol=1e-5, atol=0)
+        torch.testing.assert_close(full["norm"], torch.sqrt(full["stats"][0]), rtol=1e-6, atol=0)
