@@ -26,6 +26,7 @@
 // Barriers per tile t: dfull[t] (MMA -> epilogue, accumulator complete), dfree[t] (accumulator read into registers),
 // alo[t] / ahi[t] (K-blocks 0,1 / 2,3 of the next A operand written), pex_full/empty[t], ped_full/empty[t], turn[t].
 #include <stdlib.h>
+#include <type_traits>
 #include "mlp_tc3_common.cuh"
 
 namespace nerf {
@@ -58,67 +59,19 @@ static_assert(make_stage_table3().s[kStages3 - 1].bytes == 2u * pk::kStageBytesS
 constexpr uint32_t kDensityStageOffset = make_merged_table().s[31].offset;     // 4 blocks of [16 x 64] bf16, row 0 = w7
 
 // 32 accumulator columns (registers) -> + bias, (ReLU), 16 registers of bf16 pairs
-__device__ __forceinline__ void pack32(const uint32_t (&v)[32], const float* __restrict__ bias, bool relu, uint32_t* p) {
+// RELU is a template parameter (a run-time flag makes nvcc convert both ways and select) and the bias comes through a
+// shared-space address (LDS.128, not a generic load): the 16 epilogue warps are instruction-issue bound.
+template <bool RELU>
+__device__ __forceinline__ void pack32(const uint32_t (&v)[32], uint32_t bias_saddr, uint32_t* p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 b4 = *(const float4*)(bias + 4 * j);
+        float4 b4;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_saddr + 16u * j));
         const float x0 = __uint_as_float(v[4 * j + 0]) + b4.x, x1 = __uint_as_float(v[4 * j + 1]) + b4.y;
         const float x2 = __uint_as_float(v[4 * j + 2]) + b4.z, x3 = __uint_as_float(v[4 * j + 3]) + b4.w;
-        p[2 * j + 0] = relu ? umma::pack_bf16_relu(x0, x1) : umma::pack_bf16(x0, x1);
-        p[2 * j + 1] = relu ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
+        p[2 * j + 0] = RELU ? umma::pack_bf16_relu(x0, x1) : umma::pack_bf16(x0, x1);
+        p[2 * j + 1] = RELU ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
     }
-}
-
-// 64 accumulator columns of this thread's row -> + bias, (ReLU), bf16 pairs.  The accumulator is released (dfree)
-// as soon as the values are in registers.
-__device__ __forceinline__ void load_pack64(uint32_t d_addr, const float* __restrict__ bias, bool relu, uint32_t dfree_bar,
-                                            int lane, uint32_t (&p)[32]) {
-    uint32_t v0[32], v1[32];
-    umma::tmem_ld32(d_addr, v0);
-    umma::tmem_ld32(d_addr + 32, v1);
-    umma::tmem_wait_ld();
-    warp_arrive(dfree_bar, lane);
-    pack32(v0, bias, relu, p);
-    pack32(v1, bias + 32, relu, p + 16);
-}
-
-// Second half of a layer.  The held first-half output `p_lo` may now overwrite A columns [a_addr, +32) (every reader of
-// the old activations has completed); its store is overlapped with the load of the first 32 accumulator columns.
-template <bool PROFILE>
-__device__ __forceinline__ void store_lo_load_pack64(uint32_t a_addr, const uint32_t (&p_lo)[32], uint32_t alo_bar, uint32_t d_addr,
-                                                     const float* __restrict__ bias, bool relu, uint32_t dfree_bar, int lane,
-                                                     uint32_t (&p)[32], long long* tp) {
-    const long long t0 = PROFILE ? clock64() : 0;
-    uint32_t v0[32];
-    umma::tmem_ld32(d_addr, v0);
-    {
-        uint32_t a[16], b[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { a[j] = p_lo[j]; b[j] = p_lo[16 + j]; }
-        umma::tmem_st16(a_addr, a);
-        umma::tmem_st16(a_addr + 16, b);
-    }
-    uint32_t v1[32];
-    umma::tmem_ld32(d_addr + 32, v1);          // in flight together with the stores (their source registers were read at issue)
-    umma::tmem_wait_st();
-    warp_arrive(alo_bar, lane);
-    if (PROFILE) tp[0] += clock64() - t0;
-    umma::tmem_wait_ld();
-    warp_arrive(dfree_bar, lane);
-    if (PROFILE) { asm volatile("" ::"r"(v0[31]), "r"(v1[31])); tp[1] += clock64() - t0; }
-    pack32(v0, bias, relu, p);
-    pack32(v1, bias + 32, relu, p + 16);
-}
-
-// 32 packed registers (64 bf16) -> 32 TMEM columns of this thread's lane, then signal `bar` (one arrive per warp).
-__device__ __forceinline__ void store_a32(uint32_t a_addr, const uint32_t (&p)[32], uint32_t bar, int lane) {
-    uint32_t lo[16], hi[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { lo[j] = p[j]; hi[j] = p[16 + j]; }
-    umma::tmem_st16(a_addr, lo);
-    umma::tmem_st16(a_addr + 16, hi);
-    umma::tmem_wait_st();
-    warp_arrive(bar, lane);
 }
 
 // Row `r` of a [128 x 64] bf16 K-major 128B-swizzled PE tile, four frequencies (12 registers = three 16-byte chunks) at a
@@ -380,10 +333,10 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             const int64_t row0 = pair * 2 * t3::kTileM + r;          // this thread's row in tile X (tile Y: + 128)
             const bool save0 = (act_out != nullptr), save1 = (act_out != nullptr) && (pair * 2 + 1 < num_tiles);
             float sig_part[2] = {0.f, 0.f};
-#pragma unroll 1
-            for (int layer = 0; layer < 7; ++layer) {
-                const bool relu = (layer != 6);                       // feature_fn.4 is linear (nerf_model.py:347)
-                const float* bias = sBias + layer * 256 + cq * 32;
+            // one hidden layer (both halves, both tiles); LAST = feature_fn.4: linear (nerf_model.py:347) and feeds density_fn.0
+            auto hidden_layer = [&](auto last_tag, int layer) {
+                constexpr bool LAST = decltype(last_tag)::value;
+                const uint32_t bias_s = sbase + t3::kOffBias + 4u * (uint32_t)(layer * 256 + cq * 32);
                 uint32_t hold[2][16];                                 // first-half outputs of X and Y, kept until the tile's second half
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {                         // ---- first halves: X then Y
@@ -394,10 +347,10 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     umma::tmem_ld32(d_addr, v);
                     umma::tmem_wait_ld();
                     warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
-                    pack32(v, bias, relu, hold[t]);
+                    pack32<!LAST>(v, bias_s, hold[t]);
                     if (PROFILE && t == 0) { asm volatile("" ::"r"(hold[0][0]), "r"(hold[0][15])); tp[3] += clock64() - t_h0; }
                     if (t == 0 ? save0 : save1) save_act32(act_out, mask_out, row0 + t * 128, layer * 256 + cq * 32, hold[t]);
-                    if (layer == 6) sig_part[t] = dot_bf16x32(hold[t], sW7 + cq * 32, sig_part[t]);
+                    if (LAST) sig_part[t] = dot_bf16x32(hold[t], sW7 + cq * 32, sig_part[t]);
                 }
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {                         // ---- second halves: the held half goes in place first
@@ -415,15 +368,18 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
                     if (PROFILE && t == 0) { asm volatile("" ::"r"(v[31])); tp[1] += clock64() - t_h1; }
                     uint32_t p[16];
-                    pack32(v, bias + 128, relu, p);
+                    pack32<!LAST>(v, bias_s + 512u, p);
                     umma::tmem_st16(a_addr + 64, p);                  // features 128..255 -> A columns 64..127
                     umma::tmem_wait_st();
                     warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
                     if (PROFILE && t == 0) tp[2] += clock64() - t_h1;
                     if (t == 0 ? save0 : save1) save_act32(act_out, mask_out, row0 + t * 128, layer * 256 + 128 + cq * 32, p);
-                    if (layer == 6) sig_part[t] = dot_bf16x32(p, sW7 + 128 + cq * 32, sig_part[t]);
+                    if (LAST) sig_part[t] = dot_bf16x32(p, sW7 + 128 + cq * 32, sig_part[t]);
                 }
-            }
+            };
+#pragma unroll 1
+            for (int layer = 0; layer < 6; ++layer) hidden_layer(std::false_type{}, layer);
+            hidden_layer(std::true_type{}, 6);
             // density_fn.0 (nerf_model.py:350-353): this warp's 64 of the 256 products; the cq = 0 warp of the same rows adds
             // the four partial sums at the last step (ordered behind this write by the alo arrive below and the MMA commit)
 #pragma unroll
@@ -438,7 +394,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 umma::tmem_ld32(d_addr, v);
                 umma::tmem_wait_ld();
                 warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
-                pack32(v, sBias + pk::kBiasR0 + cq * 32, true, p);
+                pack32<true>(v, sbase + t3::kOffBias + 4u * (uint32_t)(pk::kBiasR0 + cq * 32), p);
                 umma::tmem_st16(a_addr, p);                           // r features 0..127 -> A columns 0..63
                 umma::tmem_wait_st();
                 warp_arrive(bars + 8u * (t3::kBarALo + t), lane);

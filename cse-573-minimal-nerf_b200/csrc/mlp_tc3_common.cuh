@@ -133,6 +133,13 @@ struct MmaTile {
             for (int k = 0; k < 4; ++k) umma::mma_ts(d, a + 32u * kb + 8u * k, bdesc + (uint64_t)(2 * k), kI128, (kb | k) ? 1u : first_acc);
         }
     }
+    __device__ __forceinline__ void mma4(uint32_t a_col, uint32_t b, uint32_t first_acc) {          // one K=64 block (one stage)
+        const uint32_t d = tmem + t3::kColD + 128u * T;
+        const uint32_t a = tmem + t3::kColA + 128u * T + a_col;
+        const uint64_t bdesc = ring_desc + b;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::mma_ts(d, a + 8u * k, bdesc + (uint64_t)(2 * k), kI128, k ? 1u : first_acc);
+    }
     template <int NK16> __device__ __forceinline__ void mma_pe(uint64_t a_desc, uint32_t b_off) {   // A = shared-memory PE tile
         const uint32_t d = tmem + t3::kColD + 128u * T;
         const uint64_t bdesc = ring_desc + b_off;
@@ -185,11 +192,12 @@ struct MmaTile {
             umma::mma_commit_u32(e_0);
             umma::mma_commit_u32(e_1);
             if (!FIRST_HALF) {
-                mma8(64, k2, k3, 1u);
+                mma4(64, k2, 1u);
                 umma::mma_commit_u32(e_2);
+                pass_turn();            // early: the other issuer needs ~200 clk to wake up; this tile's last 4 MMAs cover it
+                mma4(96, k3, 1u);
                 umma::mma_commit_u32(e_3);
                 umma::mma_commit_u32(bar(t3::kBarDFull + T));
-                pass_turn();
             }
         });
         if (FIRST_HALF) {               // K blocks 2,3 of the new operand are written ~500 clk after K blocks 0,1
@@ -198,11 +206,12 @@ struct MmaTile {
             need_hi();
             fence();
             issue([&] {
-                mma8(64, k2, k3, 1u);
+                mma4(64, k2, 1u);
                 umma::mma_commit_u32(e_2);
+                pass_turn();
+                mma4(96, k3, 1u);
                 umma::mma_commit_u32(e_3);
                 umma::mma_commit_u32(bar(t3::kBarDFull + T));
-                pass_turn();
             });
         }
     }

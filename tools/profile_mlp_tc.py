@@ -25,6 +25,19 @@ d = torch.nn.functional.normalize(torch.randn(N, 3, device=dev), dim=1)
 ts = (2 + 4 * torch.rand(N, S, device=dev)).contiguous()
 sigma = torch.empty(N, S, device=dev)
 rgb = torch.empty(N, S, 3, device=dev)
+if os.environ.get("NERF_PROF_PLAIN") == "1":
+    # production kernel (no counters), 20 back-to-back launches: the number to compare kernel variants with
+    plain = nat.lib().nerf_mlp_forward_tc
+    for rep in range(3):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(20):
+            nat.check(plain(nat.ptr(packed), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, nat.ptr(sigma), nat.ptr(rgb), nat.stream()), "mlp")
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / 20
+        print(f"plain kernel N={N} S={S}: {ms:.4f} ms, {N*S*920832/ms/1e9:.1f} TFLOP/s")
+    sys.exit(0)
 fn = nat.lib().nerf_debug_mlp_tc_profile
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p] * 4
