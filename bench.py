@@ -185,7 +185,7 @@ def bench_train(args, rank, world, dev):
     net.load_state_dict(synthetic.make_state_dict(0, "init"))
     net = net.to(dev)
     opt = net.configure_optimizers()["optimizer"]
-    grads = FlatGradients(net.parameters())
+    grads = FlatGradients(net.parameters(), opt)
     H = W = 800
     c2w, focal = frame_setup(H, W, 7 * rank + 3)
     image = torch.from_numpy(synthetic.analytic_scene_rgba(c2w.numpy(), H, W, focal)[..., :3].copy()).to(dev)
@@ -225,7 +225,7 @@ def bench_train(args, rank, world, dev):
             "steps": steps, "rays_per_step_per_gpu": n, "final_loss": float(loss.detach()),
             "algorithmic_tflops_per_gpu": tfl, "frac_of_sustained_peak": tfl / pk["tflops_sustained"],
             "backward": "hand-written: composite_backward_kernel, mlp_tc_bwd_kernel (tcgen05 dgrad chain), "
-                        "wgrad_tc_kernel (tcgen05 wgrad + bias sums); Adam = torch fused",
+                        "wgrad_tc_kernel (tcgen05 wgrad + bias sums); Adam = hand-written flat kernel (adam.cu), gradients accumulated straight into the flat buffer",
             "hbm_bytes_per_step_per_gpu_est": int(n * 256 * (3840 + 240 + 240 + 3872 + 1.14 * 7712)),
             "collective": "one NCCL all-reduce of the 924 680-float flat gradient buffer per step" if world > 1 else None}
 

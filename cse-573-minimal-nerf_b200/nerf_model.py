@@ -195,9 +195,11 @@ class NeRFNetwork(LightningModule):
     def configure_optimizers(self):
         start_lr, end_lr, num_epochs = 5e-4, 5e-5, 1200
         gamma = (end_lr / start_lr) ** (1 / num_epochs)
-        optimizer = torch.optim.Adam(self.parameters(), lr=start_lr, fused=all(p.is_cuda for p in self.parameters()))
-        # the fused multi-tensor update does not bump the parameters' version counters, which is what the packed
-        # bf16 weight images are keyed on: drop them explicitly after every step
+        import optim
+        # one hand-written kernel over flat parameter / gradient / moment buffers (csrc/adam.cu) instead of torch's
+        # multi-tensor Adam.  It updates the parameters in place without bumping their version counters, which is what
+        # the packed bf16 weight images are keyed on: drop them explicitly after every step
+        optimizer = optim.FlatAdam(self.parameters(), lr=start_lr)
         optimizer.register_step_post_hook(lambda *args, **kwargs: self.invalidate_packed_weights())
         lr_decay = torch.optim.lr_scheduler.ExponentialLR(optimizer=optimizer, gamma=gamma)
         return {'optimizer': optimizer, 'lr_scheduler': lr_decay}

@@ -1,0 +1,94 @@
+"""Adam for NeRFNetwork.configure_optimizers (nerf_model.py:134-143) as one hand-written kernel over flat buffers.
+
+`FlatAdam` keeps every parameter, gradient and Adam moment of the model as views of four contiguous fp32 buffers and
+updates all of them with a single `nerf_adam_step` launch (csrc/adam.cu) - the same arithmetic, in the same order, as
+torch.optim.Adam's single-tensor path.  It is a `torch.optim.Optimizer`, so `ExponentialLR`, `state_dict()` /
+`load_state_dict()` and the PL-format checkpoints (`optimizer_states`) keep working, with torch.optim.Adam's state layout
+(`step`, `exp_avg`, `exp_avg_sq` per parameter; param_groups with lr / betas / eps / weight_decay / amsgrad).
+"""
+import torch
+
+import _native as nat
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        params = [p for p in params if p.requires_grad]
+        if not params or not all(p.is_cuda and p.dtype == torch.float32 for p in params):
+            raise RuntimeError("FlatAdam: expected fp32 CUDA parameters (this path has no CPU implementation)")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None)
+        super().__init__(params, defaults)
+        self._params = params
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self._n = (n + 3) // 4 * 4
+        self.flat_params = torch.zeros(self._n, device=dev, dtype=torch.float32)
+        self.flat_grads = torch.zeros(self._n, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(self._n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(self._n, device=dev, dtype=torch.float32)
+        self._step = 0
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat_params[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_params[off:off + k].view_as(p)         # parameters become views of the flat buffer
+            p.grad = self.flat_grads[off:off + k].view_as(p)           # and so do their gradients (one all-reduce per step)
+            off += k
+        self._bind_state()
+
+    def _bind_state(self):
+        """Per-parameter state entries in torch.optim.Adam's layout, as views of the flat moment buffers."""
+        off = 0
+        for p in self._params:
+            k = p.numel()
+            self.state[p] = {"step": torch.tensor(float(self._step)),
+                             "exp_avg": self.flat_m[off:off + k].view_as(p),
+                             "exp_avg_sq": self.flat_v[off:off + k].view_as(p)}
+            off += k
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grads.zero_()
+
+    def _grads_are_flat(self):
+        off = 0
+        base = self.flat_grads.data_ptr()
+        for p in self._params:
+            if p.grad is None or p.grad.data_ptr() != base + 4 * off or not p.grad.is_contiguous():
+                return False
+            off += p.numel()
+        return True
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        if not self._grads_are_flat():            # someone re-pointed .grad (e.g. trainer.FlatGradients): gather once
+            off = 0
+            for p in self._params:
+                k = p.numel()
+                if p.grad is not None:
+                    self.flat_grads[off:off + k].copy_(p.grad.reshape(-1))
+                else:
+                    self.flat_grads[off:off + k].zero_()
+                off += k
+        g = self.param_groups[0]
+        self._step += 1
+        nat.check(nat.lib().nerf_adam_step(nat.ptr(self.flat_params), nat.ptr(self.flat_grads), nat.ptr(self.flat_m),
+                                           nat.ptr(self.flat_v), self._n, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                           float(g["eps"]), self._step, nat.stream()), "nerf_adam_step")
+        for p in self._params:
+            self.state[p]["step"] = torch.tensor(float(self._step))
+        return loss
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)        # torch copies the saved tensors in; move them back into the flat buffers
+        off = 0
+        for p in self._params:
+            k = p.numel()
+            st = self.state.get(p, {})
+            if "exp_avg" in st:
+                self.flat_m[off:off + k].copy_(st["exp_avg"].reshape(-1).to(self.flat_m.device))
+                self.flat_v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1).to(self.flat_v.device))
+                self._step = int(float(st.get("step", self._step)))
+            off += k
+        self._bind_state()

@@ -42,8 +42,11 @@ class JsonLogger:
 class FlatGradients:
     """All parameter gradients as views of one contiguous fp32 buffer (one all-reduce per step)."""
 
-    def __init__(self, params):
+    def __init__(self, params, optimizer=None):
         self.params = [p for p in params if p.requires_grad]
+        if optimizer is not None and hasattr(optimizer, "flat_grads"):
+            self.flat = optimizer.flat_grads          # optim.FlatAdam already keeps every .grad as a view of one buffer
+            return
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, device=self.params[0].device, dtype=torch.float32)
         off = 0
@@ -113,7 +116,7 @@ class Trainer:
             if scheduler is not None and ckpt.get("lr_schedulers"):
                 scheduler.load_state_dict(ckpt["lr_schedulers"][0])
             self.current_epoch, self.global_step = ckpt.get("epoch", 0) + 1, ckpt.get("global_step", 0)
-        grads = FlatGradients(model.parameters())
+        grads = FlatGradients(model.parameters(), optimizer)
         loader = None
         while self.global_step < self.max_steps and (self.max_epochs is None or self.current_epoch < self.max_epochs):
             if loader is None or (self.reload_every and self.current_epoch % self.reload_every == 0):

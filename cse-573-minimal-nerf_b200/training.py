@@ -66,7 +66,7 @@ def composite_backward(sigma, rgb, ts, g_ray):
     return dsig, drgb
 
 
-def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray):
+def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray, accumulate_into_grad=False):
     """Gradients of one network's 20 parameters (state_dict order) given dL/d(ray colour) [N,3]: all hand-written kernels -
     compositing backward, tcgen05 dgrad chain (mlp_tc_bwd.cu), tcgen05 wgrad + bias sums (wgrad_tc.cu)."""
     import ctypes
@@ -79,16 +79,22 @@ def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray):
         nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb),
                                                  N, S, nat.ptr(dz_t), nat.stream()), "nerf_mlp_backward_tc")
     params = model.ordered_params()
-    flat = torch.zeros(sum(p.numel() for p in params), device=ts.device, dtype=F32)
-    grads, off = [], 0
-    for p in params:
-        grads.append(flat[off:off + p.numel()].view_as(p))
-        off += p.numel()
+    direct = accumulate_into_grad and all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == F32 for p in params)
+    if direct:
+        # wgrad ACCUMULATES with atomics: add straight into the existing .grad buffers (views of the optimiser's flat
+        # gradient buffer) and hand autograd nothing to accumulate - 40 AccumulateGrad adds and a memset per step less
+        grads = [p.grad for p in params]
+    else:
+        flat = torch.zeros(sum(p.numel() for p in params), device=ts.device, dtype=F32)
+        grads, off = [], 0
+        for p in params:
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
     arr = (ctypes.c_void_p * 20)(*[g.data_ptr() for g in grads])
     with nat.timed_kernel("wgrad_tc_kernel", M):
         nat.check(nat.lib().nerf_wgrad_tc(nat.ptr(acts), nat.ptr(dz_t), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, arr, nat.stream()),
                   "nerf_wgrad_tc")
-    return grads
+    return [None] * 20 if direct else grads
 
 
 def mlp_backward_library_wgrad(model, o, d, ts, sigma, rgb, acts, g_ray):
@@ -228,7 +234,7 @@ class RenderFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_c, g_f):
         net, o, d, a = ctx.net, ctx.o, ctx.d, ctx.aux
-        gc = mlp_backward(net.coarse_network, o, d, a["c_ts"], a["c_sigma"], a["c_rgb"], a["c_acts"], g_c.contiguous())
-        gf = mlp_backward(net.fine_network, o, d, a["ts"], a["f_sigma"], a["f_rgb"], a["f_acts"], g_f.contiguous())
+        gc = mlp_backward(net.coarse_network, o, d, a["c_ts"], a["c_sigma"], a["c_rgb"], a["c_acts"], g_c.contiguous(), True)
+        gf = mlp_backward(net.fine_network, o, d, a["ts"], a["f_sigma"], a["f_rgb"], a["f_acts"], g_f.contiguous(), True)
         ctx.aux = None
         return (None,) * 6 + tuple(gc) + tuple(gf)

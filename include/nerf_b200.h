@@ -137,6 +137,13 @@ int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float*
 int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
                                int64_t N, int S, float* sigma, float* rgb, void* stream);
 
+/* ---- optimiser step.  nerf_model.py:134-143 (torch.optim.Adam, lr 5e-4, betas (0.9, 0.999), eps 1e-8, no weight decay)
+ * over flat fp32 buffers of n elements (all parameters of both networks): params updated in place, exp_avg / exp_avg_sq
+ * are the Adam moments, step >= 1 is the 1-based step count used for the bias corrections.  Same arithmetic and order as
+ * torch's single-tensor Adam; buffers 16-byte aligned. */
+int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,3 +133,41 @@ def test_dgrad_kernel_matches_library_chain():
             cos = F.cosine_similarity(x, y, dim=0).item()
             rel = ((x - y).norm() / y.norm().clamp(min=1e-20)).item()
             assert cos > 0.999 and rel < tol, f"{name} ({tag}): cosine {cos:.5f} rel {rel:.4f}"
+
+
+def test_flat_adam_matches_torch_adam():
+    """optim.FlatAdam (one hand-written kernel over flat buffers, csrc/adam.cu) against torch.optim.Adam on the same
+    gradients for 25 steps with a decaying learning rate, then a state_dict round trip into a fresh optimiser (the
+    PL-format checkpoints store optimizer.state_dict())."""
+    import copy
+    import optim
+    torch.manual_seed(3)
+    net_a = make_net(4, "dense")
+    net_b = copy.deepcopy(net_a)
+    opt_a = optim.FlatAdam(net_a.parameters(), lr=5e-4)
+    opt_b = torch.optim.Adam(net_b.parameters(), lr=5e-4)
+    sch_a = torch.optim.lr_scheduler.ExponentialLR(opt_a, gamma=0.9)
+    sch_b = torch.optim.lr_scheduler.ExponentialLR(opt_b, gamma=0.9)
+    gen = torch.Generator(device=DEV).manual_seed(11)
+
+    def run(steps, oa, ob, sa, sb):
+        for _ in range(steps):
+            oa.zero_grad()
+            for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+                g = torch.randn(pa.shape, device=DEV, generator=gen) * (10.0 ** float(torch.randint(-6, 1, (1,)).item()))
+                pa.grad.copy_(g)
+                pb.grad = g.clone()
+            oa.step(); ob.step(); sa.step(); sb.step()
+
+    run(25, opt_a, opt_b, sch_a, sch_b)
+    for (name, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+        torch.testing.assert_close(pa.detach(), pb.detach(), rtol=2e-6, atol=1e-7, msg=lambda m: f"{name}: {m}")
+    sd = opt_a.state_dict()
+    assert set(sd["state"][0].keys()) >= {"step", "exp_avg", "exp_avg_sq"} and sd["param_groups"][0]["betas"] == (0.9, 0.999)
+    opt_c = optim.FlatAdam(net_a.parameters(), lr=5e-4)
+    opt_c.load_state_dict(copy.deepcopy(sd))
+    sch_c = torch.optim.lr_scheduler.ExponentialLR(opt_c, gamma=0.9)
+    sch_c.load_state_dict(sch_a.state_dict())
+    run(5, opt_c, opt_b, sch_c, sch_b)
+    for (name, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+        torch.testing.assert_close(pa.detach(), pb.detach(), rtol=5e-6, atol=1e-7, msg=lambda m: f"{name} after resume: {m}")

@@ -11,7 +11,7 @@ from trainer import FlatGradients
 dev = torch.device("cuda")
 net = nerf_model.NeRFNetwork(); net.load_state_dict(synthetic.make_state_dict(0, "init")); net = net.to(dev)
 opt = net.configure_optimizers()["optimizer"]
-grads = FlatGradients(net.parameters())
+grads = FlatGradients(net.parameters(), opt)
 c2w, focal = bench.frame_setup(800, 800, 3)
 image = torch.from_numpy(synthetic.analytic_scene_rgba(c2w.numpy(), 800, 800, focal)[..., :3].copy()).to(dev)
 def step():
