@@ -129,36 +129,23 @@ __device__ __forceinline__ float dot_bf16x32(const uint32_t (&p)[16], const floa
     return acc;
 }
 
-// training, 32 features of one row: bf16 activations (four 16-byte chunks) + the matching half of the 64-bit sign word
-__device__ __forceinline__ void save_act32(__nv_bfloat16* __restrict__ act_out, unsigned long long* __restrict__ mask_out,
-                                           int64_t row, int feature, const uint32_t (&p)[16]) {
-    uint4* chunk = (uint4*)(act_out + pk::tiled_offset(row, feature, pk::kActChunks));
-    uint32_t mbits = 0u;
+// training, 32 features of one row: bf16 activations (four 16-byte chunks, tiled chunk-major) + one 32-bit word of ReLU
+// sign bits for the dgrad kernel.  `act_row` / `mask_row` point at this row's feature 0 / group 0; word layout (two-tile
+// kernels only): packed pair j = features (2j, 2j+1) of the group -> bit 15-j / bit 31-j.  The bits are collected with two
+// funnel shifts per pair: h + 0x7FFF carries into bit 15 exactly when the (non-negative) bf16 h is non-zero.
+__device__ __forceinline__ void save_act32(__nv_bfloat16* __restrict__ act_row, uint32_t* __restrict__ mask_row, int feature,
+                                           const uint32_t (&p)[16]) {
+    uint4* chunk = (uint4*)(act_row + (size_t)(feature >> 3) * 1024);
 #pragma unroll
     for (int j = 0; j < 4; ++j) chunk[j * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+    uint32_t mlo = 0u, mhi = 0u;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        mbits |= (uint32_t)((p[j] & 0x00007FFFu) != 0u) << (2 * j);
-        mbits |= (uint32_t)((p[j] & 0x7FFF0000u) != 0u) << (2 * j + 1);
+        const uint32_t t = p[j] + 0x7FFF7FFFu;
+        mhi = __funnelshift_l(t, mhi, 1);
+        mlo = __funnelshift_l(t << 16, mlo, 1);
     }
-    uint32_t* words = (uint32_t*)mask_out;           // little-endian: features 0..31 of the block are the low half
-    words[(((row >> 7) * pk::kMaskWords + (feature >> 6)) * 128 + (row & 127)) * 2 + ((feature >> 5) & 1)] = mbits;
-}
-
-// training: keep what the next layer consumes (post-activation bf16, tiled chunk-major, pack_layout.cuh) and the 64-bit
-// word of ReLU sign bits the dgrad kernel masks with.
-__device__ __forceinline__ void save_act64(__nv_bfloat16* __restrict__ act_out, unsigned long long* __restrict__ mask_out,
-                                           int64_t row, int feature, const uint32_t (&p)[32]) {
-    uint4* chunk = (uint4*)(act_out + pk::tiled_offset(row, feature, pk::kActChunks));
-    unsigned long long mbits = 0ull;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) chunk[j * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        mbits |= (unsigned long long)((p[j] & 0x00007FFFu) != 0u) << (2 * j);
-        mbits |= (unsigned long long)((p[j] & 0x7FFF0000u) != 0u) << (2 * j + 1);
-    }
-    mask_out[((row >> 7) * pk::kMaskWords + (feature >> 6)) * 128 + (row & 127)] = mbits;
+    mask_row[(size_t)(feature >> 5) * 128] = (mhi << 16) | mlo;
 }
 
 // dbg counters (PROFILE), per CTA x 16: 0 MMA warp total, 1 wait weights, 2 wait dfree, 3 wait alo/ahi, 4 wait PE,
@@ -332,6 +319,11 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int64_t row0 = pair * 2 * t3::kTileM + r;          // this thread's row in tile X (tile Y: + 128)
             const bool save0 = (act_out != nullptr), save1 = (act_out != nullptr) && (pair * 2 + 1 < num_tiles);
+            // this thread's rows in the tiled chunk-major training tensors (pack_layout.cuh): feature 0 / sign-word group 0
+            __nv_bfloat16* const act_row0 = act_out + pk::tiled_offset(row0, 0, pk::kActChunks);
+            __nv_bfloat16* const act_row1 = act_row0 + (size_t)pk::kActChunks * 1024;
+            uint32_t* const mask_row0 = (uint32_t*)mask_out + ((row0 >> 7) * (2 * pk::kMaskWords)) * 128 + (row0 & 127);
+            uint32_t* const mask_row1 = mask_row0 + (size_t)(2 * pk::kMaskWords) * 128;
             float sig_part[2] = {0.f, 0.f};
             // one hidden layer (both halves, both tiles); LAST = feature_fn.4: linear (nerf_model.py:347) and feeds density_fn.0
             auto hidden_layer = [&](auto last_tag, int layer) {
@@ -349,7 +341,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
                     pack32<!LAST>(v, bias_s, hold[t]);
                     if (PROFILE && t == 0) { asm volatile("" ::"r"(hold[0][0]), "r"(hold[0][15])); tp[3] += clock64() - t_h0; }
-                    if (t == 0 ? save0 : save1) save_act32(act_out, mask_out, row0 + t * 128, layer * 256 + cq * 32, hold[t]);
+                    if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, layer * 256 + cq * 32, hold[t]);
                     if (LAST) sig_part[t] = dot_bf16x32(hold[t], sW7 + cq * 32, sig_part[t]);
                 }
 #pragma unroll
@@ -373,7 +365,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     umma::tmem_wait_st();
                     warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
                     if (PROFILE && t == 0) tp[2] += clock64() - t_h1;
-                    if (t == 0 ? save0 : save1) save_act32(act_out, mask_out, row0 + t * 128, layer * 256 + 128 + cq * 32, p);
+                    if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, layer * 256 + 128 + cq * 32, p);
                     if (LAST) sig_part[t] = dot_bf16x32(p, sW7 + 128 + cq * 32, sig_part[t]);
                 }
             };
@@ -398,7 +390,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 umma::tmem_st16(a_addr, p);                           // r features 0..127 -> A columns 0..63
                 umma::tmem_wait_st();
                 warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
-                if (t == 0 ? save0 : save1) save_act32(act_out, mask_out, row0 + t * 128, 1792 + cq * 32, p);
+                if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, 1792 + cq * 32, p);
             }
             // ---- rgb_fn.2: columns 0..2 -> sigmoid(. + b) (nerf_model.py:358-359); sigma = relu(feat . w7 + b7)
 #pragma unroll

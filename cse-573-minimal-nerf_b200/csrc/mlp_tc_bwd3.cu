@@ -7,11 +7,21 @@
 //     dz5  = (dz6 . W6) * [h5 > 0]                             steps 2,3   (A = previous dz in TMEM, TS; B = W^T stages)
 //     dz4 .. dz0 likewise through feature_fn.2, feature_fn.0 (h columns), mlp.6, mlp.4, mlp.2     steps 4..13
 //   every dz is written to global (bf16, tiled chunk-major, pack_layout.cuh) for wgrad, plus the 16-wide heads block.
-// ReLU masks are the sign words the forward kernel wrote per (row, 64-feature block), read here as 32-bit halves.
+// ReLU masks are the 32-bit sign words mlp_tc3.cu wrote per (row, 32-feature group): packed pair j -> bits 15-j / 31-j;
+// they are applied to the PACKED bf16 pairs (shift + PRMT sign replication + AND: three instructions per pair).
 // mlp.0's dgrad (d PE) is not needed: the inputs carry no gradient.
 #include "mlp_tc3_common.cuh"
 
 namespace nerf {
+
+// 0xFFFF fields for the bf16 halves whose sign-word bits (bit 15 -> low half, bit 31 -> high half of `s`) are set:
+// prmt in its generic mode replicates the msb of the selected byte when the selector nibble has bit 3 set
+// (__byte_perm only forwards three selector bits per nibble).
+__device__ __forceinline__ uint32_t keep_mask(uint32_t s) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(r) : "r"(s));
+    return r;
+}
 
 namespace b3 {
 constexpr uint32_t kOffDr = 0;                                    // dr tiles of X and Y: 2 x 2 K-blocks x [128 x 64] bf16
@@ -116,18 +126,17 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
 #pragma unroll 1
                 for (int c = 0; c < 16; ++c) {                    // chunk c = features 8c .. 8c+7 of r (rgb_fn.0's ReLU output)
                     // sign bits written by the forward kernel: 32-bit half (c >> 2) & 1 of block 28 + (c >> 3)
+                    // sign word of r's 32-feature group 56 + (c >> 2) (r = activations 1792..1919); this chunk = pairs 4(c&3)..+3
                     uint32_t mb = 0u;
-                    if (store) mb = masks32[(((row >> 7) * pk::kMaskWords + 28 + (c >> 3)) * 128 + (row & 127)) * 2 + ((c >> 2) & 1)];
-                    mb >>= (c & 3) * 8;
+                    if (store) mb = masks32[((row >> 7) * (2 * pk::kMaskWords) + 56 + (c >> 2)) * 128 + (row & 127)];
+                    mb <<= (c & 3) * 4;
                     uint32_t v[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int k = c * 8 + 2 * j;
-                        float a = g0 * W9[k] + g1 * W9[128 + k] + g2 * W9[256 + k];            // nerf_model.py:358 backward
-                        float b = g0 * W9[k + 1] + g1 * W9[128 + k + 1] + g2 * W9[256 + k + 1];
-                        if (!((mb >> (2 * j)) & 1u)) a = 0.f;
-                        if (!((mb >> (2 * j + 1)) & 1u)) b = 0.f;
-                        v[j] = umma::pack_bf16(a, b);
+                        const float a = g0 * W9[k] + g1 * W9[128 + k] + g2 * W9[256 + k];            // nerf_model.py:358 backward
+                        const float b = g0 * W9[k + 1] + g1 * W9[128 + k + 1] + g2 * W9[256 + k + 1];
+                        v[j] = umma::pack_bf16(a, b) & keep_mask(mb << j);
                     }
                     const uint4 q4 = make_uint4(v[0], v[1], v[2], v[3]);
                     const int kb = c >> 3, cc = c & 7;            // K block, chunk inside its 128-byte row
@@ -161,17 +170,17 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
         };
         // 32 accumulator columns -> (+ dsigma (x) w7 | ReLU mask) -> 16 registers of bf16 pairs
         auto finish = [&](const uint32_t (&v)[32], bool first, float dsg, uint32_t mb, int col0, uint32_t* p) {
+            if (first) {                                    // + dsigma_pre (x) w7  (density head, nerf_model.py:351)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
-                if (first) {                                // + dsigma_pre (x) w7  (density head, nerf_model.py:351)
-                    a = fmaf(dsg, w7[col0 + 2 * i], a);
-                    b = fmaf(dsg, w7[col0 + 2 * i + 1], b);
-                } else {
-                    if (!((mb >> (2 * i)) & 1u)) a = 0.f;
-                    if (!((mb >> (2 * i + 1)) & 1u)) b = 0.f;
+                for (int i = 0; i < 16; ++i) {
+                    const float a = fmaf(dsg, w7[col0 + 2 * i], __uint_as_float(v[2 * i]));
+                    const float b = fmaf(dsg, w7[col0 + 2 * i + 1], __uint_as_float(v[2 * i + 1]));
+                    p[i] = umma::pack_bf16(a, b);
                 }
-                p[i] = umma::pack_bf16(a, b);
+            } else {                                        // ReLU mask on the packed pair: bits 15-i / 31-i -> 0xFFFF fields
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    p[i] = umma::pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & keep_mask(mb << i);
             }
         };
         auto store_dz = [&](int64_t row, int feature, const uint32_t* p) {
@@ -198,7 +207,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                     const int col0 = cq * 32;
                     // ReLU mask source: saved output of layer j (post-ReLU), except dz6 (feature_fn.4 is linear)
                     uint32_t mb = 0u;
-                    if (!first && st) mb = masks32[(((row >> 7) * pk::kMaskWords + ((j * 256 + col0) >> 6)) * 128 + (row & 127)) * 2 + (cq & 1)];
+                    if (!first && st) mb = masks32[((row >> 7) * (2 * pk::kMaskWords) + ((j * 256 + col0) >> 5)) * 128 + (row & 127)];
                     const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
                     wait_d(t);
                     uint32_t v[32];
@@ -214,7 +223,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                     const bool st = t == 0 ? st0 : st1;
                     const int col0 = 128 + cq * 32;
                     uint32_t mb = 0u;
-                    if (!first && st) mb = masks32[(((row >> 7) * pk::kMaskWords + ((j * 256 + col0) >> 6)) * 128 + (row & 127)) * 2 + (cq & 1)];
+                    if (!first && st) mb = masks32[((row >> 7) * (2 * pk::kMaskWords) + ((j * 256 + col0) >> 5)) * 128 + (row & 127)];
                     const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
                     const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(cq * 16);
                     wait_d(t);

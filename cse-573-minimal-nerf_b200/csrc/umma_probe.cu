@@ -344,3 +344,49 @@ extern "C" int nerf_debug_copy_stream(const void* src, uint32_t src_bytes, int m
     copy_stream_probe_kernel<<<grid, 32 * (nprod + 1), smem, (cudaStream_t)stream>>>(tm, (const uint8_t*)src, src_bytes, mode, bytes, slots, nstages, out);
     return check_launch("nerf_debug_copy_stream");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// HBM write / read bandwidth probes (plain grid-stride kernels, 16-byte accesses): the write-only figure is the roofline of
+// the training-form forward and of the dgrad kernel, which only write their saved tensors.
+namespace nerf {
+__global__ void __launch_bounds__(512) write_bw_kernel(uint4* __restrict__ dst, int64_t n16, uint32_t value) {
+    const uint4 v = make_uint4(value, value + 1, value + 2, value + 3);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+__global__ void __launch_bounds__(512) read_bw_kernel(const uint4* __restrict__ src, int64_t n16, uint32_t* __restrict__ sink) {
+    uint32_t acc = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(src + i);
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345679u) *sink = acc;
+}
+}  // namespace nerf
+
+namespace nerf {
+// the training kernels' store pattern: a warp writes 512 contiguous bytes (one 16-byte chunk row of its 32 sample rows), a
+// CTA walks its own 480 KB tile region chunk row by chunk row (2 KB apart), 148 CTAs at scattered tile regions at once
+__global__ void __launch_bounds__(512) write_tiled_kernel(uint4* __restrict__ dst, int64_t tiles, uint32_t value) {
+    const uint4 v = make_uint4(value, value + 1, value + 2, value + 3);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, cq = warp >> 2;                       // 16 warps: row quarter, column quarter
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        uint4* base = dst + tile * (240 * 128);                   // 240 chunk rows x 128 rows x 16 B
+        for (int step = 0; step < 15; ++step)                     // 15 half-steps of 128 features = 16 chunk rows each
+#pragma unroll
+            for (int j = 0; j < 4; ++j) base[(step * 16 + cq * 4 + j) * 128 + q * 32 + lane] = v;
+    }
+}
+}  // namespace nerf
+
+extern "C" int nerf_debug_hbm_bw(void* buf, int64_t bytes, int mode, int blocks_per_sm, void* sink, void* stream) {
+    using namespace nerf;
+    const int grid = num_sms() * blocks_per_sm;
+    if (mode == 2) {
+        write_tiled_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>((uint4*)buf, bytes / (240 * 128 * 16), 7u);
+        return check_launch("nerf_debug_hbm_bw");
+    }
+    if (mode == 0) write_bw_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>((uint4*)buf, bytes / 16, 7u);
+    else read_bw_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>((const uint4*)buf, bytes / 16, (uint32_t*)sink);
+    return check_launch("nerf_debug_hbm_bw");
+}
