@@ -65,10 +65,16 @@ template <bool RELU>
 __device__ __forceinline__ void pack32(const uint32_t (&v)[32], uint32_t bias_saddr, uint32_t* p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        float4 b4;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_saddr + 16u * j));
-        const float x0 = __uint_as_float(v[4 * j + 0]) + b4.x, x1 = __uint_as_float(v[4 * j + 1]) + b4.y;
-        const float x2 = __uint_as_float(v[4 * j + 2]) + b4.z, x3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+        // 4 accumulators + 4 biases as two packed fp32 pairs (add.rn.f32x2: one instruction per pair on sm_100)
+        unsigned long long b01, b23, x01, x23;
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b01), "=l"(b23) : "r"(bias_saddr + 16u * j));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x01) : "r"(v[4 * j + 0]), "r"(v[4 * j + 1]));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x23) : "r"(v[4 * j + 2]), "r"(v[4 * j + 3]));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(x01) : "l"(b01));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(x23) : "l"(b23));
+        float x0, x1, x2, x3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(x2), "=f"(x3) : "l"(x23));
         p[2 * j + 0] = RELU ? umma::pack_bf16_relu(x0, x1) : umma::pack_bf16(x0, x1);
         p[2 * j + 1] = RELU ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
     }

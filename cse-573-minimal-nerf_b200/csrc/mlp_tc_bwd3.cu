@@ -10,6 +10,7 @@
 // ReLU masks are the 32-bit sign words mlp_tc3.cu wrote per (row, 32-feature group): packed pair j -> bits 15-j / 31-j;
 // they are applied to the PACKED bf16 pairs (shift + PRMT sign replication + AND: three instructions per pair).
 // mlp.0's dgrad (d PE) is not needed: the inputs carry no gradient.
+#include <type_traits>
 #include "mlp_tc3_common.cuh"
 
 namespace nerf {
@@ -168,84 +169,77 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
             umma::tc_fence_after();
             ++nd[t];
         };
-        // 32 accumulator columns -> (+ dsigma (x) w7 | ReLU mask) -> 16 registers of bf16 pairs
-        auto finish = [&](const uint32_t (&v)[32], bool first, float dsg, uint32_t mb, int col0, uint32_t* p) {
-            if (first) {                                    // + dsigma_pre (x) w7  (density head, nerf_model.py:351)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float a = fmaf(dsg, w7[col0 + 2 * i], __uint_as_float(v[2 * i]));
-                    const float b = fmaf(dsg, w7[col0 + 2 * i + 1], __uint_as_float(v[2 * i + 1]));
-                    p[i] = umma::pack_bf16(a, b);
-                }
-            } else {                                        // ReLU mask on the packed pair: bits 15-i / 31-i -> 0xFFFF fields
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    p[i] = umma::pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & keep_mask(mb << i);
-            }
-        };
-        auto store_dz = [&](int64_t row, int feature, const uint32_t* p) {
-            uint4* dst = (uint4*)(dz_out + pk::tiled_offset(row, feature, pk::kDzChunks));
+        auto store_dz = [&](__nv_bfloat16* dz_row, int feature, const uint32_t* p) {
+            uint4* dst = (uint4*)(dz_row + (size_t)(feature >> 3) * 1024);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i * 128] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
         };
 
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int64_t row0 = pair * 2 * t3::kTileM + r;
-            const bool st0 = true, st1 = (pair * 2 + 1 < num_tiles);
+            const bool st1 = (pair * 2 + 1 < num_tiles);
             float dsg[2];
             dsg[0] = (row0 < total) ? dsigma_pre[row0] : 0.f;
             dsg[1] = (row0 + 128 < total) ? dsigma_pre[row0 + 128] : 0.f;
-#pragma unroll 1
-            for (int L = 0; L < 7; ++L) {
-                const int j = 6 - L;                        // output: dz_j (gradient w.r.t. the pre-activation of layer j)
-                const bool first = (L == 0);
+            // this thread's rows in the tiled chunk-major tensors: feature 0 of dz, sign-word group 0 of the masks
+            __nv_bfloat16* const dz_row0 = dz_out + pk::tiled_offset(row0, 0, pk::kDzChunks);
+            __nv_bfloat16* const dz_row1 = dz_row0 + (size_t)pk::kDzChunks * 1024;
+            const uint32_t* const mask_row0 = masks32 + ((row0 >> 7) * (2 * pk::kMaskWords)) * 128 + (row0 & 127);
+            const uint32_t* const mask_row1 = mask_row0 + (size_t)(2 * pk::kMaskWords) * 128;
+            // one step of the chain (both halves, both tiles).  FIRST: dz6 = accumulator + dsigma_pre (x) w7 (density head,
+            // nerf_model.py:351), no mask (feature_fn.4 is linear); otherwise the ReLU mask of layer j's saved output is applied
+            // to the packed pair (bits 15-i / 31-i of the sign word -> 0xFFFF fields).  j > 0: dz_j is the next A operand.
+            auto chain_step = [&](auto first_tag, int j) {
+                constexpr bool FIRST = decltype(first_tag)::value;
                 uint32_t hold[2][16];
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {               // ---- first halves (features cq*32 ..): X then Y
-                    const int64_t row = row0 + t * 128;
-                    const bool st = t == 0 ? st0 : st1;
-                    const int col0 = cq * 32;
-                    // ReLU mask source: saved output of layer j (post-ReLU), except dz6 (feature_fn.4 is linear)
-                    uint32_t mb = 0u;
-                    if (!first && st) mb = masks32[((row >> 7) * (2 * pk::kMaskWords) + ((j * 256 + col0) >> 5)) * 128 + (row & 127)];
-                    const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
-                    wait_d(t);
-                    uint32_t v[32];
-                    umma::tmem_ld32(d_addr, v);
-                    umma::tmem_wait_ld();
-                    warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
-                    finish(v, first, dsg[t], mb, col0, hold[t]);
-                    if (st) store_dz(row, j * 256 + col0, hold[t]);
-                }
+                for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {               // ---- second halves (features 128 + cq*32 ..)
-                    const int64_t row = row0 + t * 128;
-                    const bool st = t == 0 ? st0 : st1;
-                    const int col0 = 128 + cq * 32;
-                    uint32_t mb = 0u;
-                    if (!first && st) mb = masks32[((row >> 7) * (2 * pk::kMaskWords) + ((j * 256 + col0) >> 5)) * 128 + (row & 127)];
-                    const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
-                    const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(cq * 16);
-                    wait_d(t);
-                    uint32_t v[32];
-                    umma::tmem_ld32(d_addr, v);
-                    if (j > 0) {                            // dz_j is the A operand of the next dgrad GEMM: held half in place first
-                        umma::tmem_st16(a_addr, hold[t]);
-                        umma::tmem_wait_st();
-                        warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
+                    for (int t = 0; t < 2; ++t) {
+                        const bool st = (t == 0) || st1;
+                        const int col0 = h * 128 + cq * 32;
+                        uint32_t mb = 0u;
+                        if (!FIRST && st) mb = __ldg((t ? mask_row1 : mask_row0) + (size_t)((j * 256 + col0) >> 5) * 128);
+                        const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
+                        const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(cq * 16);
+                        wait_d(t);
+                        uint32_t v[32];
+                        umma::tmem_ld32(d_addr, v);
+                        if (h == 1 && j > 0) {              // held first half goes in place now: every reader of the old operand is done
+                            umma::tmem_st16(a_addr, hold[t]);
+                            umma::tmem_wait_st();
+                            warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
+                        }
+                        umma::tmem_wait_ld();
+                        warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
+                        uint32_t pk_[16];
+                        uint32_t* p = (h == 0) ? hold[t] : pk_;
+                        if (FIRST) {
+                            const uint32_t w7s = sbase + b3::kOffConst + 4u * (uint32_t)(384 + col0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float4 w;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(w7s + 16u * i));
+                                p[2 * i] = umma::pack_bf16(fmaf(dsg[t], w.x, __uint_as_float(v[4 * i])), fmaf(dsg[t], w.y, __uint_as_float(v[4 * i + 1])));
+                                p[2 * i + 1] = umma::pack_bf16(fmaf(dsg[t], w.z, __uint_as_float(v[4 * i + 2])), fmaf(dsg[t], w.w, __uint_as_float(v[4 * i + 3])));
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                p[i] = umma::pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & keep_mask(mb << i);
+                        }
+                        if (h == 1 && j > 0) {
+                            umma::tmem_st16(a_addr + 64, pk_);
+                            umma::tmem_wait_st();
+                            warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
+                        }
+                        if (st) store_dz(t ? dz_row1 : dz_row0, j * 256 + col0, p);     // rows past `total` carry zeros
                     }
-                    umma::tmem_wait_ld();
-                    warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
-                    uint32_t p[16];
-                    finish(v, first, dsg[t], mb, col0, p);
-                    if (j > 0) {
-                        umma::tmem_st16(a_addr + 64, p);
-                        umma::tmem_wait_st();
-                        warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
-                    }
-                    if (st) store_dz(row, j * 256 + col0, p);     // rows past `total` carry zeros (their dsigma / drgb are zero)
                 }
-            }
+            };
+            chain_step(std::true_type{}, 6);
+#pragma unroll 1
+            for (int j = 5; j >= 0; --j) chain_step(std::false_type{}, j);
         }
     }
     umma::tc_fence_before();
