@@ -69,23 +69,28 @@ struct Job {
 __constant__ Job c_jobs[10] = {
     // dz0 and dz4 halves x PE(x): dW(mlp.0)[:, 0:60] and dW(feature_fn.0)[:, 256:316], and both layers' biases
     {4, {{SRC_DZ, 0, 0, 0, 60, 0, 1}, {SRC_DZ, 128, 0, 128, 60, 0, 1}, {SRC_DZ, 1024, 4, 0, 316, 256, 1}, {SRC_DZ, 1152, 4, 128, 316, 256, 1}},
-     0, SRC_ACTS, 0, PE_X, 60, OUT_NORMAL, 0, 17},
+     0, SRC_ACTS, 0, PE_X, 60, OUT_NORMAL, 0, 23},
     {2, {{SRC_DZ, 256, 1, 0, 256, 0, 1}, {SRC_DZ, 384, 1, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 0, PE_NONE, 0, OUT_NORMAL, 0, 17},      // mlp.2
     {2, {{SRC_DZ, 512, 2, 0, 256, 0, 1}, {SRC_DZ, 640, 2, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 256, PE_NONE, 0, OUT_NORMAL, 0, 17},    // mlp.4
     {2, {{SRC_DZ, 768, 3, 0, 256, 0, 1}, {SRC_DZ, 896, 3, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 512, PE_NONE, 0, OUT_NORMAL, 0, 17},    // mlp.6
-    {2, {{SRC_DZ, 1024, 4, 0, 316, 0, 0}, {SRC_DZ, 1152, 4, 128, 316, 0, 0}, NB, NB}, 16, SRC_ACTS, 768, PE_NONE, 0, OUT_NORMAL, 0, 17},  // feature_fn.0 (h3 part)
-    {2, {{SRC_DZ, 1280, 5, 0, 256, 0, 1}, {SRC_DZ, 1408, 5, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1024, PE_NONE, 0, OUT_NORMAL, 0, 17}, // feature_fn.2
-    {2, {{SRC_DZ, 1536, 6, 0, 256, 0, 1}, {SRC_DZ, 1664, 6, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1280, PE_NONE, 0, OUT_NORMAL, 0, 17}, // feature_fn.4
-    {1, {{SRC_DZ, 1792, 8, 0, 280, 256, 1}, NB, NB, NB}, 16, SRC_ACTS, 1536, PE_DIR, 24, OUT_NORMAL, 0, 13},                             // rgb_fn.0: [feat | PE(dir)]
-    {2, {{SRC_ACTS, 1536, 7, 0, 256, 0, 0}, {SRC_ACTS, 1664, 7, 128, 256, 0, 0}, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_DENSITY, 0, 9},  // density_fn.0: feat^T . heads
-    {1, {{SRC_ACTS, 1792, 9, 0, 128, 0, 0}, NB, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_RGB, 1, 5},                                    // rgb_fn.2: r^T . heads (+ head biases)
+    {2, {{SRC_DZ, 1024, 4, 0, 316, 0, 0}, {SRC_DZ, 1152, 4, 128, 316, 0, 0}, NB, NB}, 16, SRC_ACTS, 768, PE_NONE, 0, OUT_NORMAL, 0, 16},  // feature_fn.0 (h3 part)
+    {2, {{SRC_DZ, 1280, 5, 0, 256, 0, 1}, {SRC_DZ, 1408, 5, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1024, PE_NONE, 0, OUT_NORMAL, 0, 16}, // feature_fn.2
+    {2, {{SRC_DZ, 1536, 6, 0, 256, 0, 1}, {SRC_DZ, 1664, 6, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1280, PE_NONE, 0, OUT_NORMAL, 0, 16}, // feature_fn.4
+    {1, {{SRC_DZ, 1792, 8, 0, 280, 256, 1}, NB, NB, NB}, 16, SRC_ACTS, 1536, PE_DIR, 24, OUT_NORMAL, 0, 10},                             // rgb_fn.0: [feat | PE(dir)]
+    {2, {{SRC_ACTS, 1536, 7, 0, 256, 0, 0}, {SRC_ACTS, 1664, 7, 128, 256, 0, 0}, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_DENSITY, 0, 10},  // density_fn.0: feat^T . heads
+    {1, {{SRC_ACTS, 1792, 9, 0, 128, 0, 0}, NB, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_RGB, 1, 6},                                    // rgb_fn.2: r^T . heads (+ head biases)
 };
 #undef NB
 constexpr int kNumJobs = 10;
-constexpr int kGridCtas = 7 * 17 + 13 + 9 + 5;     // 146
+constexpr int kGridCtas = 23 + 3 * 17 + 3 * 16 + 10 + 10 + 6;     // 148: CTA shares follow the measured per-tile cost of each job
+                                                                 // (tools/profile_wgrad.py: the PE(x) job recomputes 60 sin/cos per row and is
+                                                                 // issue-bound, the 256-wide jobs are HBM-bound), not its bytes
 }  // namespace wg
 
 struct Grads { float* p[20]; };
+
+// diagnostic: per-CTA (elapsed clocks, clocks until the last MMA completed) of the most recent launch (tools/profile_wgrad.py)
+__device__ long long g_wgrad_cycles[2 * 160];
 
 __global__ void __launch_bounds__(wg::kThreads, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __restrict__ dz, const float* __restrict__ o_rays,
@@ -104,6 +109,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t num_tiles = (total + 127) / 128;
+    const long long t_start = clock64();
 
     // which job, and which share of its tiles, this CTA owns
     int job_idx = 0, first = blockIdx.x;
@@ -319,6 +325,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
         // ---- epilogue: D_i[m = lane (row of block i), n] -> atomics into dW (skipped by CTAs that had no tile)
         umma::mbar_wait(done, 0);
         umma::tc_fence_after();
+        if (tid == 128) g_wgrad_cycles[2 * blockIdx.x + 1] = clock64() - t_start;
         if (first < num_tiles) {
             const int m = (warp & 3) * 32 + lane;
             const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -362,12 +369,17 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
     }
     umma::tc_fence_before();
     __syncthreads();
+    if (tid == 0) g_wgrad_cycles[2 * blockIdx.x] = clock64() - t_start;
     if (warp == 3) umma::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace nerf
 
 using namespace nerf;
+
+extern "C" int nerf_debug_wgrad_cycles(long long* host_out320) {
+    return cudaMemcpyFromSymbol(host_out320, g_wgrad_cycles, sizeof(long long) * 320) == cudaSuccess ? 0 : NERF_E_CUDA;
+}
 
 extern "C" int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
                              float* const* grads20_host, void* stream) {
