@@ -61,8 +61,12 @@ constexpr uint32_t kDensityStageOffset = make_merged_table().s[31].offset;     /
 // 32 accumulator columns (registers) -> + bias, (ReLU), 16 registers of bf16 pairs
 // RELU is a template parameter (a run-time flag makes nvcc convert both ways and select) and the bias comes through a
 // shared-space address (LDS.128, not a generic load): the 16 epilogue warps are instruction-issue bound.
-template <bool RELU>
-__device__ __forceinline__ void pack32(const uint32_t (&v)[32], uint32_t bias_saddr, uint32_t* p) {
+// `signs` (training form): one funnel shift per element collects the SIGN bits of the biased pre-activations - even elements
+// (low bf16 halves) into bits 15..0, odd elements into bits 31..16, pair j at bit 15-j / 31-j - i.e. the complement of the
+// ReLU mask, which the dgrad kernel applies as p & ~mask.
+template <bool RELU, bool SIGNS>
+__device__ __forceinline__ uint32_t pack32(const uint32_t (&v)[32], uint32_t bias_saddr, uint32_t* p) {
+    uint32_t s_lo = 0u, s_hi = 0u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         // 4 accumulators + 4 biases as two packed fp32 pairs (add.rn.f32x2: one instruction per pair on sm_100)
@@ -75,9 +79,16 @@ __device__ __forceinline__ void pack32(const uint32_t (&v)[32], uint32_t bias_sa
         float x0, x1, x2, x3;
         asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x01));
         asm("mov.b64 {%0, %1}, %2;" : "=f"(x2), "=f"(x3) : "l"(x23));
+        if (SIGNS) {
+            s_lo = __funnelshift_l(__float_as_uint(x0), s_lo, 1);
+            s_hi = __funnelshift_l(__float_as_uint(x1), s_hi, 1);
+            s_lo = __funnelshift_l(__float_as_uint(x2), s_lo, 1);
+            s_hi = __funnelshift_l(__float_as_uint(x3), s_hi, 1);
+        }
         p[2 * j + 0] = RELU ? umma::pack_bf16_relu(x0, x1) : umma::pack_bf16(x0, x1);
         p[2 * j + 1] = RELU ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
     }
+    return (s_hi << 16) | s_lo;
 }
 
 // Row `r` of a [128 x 64] bf16 K-major 128B-swizzled PE tile, four frequencies (12 registers = three 16-byte chunks) at a
@@ -135,28 +146,20 @@ __device__ __forceinline__ float dot_bf16x32(const uint32_t (&p)[16], const floa
     return acc;
 }
 
-// training, 32 features of one row: bf16 activations (four 16-byte chunks, tiled chunk-major) + one 32-bit word of ReLU
-// sign bits for the dgrad kernel.  `act_row` / `mask_row` point at this row's feature 0 / group 0; word layout (two-tile
-// kernels only): packed pair j = features (2j, 2j+1) of the group -> bit 15-j / bit 31-j.  The bits are collected with two
-// funnel shifts per pair: h + 0x7FFF carries into bit 15 exactly when the (non-negative) bf16 h is non-zero.
+// training, 32 features of one row: bf16 activations (four 16-byte chunks, tiled chunk-major) + the 32-bit word of sign bits
+// pack32 collected (two-tile kernels only; pair j = features (2j, 2j+1) of the group -> bit 15-j / 31-j, 1 = pre-activation
+// negative = ReLU inactive).  `act_row` / `mask_row` point at this row's feature 0 / group 0.
 __device__ __forceinline__ void save_act32(__nv_bfloat16* __restrict__ act_row, uint32_t* __restrict__ mask_row, int feature,
-                                           const uint32_t (&p)[16]) {
+                                           const uint32_t (&p)[16], uint32_t signs) {
     uint4* chunk = (uint4*)(act_row + (size_t)(feature >> 3) * 1024);
 #pragma unroll
     for (int j = 0; j < 4; ++j) chunk[j * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-    uint32_t mlo = 0u, mhi = 0u;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const uint32_t t = p[j] + 0x7FFF7FFFu;
-        mhi = __funnelshift_l(t, mhi, 1);
-        mlo = __funnelshift_l(t << 16, mlo, 1);
-    }
-    mask_row[(size_t)(feature >> 5) * 128] = (mhi << 16) | mlo;
+    mask_row[(size_t)(feature >> 5) * 128] = signs;
 }
 
 // dbg counters (PROFILE), per CTA x 16: 0 MMA warp total, 1 wait weights, 2 wait dfree, 3 wait alo/ahi, 4 wait PE,
 // 5 producer wait empty, 6 epilogue X total, 7 epilogue X wait dfull, 8 pairs; dbg[148*16 ...] = CTA 0's wait detail
-template <bool PROFILE>
+template <bool PROFILE, bool TRAIN>
 __global__ void __launch_bounds__(t3::kThreads, 1)
 mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_rays, const float* __restrict__ d_rays,
                const float* __restrict__ ts, const float* __restrict__ samples, int64_t total, int S,
@@ -324,7 +327,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
 
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int64_t row0 = pair * 2 * t3::kTileM + r;          // this thread's row in tile X (tile Y: + 128)
-            const bool save0 = (act_out != nullptr), save1 = (act_out != nullptr) && (pair * 2 + 1 < num_tiles);
+            const bool save0 = TRAIN, save1 = TRAIN && (pair * 2 + 1 < num_tiles);
             // this thread's rows in the tiled chunk-major training tensors (pack_layout.cuh): feature 0 / sign-word group 0
             __nv_bfloat16* const act_row0 = act_out + pk::tiled_offset(row0, 0, pk::kActChunks);
             __nv_bfloat16* const act_row1 = act_row0 + (size_t)pk::kActChunks * 1024;
@@ -345,9 +348,9 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     umma::tmem_ld32(d_addr, v);
                     umma::tmem_wait_ld();
                     warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
-                    pack32<!LAST>(v, bias_s, hold[t]);
+                    const uint32_t sg0 = pack32<!LAST, TRAIN>(v, bias_s, hold[t]);
                     if (PROFILE && t == 0) { asm volatile("" ::"r"(hold[0][0]), "r"(hold[0][15])); tp[3] += clock64() - t_h0; }
-                    if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, layer * 256 + cq * 32, hold[t]);
+                    if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, layer * 256 + cq * 32, hold[t], sg0);
                     if (LAST) sig_part[t] = dot_bf16x32(hold[t], sW7 + cq * 32, sig_part[t]);
                 }
 #pragma unroll
@@ -366,12 +369,12 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
                     if (PROFILE && t == 0) { asm volatile("" ::"r"(v[31])); tp[1] += clock64() - t_h1; }
                     uint32_t p[16];
-                    pack32<!LAST>(v, bias_s + 512u, p);
+                    const uint32_t sg1 = pack32<!LAST, TRAIN>(v, bias_s + 512u, p);
                     umma::tmem_st16(a_addr + 64, p);                  // features 128..255 -> A columns 64..127
                     umma::tmem_wait_st();
                     warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
                     if (PROFILE && t == 0) tp[2] += clock64() - t_h1;
-                    if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, layer * 256 + 128 + cq * 32, p);
+                    if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, layer * 256 + 128 + cq * 32, p, sg1);
                     if (LAST) sig_part[t] = dot_bf16x32(p, sW7 + 128 + cq * 32, sig_part[t]);
                 }
             };
@@ -392,11 +395,11 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 umma::tmem_ld32(d_addr, v);
                 umma::tmem_wait_ld();
                 warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
-                pack32<true>(v, sbase + t3::kOffBias + 4u * (uint32_t)(pk::kBiasR0 + cq * 32), p);
+                const uint32_t sgr = pack32<true, TRAIN>(v, sbase + t3::kOffBias + 4u * (uint32_t)(pk::kBiasR0 + cq * 32), p);
                 umma::tmem_st16(a_addr, p);                           // r features 0..127 -> A columns 0..63
                 umma::tmem_wait_st();
                 warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
-                if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, 1792 + cq * 32, p);
+                if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, 1792 + cq * 32, p, sgr);
             }
             // ---- rgb_fn.2: columns 0..2 -> sigmoid(. + b) (nerf_model.py:358-359); sigma = relu(feat . w7 + b7)
 #pragma unroll
@@ -432,9 +435,11 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
                    int64_t total, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream, long long* dbg) {
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e != cudaSuccess) { set_error("nerf_mlp_forward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
         attr_set = true;
     }
@@ -445,12 +450,16 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
         const char* e = getenv("NERF_TC_MAX_CTAS");
         if (e && atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
     }
+    const uint8_t* pw = (const uint8_t*)packed;
+    __nv_bfloat16* ao = (__nv_bfloat16*)act_out;
+    unsigned long long* mo = (unsigned long long*)mask_out;
+    cudaStream_t st = (cudaStream_t)stream;
     if (dbg)
-        mlp_tc3_kernel<true><<<grid, t3::kThreads, t3::kSmemBytes, (cudaStream_t)stream>>>(
-            (const uint8_t*)packed, o, d, ts, samples, total, S, sigma, rgb, (__nv_bfloat16*)act_out, (unsigned long long*)mask_out, dbg);
+        mlp_tc3_kernel<true, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, dbg);
+    else if (act_out)                                 // training form: also stores activations + sign words
+        mlp_tc3_kernel<false, true><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, ao, mo, nullptr);
     else
-        mlp_tc3_kernel<false><<<grid, t3::kThreads, t3::kSmemBytes, (cudaStream_t)stream>>>(
-            (const uint8_t*)packed, o, d, ts, samples, total, S, sigma, rgb, (__nv_bfloat16*)act_out, (unsigned long long*)mask_out, nullptr);
+        mlp_tc3_kernel<false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, nullptr);
     return check_launch("nerf_mlp_forward_tc");
 }
 

@@ -7,18 +7,20 @@
 //     dz5  = (dz6 . W6) * [h5 > 0]                             steps 2,3   (A = previous dz in TMEM, TS; B = W^T stages)
 //     dz4 .. dz0 likewise through feature_fn.2, feature_fn.0 (h columns), mlp.6, mlp.4, mlp.2     steps 4..13
 //   every dz is written to global (bf16, tiled chunk-major, pack_layout.cuh) for wgrad, plus the 16-wide heads block.
-// ReLU masks are the 32-bit sign words mlp_tc3.cu wrote per (row, 32-feature group): packed pair j -> bits 15-j / 31-j;
-// they are applied to the PACKED bf16 pairs (shift + PRMT sign replication + AND: three instructions per pair).
+// ReLU masks are the 32-bit SIGN words mlp_tc3.cu wrote per (row, 32-feature group): packed pair j -> bits 15-j / 31-j,
+// 1 = pre-activation negative; they are applied to the PACKED bf16 pairs (shift + PRMT sign replication + AND-NOT: three
+// instructions per pair).
 // mlp.0's dgrad (d PE) is not needed: the inputs carry no gradient.
 #include <type_traits>
 #include "mlp_tc3_common.cuh"
 
 namespace nerf {
 
-// 0xFFFF fields for the bf16 halves whose sign-word bits (bit 15 -> low half, bit 31 -> high half of `s`) are set:
+// 0xFFFF fields for the bf16 halves whose sign-word bits (bit 15 -> low half, bit 31 -> high half of `s`) are set
+// (= the halves to ZERO):
 // prmt in its generic mode replicates the msb of the selected byte when the selector nibble has bit 3 set
 // (__byte_perm only forwards three selector bits per nibble).
-__device__ __forceinline__ uint32_t keep_mask(uint32_t s) {
+__device__ __forceinline__ uint32_t drop_mask(uint32_t s) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(r) : "r"(s));
     return r;
@@ -128,7 +130,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                 for (int c = 0; c < 16; ++c) {                    // chunk c = features 8c .. 8c+7 of r (rgb_fn.0's ReLU output)
                     // sign bits written by the forward kernel: 32-bit half (c >> 2) & 1 of block 28 + (c >> 3)
                     // sign word of r's 32-feature group 56 + (c >> 2) (r = activations 1792..1919); this chunk = pairs 4(c&3)..+3
-                    uint32_t mb = 0u;
+                    uint32_t mb = 0xFFFFFFFFu;
                     if (store) mb = masks32[((row >> 7) * (2 * pk::kMaskWords) + 56 + (c >> 2)) * 128 + (row & 127)];
                     mb <<= (c & 3) * 4;
                     uint32_t v[4];
@@ -137,7 +139,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                         const int k = c * 8 + 2 * j;
                         const float a = g0 * W9[k] + g1 * W9[128 + k] + g2 * W9[256 + k];            // nerf_model.py:358 backward
                         const float b = g0 * W9[k + 1] + g1 * W9[128 + k + 1] + g2 * W9[256 + k + 1];
-                        v[j] = umma::pack_bf16(a, b) & keep_mask(mb << j);
+                        v[j] = umma::pack_bf16(a, b) & ~drop_mask(mb << j);
                     }
                     const uint4 q4 = make_uint4(v[0], v[1], v[2], v[3]);
                     const int kb = c >> 3, cc = c & 7;            // K block, chunk inside its 128-byte row
@@ -198,7 +200,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                     for (int t = 0; t < 2; ++t) {
                         const bool st = (t == 0) || st1;
                         const int col0 = h * 128 + cq * 32;
-                        uint32_t mb = 0u;
+                        uint32_t mb = 0xFFFFFFFFu;
                         if (!FIRST && st) mb = __ldg((t ? mask_row1 : mask_row0) + (size_t)((j * 256 + col0) >> 5) * 128);
                         const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
                         const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(cq * 16);
@@ -226,7 +228,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                         } else {
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
-                                p[i] = umma::pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & keep_mask(mb << i);
+                                p[i] = umma::pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & ~drop_mask(mb << i);
                         }
                         if (h == 1 && j > 0) {
                             umma::tmem_st16(a_addr + 64, pk_);
