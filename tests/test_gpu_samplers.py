@@ -182,9 +182,9 @@ def test_mlp_fp32(golden, mods):
 
 def test_compositing_large_batch_kernel(mods):
     """nerf_composite switches to the thread-per-ray kernel (tiles staged through shared memory) from 32768 rays on: the
-    running sum and the weights are taken in the same order as in the warp-per-ray kernel, so a 40000-ray batch must match
-    its two halves bit for bit in the weights; the per-ray sums (colour, depth, opacity) are added in sample order instead
-    of lane-partials + tree and agree to a few ulp; the density statistics to rounding."""
+    running sum is taken in sample order there and by a 5-step shuffle scan in the warp-per-ray kernel, the per-ray sums in
+    sample order vs lane partials + tree: a 40000-ray batch must match its two halves to a few ulp (2e-6) in weights,
+    colour, depth and opacity, and the density statistics to rounding."""
     _, h, _ = mods
     N = 40000
     for S in (64, 192, 37):
@@ -195,8 +195,7 @@ def test_compositing_large_batch_kernel(mods):
         rgb = torch.rand(N, S, 3, device=DEV, generator=gen)
         full = h.composite(sg, rgb, ts)
         halves = [h.composite(sg[a:b].contiguous(), rgb[a:b].contiguous(), ts[a:b].contiguous()) for a, b in ((0, N // 2), (N // 2, N))]
-        assert torch.equal(full["weights"], torch.cat([x["weights"] for x in halves])), S
-        for key in ("rgb", "depth", "acc"):
+        for key in ("weights", "rgb", "depth", "acc"):
             torch.testing.assert_close(full[key], torch.cat([x[key] for x in halves]), atol=2e-6, rtol=2e-6)
         torch.testing.assert_close(full["stats"], halves[0]["stats"] + halves[1]["stats"], rtol=1e-5, atol=0)
         torch.testing.assert_close(full["norm"], torch.sqrt(full["stats"][0]), rtol=1e-6, atol=0)
