@@ -363,10 +363,9 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     umma::tmem_ld32(d_addr, v);
                     umma::tmem_st16(a_addr, hold[t]);                 // features 0..127 -> A columns 0..63
                     umma::tmem_wait_st();
-                    warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
                     if (PROFILE && t == 0) tp[0] += clock64() - t_h1;
                     umma::tmem_wait_ld();
-                    warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
+                    warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);       // = accumulator free AND K blocks 0,1 of the new operand written
                     if (PROFILE && t == 0) { asm volatile("" ::"r"(v[31])); tp[1] += clock64() - t_h1; }
                     uint32_t p[16];
                     const uint32_t sg1 = pack32<!LAST, TRAIN>(v, bias_s + 512u, p);

@@ -118,8 +118,9 @@ struct MmaTile {
         ++n_step;
     }
     __device__ __forceinline__ void pass_turn() { umma::mbar_arrive_u32(bar(t3::kBarTurn + T)); }   // leader lane, after its MMAs
-    // the same epilogue task signals alo BEFORE dfree: after begin_step() the first-half operand is known to be written
-    __device__ __forceinline__ void lo_implied() { ++n_alo; }
+    // a hidden layer's second-half task stores K blocks 0,1 of the new operand (and waits for the store) BEFORE it signals
+    // dfree: after begin_step() they are known to be written; alo is only signalled by rgb_fn.0's task (for rgb_fn.2)
+    __device__ __forceinline__ void lo_implied() {}
     __device__ __forceinline__ void need_lo() { wait(bar(t3::kBarALo + T), n_alo & 1u, 3); ++n_alo; }
     __device__ __forceinline__ void need_hi() { wait(bar(t3::kBarAHi + T), n_ahi & 1u, 3); ++n_ahi; }
     // ---- unguarded pieces (callers hold the leader lane)

@@ -209,8 +209,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                         umma::tmem_ld32(d_addr, v);
                         if (h == 1 && j > 0) {              // held first half goes in place now: every reader of the old operand is done
                             umma::tmem_st16(a_addr, hold[t]);
-                            umma::tmem_wait_st();
-                            warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
+                            umma::tmem_wait_st();                   // signalled together with dfree below
                         }
                         umma::tmem_wait_ld();
                         warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
