@@ -410,7 +410,9 @@ namespace nerf {
 int launch_mlp_tc2(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
                    int64_t total, int S, float* sigma, float* rgb, void* stream, long long* dbg);
 int launch_mlp_tc3(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
-                   int64_t total, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream, long long* dbg);
+                   int64_t total, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream, long long* dbg,
+                   const CompositeOutputs* comp);
+bool mlp_tc3_can_composite(int S, int* group_rays, int* group_tiles);
 }
 
 using namespace nerf;
@@ -449,7 +451,7 @@ static int launch_mlp_tc(const void* packed, const float* o, const float* d, con
     const int64_t total = N * S;
     NERF_REQUIRE(!act_out || ((uintptr_t)act_out & 15) == 0, "nerf_mlp_forward_tc: act_out must be 16-byte aligned");
     if (use_pair_kernel() && !act_out) return launch_mlp_tc2(packed, o, d, ts, samples, total, S, sigma, rgb, stream, dbg);
-    if (!use_one_tile_kernel()) return launch_mlp_tc3(packed, o, d, ts, samples, total, S, sigma, rgb, act_out, mask_out, stream, dbg);
+    if (!use_one_tile_kernel()) return launch_mlp_tc3(packed, o, d, ts, samples, total, S, sigma, rgb, act_out, mask_out, stream, dbg, nullptr);
     const int64_t tiles = (total + tc::kTileM - 1) / tc::kTileM;
     int grid = (int)(tiles < num_sms() ? tiles : num_sms());
     if (dbg) {                                        // diagnostic runs only: NERF_TC_MAX_CTAS limits the grid
@@ -489,4 +491,31 @@ extern "C" int nerf_mlp_forward_tc_train(const void* packed, const float* o, con
                                          int64_t N, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream) {
     NERF_REQUIRE(N == 0 || (act_out && mask_out), "nerf_mlp_forward_tc_train: act_out / mask_out is NULL");
     return launch_mlp_tc(packed, o, d, ts, nullptr, N, S, sigma, rgb, stream, nullptr, act_out, mask_out);
+}
+
+// ---- K8 + K2: the same network with alpha compositing (nerf_helpers.py:58-104) done inside the kernel by a dedicated warp
+// (mlp_tc3.cu, COMP form).  sigma / rgb may be NULL (render: the per-sample outputs never leave the SM); act_out / mask_out
+// non-NULL selects the training form, which needs sigma and rgb as well (the compositing backward reads them).
+// (The diagnostic one-tile / CTA-pair schedules selected by NERF_TC_ONE_TILE / NERF_TC_PAIR have no fused form: report
+// "unsupported" so that callers take the two-launch path and the matching dgrad kernel sees its own mask format.)
+extern "C" int nerf_mlp_composite_tc_supported(int S) {
+    return (mlp_tc3_can_composite(S, nullptr, nullptr) && !use_one_tile_kernel() && !use_pair_kernel()) ? 1 : 0;
+}
+
+extern "C" int nerf_mlp_composite_tc(const void* packed, const float* o, const float* d, const float* ts, int64_t N, int S,
+                                     float* sigma, float* rgb, void* act_out, void* mask_out,
+                                     float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream) {
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_composite_tc: bad size N=%lld S=%d", (long long)N, S);
+    if (N == 0) return 0;
+    NERF_REQUIRE(packed && o && d && ts && ray_rgb, "nerf_mlp_composite_tc: null pointer");
+    NERF_REQUIRE((sigma == nullptr) == (rgb == nullptr), "nerf_mlp_composite_tc: sigma and rgb go together");
+    NERF_REQUIRE((act_out == nullptr) == (mask_out == nullptr), "nerf_mlp_composite_tc: act_out and mask_out go together");
+    NERF_REQUIRE(!act_out || sigma, "nerf_mlp_composite_tc: the training form also needs sigma / rgb");
+    NERF_REQUIRE(((uintptr_t)packed & 127) == 0, "nerf_mlp_composite_tc: packed buffer must be 128-byte aligned");
+    NERF_REQUIRE(!act_out || ((uintptr_t)act_out & 15) == 0, "nerf_mlp_composite_tc: act_out must be 16-byte aligned");
+    NERF_REQUIRE(nerf_mlp_composite_tc_supported(S),
+                 "nerf_mlp_composite_tc: S = %d is not supported (needs S %% 32 == 0 and a ray group of at most 6 tiles); "
+                 "use nerf_mlp_forward_tc + nerf_composite", S);
+    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4};
+    return launch_mlp_tc3(packed, o, d, ts, nullptr, N * S, S, sigma, rgb, act_out, mask_out, stream, nullptr, &comp);
 }

@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <type_traits>
 #include "mlp_tc3_common.cuh"
+#include "composite_scan.cuh"
 
 namespace nerf {
 
@@ -159,12 +160,94 @@ __device__ __forceinline__ void save_act32(__nv_bfloat16* __restrict__ act_row, 
 
 // dbg counters (PROFILE), per CTA x 16: 0 MMA warp total, 1 wait weights, 2 wait dfree, 3 wait alo/ahi, 4 wait PE,
 // 5 producer wait empty, 6 epilogue X total, 7 epilogue X wait dfull, 8 pairs; dbg[148*16 ...] = CTA 0's wait detail
-template <bool PROFILE, bool TRAIN>
+// COMP form (fused compositing, nerf_helpers.py:58-104 inside the MLP kernel): every CTA owns a CONTIGUOUS range of ray
+// groups - a group is the smallest run of whole rays that is also a whole number of 128-sample tiles (S = 64: 2 rays = 1
+// tile, S = 192: 2 rays = 3 tiles) - so every ray's samples are produced by one CTA.  The last step's epilogue warps put
+// (sigma, r, g, b) of each sample into a shared-memory ring of tiles instead of (render) / as well as (training) global
+// memory, and the four PE warps - which run a pair ahead of the MMAs and have issue slots to spare - turn finished groups into
+// weights, ray colour, depth and opacity between two encodings, with the same warp-scan code as the stand-alone compositing
+// kernel (composite_scan.cuh): one ray per warp, lane = sample, overlapped with the MMAs / epilogues of the following tiles.
+// (A dedicated fifth warpgroup does not fit the register file: 896 threads launch with 72 registers, and the pool then
+// leaves the MMA-issuing warps 48-56 registers - their issue loop starts reloading descriptors from local memory.)
+struct FusedComposite {
+    float* weights;      // [N,S] or null
+    float* ray_rgb;      // [N,3]
+    float* depth;        // [N] or null
+    float* acc;          // [N] or null
+    float* stats;        // [4] or null: sum sigma^2, count sigma != 0, sqrt(sum sigma^2) (published by the last CTA), ticket
+    int group_rays, group_tiles;
+    int64_t num_groups, N;
+};
+
+// COMP form, run by each of the four PE warps: composite every ray group whose local tiles lie below `limit`, starting at
+// local tile `next_lt` (advanced; `last` = number of local tiles that exist).  A group's rays are dealt round-robin to the warps; all four warps wait for the group's
+// tiles and release them.  Same arithmetic, in the same order, as composite_kernel<1> (samplers.cu).
+__device__ __forceinline__ void composite_groups(const FusedComposite& fc, const float* __restrict__ ts, int S, int64_t g0, uint8_t* smem,
+                                              uint32_t bars, uint32_t& next_lt, uint32_t limit, uint32_t last, int w, int lane, float* stat) {
+    const float4* sOut = (const float4*)(smem + t3::kOffOut);
+    const uint32_t TG = (uint32_t)fc.group_tiles;
+    while (next_lt + TG <= limit) {
+        const uint32_t lt0 = next_lt;
+        for (uint32_t j = 0; j < TG; ++j) {
+            const uint32_t lt = lt0 + j;
+            if (lt < last) umma::mbar_wait_u32(bars + 8u * (t3::kBarOutFull + (lt & (t3::kOutSlots - 1))), (lt >> 3) & 1u);
+        }
+        const int64_t n_first = (g0 + lt0 / TG) * fc.group_rays;
+        for (int j = 0; j < fc.group_rays; ++j) {
+            const int64_t n = n_first + j;
+            if (((int)n & 3) != w || n >= fc.N) continue;                               // ray n -> warp n % 4
+            const float* tp = ts + n * S;
+            float* wp = fc.weights ? fc.weights + n * S : nullptr;
+            const uint32_t grow0 = lt0 * t3::kTileM + (uint32_t)(j * S);                // CTA-local row of the ray's first sample
+            float running = 0.f;       // sum_{j<i} -sigma_j delta_j, nerf_helpers.py:86-89
+            float cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f, st_sq = 0.f, st_nz = 0.f;
+            float t_n = __ldg(tp + lane);                                                // S is a multiple of 32
+            for (int base = 0; base < S; base += kWarp) {
+                const int i = base + lane;
+                const float t = t_n;
+                if (base + kWarp < S) t_n = __ldg(tp + base + kWarp + lane);             // next chunk's depths in flight
+                const uint32_t grow = grow0 + (uint32_t)i;
+                const float4 v = sOut[((grow >> 7) & (t3::kOutSlots - 1)) * t3::kTileM + (grow & 127u)];
+                const float s = v.x;
+                float tn = __shfl_down_sync(kFull, t, 1);
+                const float t_first_next = __shfl_sync(kFull, t_n, 0);
+                if (lane == 31 && i + 1 < S) tn = t_first_next;
+                const float dl = (i == S - 1) ? 1e10f : __fsub_rn(tn, t);               // nerf_helpers.py:71-72
+                const float x = __fmul_rn(__fmul_rn(-1.0f, s), dl);                      // -1 * density * deltas
+                const float excl = chunk_exclusive_scan_tree(x, running, lane);
+                const float trans = expf(excl);                                          // nerf_helpers.py:89
+                const float wgt = __fmul_rn(__fsub_rn(1.0f, expf(x)), trans);            // nerf_helpers.py:90
+                if (wp) wp[i] = wgt;
+                cr = fmaf(wgt, v.y, cr); cg = fmaf(wgt, v.z, cg); cb = fmaf(wgt, v.w, cb);   // nerf_helpers.py:103
+                dsum = fmaf(wgt, t, dsum); asum += wgt;
+                st_sq = fmaf(s, s, st_sq); st_nz += (s != 0.f) ? 1.f : 0.f;
+            }
+            cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+            dsum = warp_sum(dsum); asum = warp_sum(asum);
+            st_sq = warp_sum(st_sq); st_nz = warp_sum(st_nz);
+            if (lane == 0) {
+                fc.ray_rgb[n * 3 + 0] = cr; fc.ray_rgb[n * 3 + 1] = cg; fc.ray_rgb[n * 3 + 2] = cb;
+                if (fc.depth) fc.depth[n] = dsum;
+                if (fc.acc) fc.acc[n] = asum;
+                stat[0] += st_sq; stat[1] += st_nz;
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            for (uint32_t j = 0; j < TG; ++j) {
+                const uint32_t lt = lt0 + j;
+                if (lt < last) umma::mbar_arrive_u32(bars + 8u * (t3::kBarOutEmpty + (lt & (t3::kOutSlots - 1))));
+            }
+        next_lt = lt0 + TG;
+    }
+}
+
+template <bool PROFILE, bool TRAIN, bool COMP>
 __global__ void __launch_bounds__(t3::kThreads, 1)
 mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_rays, const float* __restrict__ d_rays,
                const float* __restrict__ ts, const float* __restrict__ samples, int64_t total, int S,
                float* __restrict__ sigma_out, float* __restrict__ rgb_out, __nv_bfloat16* __restrict__ act_out,
-               unsigned long long* __restrict__ mask_out, long long* __restrict__ dbg) {
+               unsigned long long* __restrict__ mask_out, long long* __restrict__ dbg, const FusedComposite fc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = umma::smem_u32(smem);
@@ -172,14 +255,34 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
     float* sBias = (float*)(smem + t3::kOffBias);
     float* sW7 = (float*)(smem + t3::kOffW7);
     float* sSig = (float*)(smem + t3::kOffSig);
+    float* sStat = (float*)(smem + t3::kOffStat);
     uint32_t* tmem_holder = (uint32_t*)(smem + t3::kOffTmemHolder);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t num_tiles = (total + t3::kTileM - 1) / t3::kTileM;
-    const int64_t num_pairs = (num_tiles + 1) / 2;
+    // This CTA's tile pairs: pair k = tiles (tile0 + k * tile_stride, + 1), k < n_local; tiles >= tile_end
+    // are not this CTA's.  Round-robin over all pairs, or (COMP) the contiguous tiles of ray groups [g0, g1).
+    // (tile indices are 32-bit: 2^32 tiles would be 5 x 10^11 samples)
+    uint32_t tile0, tile_stride, tile_end, n_local;
+    int64_t g0 = 0;
+    if (COMP) {
+        g0 = fc.num_groups * blockIdx.x / gridDim.x;
+        const int64_t g1 = fc.num_groups * (blockIdx.x + 1) / gridDim.x;
+        tile0 = (uint32_t)(g0 * fc.group_tiles);
+        tile_end = (uint32_t)(g1 * fc.group_tiles < num_tiles ? g1 * fc.group_tiles : num_tiles);
+        tile_stride = 2;
+        n_local = tile_end > tile0 ? (tile_end - tile0 + 1u) / 2u : 0u;
+    } else {
+        const int64_t num_pairs = (num_tiles + 1) / 2;
+        tile0 = 2u * blockIdx.x;
+        tile_stride = 2u * gridDim.x;
+        tile_end = (uint32_t)num_tiles;
+        n_local = (uint32_t)((num_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    }
 
     if (tid == 0) {
         uint64_t* b = (uint64_t*)(smem + t3::kOffBars);
+        for (int i = 0; i < t3::kOutSlots; ++i) { umma::mbar_init(&b[t3::kBarOutFull + i], 4); umma::mbar_init(&b[t3::kBarOutEmpty + i], t3::kPEWarps); }
         for (int i = 0; i < t3::kSlots; ++i) { umma::mbar_init(&b[t3::kBarFull + i], 1); umma::mbar_init(&b[t3::kBarEmpty + i], 2); }
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&b[t3::kBarDFull + i], 1);
@@ -197,7 +300,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
     if (warp == 2) umma::tmem_alloc(tmem_holder, 512);
     {   // biases: resident for the whole kernel
         const float* gb = (const float*)(packed + pk::kLayout.bias_offset);
-        for (int i = tid; i < pk::kBiasFloats; i += t3::kThreads) sBias[i] = gb[i];
+        for (int i = tid; i < pk::kBiasFloats; i += (int)blockDim.x) sBias[i] = gb[i];
         // density_fn.0.weight as the packer rounded it to bf16: row 0 of the four [16 x 64] blocks (row 0 is not swizzled)
         if (tid < 256) {
             const __nv_bfloat16* w7 = (const __nv_bfloat16*)(packed + kDensityStageOffset + (tid >> 6) * pk::kStageBytesSmall);
@@ -219,7 +322,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             const uint32_t ring = sbase + t3::kOffRing;
             long long t_wait = 0;
             uint32_t cnt = 0;
-            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            for (uint32_t k = 0; k < n_local; ++k) {
                 for (int s = 0; s < kStages3; ++s, ++cnt) {
                     if ((cnt & 1u) != me) continue;
                     const uint32_t slot = cnt & (t3::kSlots - 1), ph = (cnt >> 3) & 1u;
@@ -243,32 +346,42 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 MmaTile<0, PROFILE> m;
                 m.init(bars, sbase + t3::kOffRing, tmem, elected);
                 if (PROFILE) m.detail = sbase + t3::kOffDetail;
-                m.run(sbase, num_pairs);
+                m.run(sbase, n_local);
                 __syncwarp();
                 if (PROFILE && blockIdx.x == 0) for (int i = lane; i < 64; i += 32) dbg[148 * 16 + i] = ((long long*)(smem + t3::kOffDetail))[i];
                 if (PROFILE && elected) {
                     dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
                     for (int i = 1; i < 5; ++i) dbg[blockIdx.x * 16 + i] = m.prof[i];
                     dbg[blockIdx.x * 16 + 9] = m.prof[0];
-                    dbg[blockIdx.x * 16 + 8] = (num_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
+                    dbg[blockIdx.x * 16 + 8] = n_local;
                 }
             } else {
                 MmaTile<1, PROFILE> m;
                 m.init(bars, sbase + t3::kOffRing, tmem, elected);
-                m.run(sbase, num_pairs);
+                m.run(sbase, n_local);
             }
         }
     } else if (warp >= 20) {
         // ------------------------------------------------------------------ PE producers (128 threads, thread = row)
         reg_dec<t3::kRegsPE>();
         const int r = (warp - 20) * 32 + lane;
-        uint32_t it = 0;
-        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
+        const uint32_t ntl = tile_end > tile0 ? (uint32_t)(tile_end - tile0) : 0u;      // COMP: this CTA's tiles
+        uint32_t comp_lt = 0;                                                            // COMP: first tile of the next group to composite
+        if (COMP && lane == 0) { sStat[2 * (warp - 20)] = 0.f; sStat[2 * (warp - 20) + 1] = 0.f; }
+        for (uint32_t it = 0; it <= n_local; ++it) {
+            const uint32_t tile_x = tile0 + it * tile_stride;
+            // COMP: groups whose tiles all belong to pairs <= it - 2 are complete (pair it - 1 is in flight); after the last
+            // pair, everything that is left
+            if (COMP)
+                composite_groups(fc, ts, S, g0, smem, bars, comp_lt,
+                                 it == n_local ? ntl + (uint32_t)fc.group_tiles - 1u : (it >= 2u ? 2u * (it - 1u) : 0u), ntl,
+                                 warp - 20, lane, sStat + 2 * (warp - 20));
+            if (it == n_local) break;
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
-                const int64_t row = (pair * 2 + t) * t3::kTileM + r;
+                const int64_t row = (int64_t)(tile_x + t) * t3::kTileM + r;
                 float x[3] = {0.f, 0.f, 0.f};
-                if (row < total) {
+                if (tile_x + t < tile_end && row < total) {
                     if (samples) {
 #pragma unroll
                         for (int k = 0; k < 3; ++k) x[k] = samples[row * 3 + k];
@@ -289,9 +402,9 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             }
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
-                const int64_t row = (pair * 2 + t) * t3::kTileM + r;
+                const int64_t row = (int64_t)(tile_x + t) * t3::kTileM + r;
                 float u[3] = {0.f, 0.f, 0.f};
-                if (row < total) {
+                if (tile_x + t < tile_end && row < total) {
                     const int64_t n = row / S;
                     const float dx = __ldg(d_rays + n * 3), dy = __ldg(d_rays + n * 3 + 1), dz = __ldg(d_rays + n * 3 + 2);
                     const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);                    // nerf_model.py:373
@@ -302,6 +415,19 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 umma::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive_u32(bars + 8u * (t3::kBarPedFull + t));
+            }
+        }
+        if (COMP) {
+            if (fc.stats && lane == 0) {
+                atomicAdd(fc.stats + 0, sStat[2 * (warp - 20)]);
+                atomicAdd(fc.stats + 1, sStat[2 * (warp - 20) + 1]);
+                // the last warp to arrive publishes the norm the reference logs (nerf_model.py:105,124): stats[2] = sqrt(stats[0])
+                __threadfence();
+                const unsigned ticket = atomicAdd((unsigned*)(fc.stats + 3), 1u);
+                if (ticket == gridDim.x * t3::kPEWarps - 1) {
+                    __threadfence();
+                    fc.stats[2] = sqrtf(atomicAdd(fc.stats + 0, 0.f));
+                }
             }
         }
     } else {
@@ -325,9 +451,10 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             ++nd[t];
         };
 
-        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-            const int64_t row0 = pair * 2 * t3::kTileM + r;          // this thread's row in tile X (tile Y: + 128)
-            const bool save0 = TRAIN, save1 = TRAIN && (pair * 2 + 1 < num_tiles);
+        for (uint32_t it = 0; it < n_local; ++it) {
+            const uint32_t tile_x = tile0 + it * tile_stride;
+            const int64_t row0 = (int64_t)tile_x * t3::kTileM + r;   // this thread's row in tile X (tile Y: + 128)
+            const bool save0 = TRAIN, save1 = TRAIN && (tile_x + 1 < tile_end);
             // this thread's rows in the tiled chunk-major training tensors (pack_layout.cuh): feature 0 / sign-word group 0
             __nv_bfloat16* const act_row0 = act_out + pk::tiled_offset(row0, 0, pk::kActChunks);
             __nv_bfloat16* const act_row1 = act_row0 + (size_t)pk::kActChunks * 1024;
@@ -413,7 +540,28 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     umma::tmem_wait_ld();
                 }
                 warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
-                if (cq == 0 && row < total) {
+                if (COMP) {
+                    const uint32_t lt = 2u * it + (uint32_t)t;                   // CTA-local tile index
+                    if (cq == 0 && tile_x + t < tile_end) {
+                        const uint32_t slot = lt & (t3::kOutSlots - 1);
+                        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row < total) {
+                            out.x = fmaxf(sg + sBias[pk::kBiasSigma], 0.f);
+                            out.y = 1.0f / (1.0f + __expf(-(__uint_as_float(v[0]) + sBias[pk::kBiasRgb + 0])));
+                            out.z = 1.0f / (1.0f + __expf(-(__uint_as_float(v[1]) + sBias[pk::kBiasRgb + 1])));
+                            out.w = 1.0f / (1.0f + __expf(-(__uint_as_float(v[2]) + sBias[pk::kBiasRgb + 2])));
+                            if (sigma_out) {                                         // training keeps them for the backward pass
+                                sigma_out[row] = out.x;
+                                rgb_out[row * 3 + 0] = out.y; rgb_out[row * 3 + 1] = out.z; rgb_out[row * 3 + 2] = out.w;
+                            }
+                        }
+                        // the slot's previous tile (kOutSlots tiles ago) has been composited
+                        umma::mbar_wait_u32(bars + 8u * (t3::kBarOutEmpty + slot), ((lt >> 3) & 1u) ^ 1u);
+                        ((float4*)(smem + t3::kOffOut))[slot * t3::kTileM + r] = out;
+                        __syncwarp();
+                        if (lane == 0) umma::mbar_arrive_u32(bars + 8u * (t3::kBarOutFull + slot));
+                    }
+                } else if (cq == 0 && row < total) {
                     sigma_out[row] = fmaxf(sg + sBias[pk::kBiasSigma], 0.f);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -430,35 +578,71 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
     if (warp == 2) umma::tmem_dealloc(tmem, 512);
 }
 
+// Fused compositing needs whole 32-sample chunks per ray and a ray group (whole rays = whole tiles) that fits the output ring
+bool mlp_tc3_can_composite(int S, int* group_rays, int* group_tiles) {
+    if (S <= 0 || S % 32 != 0) return false;
+    int g = 1;
+    while ((g * S) % t3::kTileM != 0) ++g;              // 128 / gcd(S, 128) <= 4
+    const int tg = g * S / t3::kTileM;
+    if (tg > t3::kOutSlots - 2) return false;
+    if (group_rays) *group_rays = g;
+    if (group_tiles) *group_tiles = tg;
+    return true;
+}
+
 int launch_mlp_tc3(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
-                   int64_t total, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream, long long* dbg) {
+                   int64_t total, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream, long long* dbg,
+                   const CompositeOutputs* comp) {
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e != cudaSuccess) { set_error("nerf_mlp_forward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
         attr_set = true;
     }
     const int64_t tiles = (total + t3::kTileM - 1) / t3::kTileM;
     const int64_t pairs = (tiles + 1) / 2;
+    const uint8_t* pw = (const uint8_t*)packed;
+    __nv_bfloat16* ao = (__nv_bfloat16*)act_out;
+    unsigned long long* mo = (unsigned long long*)mask_out;
+    cudaStream_t st = (cudaStream_t)stream;
+    FusedComposite fc{};
+    if (comp) {                                         // fused compositing: contiguous ray groups per CTA, 25 warps
+        if (!mlp_tc3_can_composite(S, &fc.group_rays, &fc.group_tiles) || !ts || samples || dbg) {
+            set_error("nerf_mlp_composite_tc: S = %d cannot be composited inside the kernel (needs S %% 32 == 0, rays + depths input)", S);
+            return NERF_E_ARG;
+        }
+        fc.weights = comp->weights; fc.ray_rgb = comp->ray_rgb; fc.depth = comp->depth; fc.acc = comp->acc; fc.stats = comp->stats;
+        fc.N = total / S;
+        fc.num_groups = (fc.N + fc.group_rays - 1) / fc.group_rays;
+        // at least two tiles per CTA where possible, so that both halves of a pair do useful work
+        int64_t want = (tiles + 1) / 2;
+        if (want > fc.num_groups) want = fc.num_groups;
+        const int grid = (int)(want < num_sms() ? want : num_sms());
+        if (act_out)
+            mlp_tc3_kernel<false, true, true><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, nullptr, total, S, sigma, rgb, ao, mo, nullptr, fc);
+        else
+            mlp_tc3_kernel<false, false, true><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, nullptr, total, S, sigma, rgb, nullptr, nullptr, nullptr, fc);
+        return check_launch("nerf_mlp_composite_tc");
+    }
     int grid = (int)(pairs < num_sms() ? pairs : num_sms());
     if (dbg) {                                        // diagnostic runs only: NERF_TC_MAX_CTAS limits the grid
         const char* e = getenv("NERF_TC_MAX_CTAS");
         if (e && atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
     }
-    const uint8_t* pw = (const uint8_t*)packed;
-    __nv_bfloat16* ao = (__nv_bfloat16*)act_out;
-    unsigned long long* mo = (unsigned long long*)mask_out;
-    cudaStream_t st = (cudaStream_t)stream;
     if (dbg)
-        mlp_tc3_kernel<true, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, dbg);
+        mlp_tc3_kernel<true, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, dbg, fc);
     else if (act_out)                                 // training form: also stores activations + sign words
-        mlp_tc3_kernel<false, true><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, ao, mo, nullptr);
+        mlp_tc3_kernel<false, true, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, ao, mo, nullptr, fc);
     else
-        mlp_tc3_kernel<false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, nullptr);
+        mlp_tc3_kernel<false, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, nullptr, fc);
     return check_launch("nerf_mlp_forward_tc");
 }
 

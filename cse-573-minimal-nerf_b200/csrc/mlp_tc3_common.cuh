@@ -20,10 +20,16 @@ constexpr uint32_t kOffRing = 65536;
 constexpr uint32_t kOffBias = kOffRing + kSlots * kSlotBytes;
 constexpr uint32_t kOffW7 = kOffBias + ((pk::kBiasFloats * 4 + 15) / 16) * 16;     // density_fn.0 weights, fp32 [256]
 constexpr uint32_t kOffSig = kOffW7 + 1024;                                          // sigma partial sums [2 tiles][4][128]
-constexpr uint32_t kOffBars = kOffSig + 4096;
+// fused compositing (mlp_tc3.cu, COMP form): ring of kOutSlots tiles of (sigma, r, g, b) per sample, written by the last
+// step's epilogue warps and consumed by the PE warps, which composite finished rays between two encodings
+constexpr int kOutSlots = 8;
+constexpr uint32_t kOffOut = kOffSig + 4096;                                         // kOutSlots x [128] float4
+constexpr uint32_t kOffStat = kOffOut + kOutSlots * kTileM * 16;                     // per PE warp: sum sigma^2, count sigma != 0
+constexpr uint32_t kOffBars = kOffStat + 64;
 // barrier indices (8 bytes each)
 constexpr uint32_t kBarFull = 0, kBarEmpty = 8, kBarDFull = 16, kBarDFree = 18, kBarALo = 20, kBarAHi = 22, kBarPexFull = 24,
-                   kBarPexEmpty = 26, kBarPedFull = 28, kBarPedEmpty = 30, kBarTurn = 32, kNumBars = 34;
+                   kBarPexEmpty = 26, kBarPedFull = 28, kBarPedEmpty = 30, kBarTurn = 32, kBarOutFull = 34, kBarOutEmpty = 42,
+                   kNumBars = 50;
 constexpr uint32_t kOffTmemHolder = kOffBars + kNumBars * 8;
 constexpr uint32_t kOffDetail = kOffTmemHolder + 16;                                 // PROFILE builds: 96 x int64
 constexpr uint32_t kSmemBytes = kOffDetail + 96 * 8 + 1024;
@@ -275,12 +281,11 @@ struct MmaTile {
             }
         }
     }
-    // the whole per-CTA program of tile T
-    __device__ __forceinline__ void run(uint32_t sbase, int64_t num_pairs) {
+    // the whole per-CTA program of tile T: n_local tile pairs
+    __device__ __forceinline__ void run(uint32_t sbase, uint32_t n_local) {
         const uint64_t descPE = umma::make_desc_k_sw128(sbase + t3::kOffPE + T * 16384);
         const uint64_t descPD = umma::make_desc_k_sw128(sbase + t3::kOffPEDir + T * 16384);
-        uint32_t it = 0;
-        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
+        for (uint32_t it = 0; it < n_local; ++it) {
             stage_in_pair = 0;
             wait_pe(t3::kBarPexFull, it & 1u);
             first_layer_half(descPE);                                  // mlp.0

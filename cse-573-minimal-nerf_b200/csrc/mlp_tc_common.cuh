@@ -14,6 +14,9 @@ constexpr float k2PiHi = 6.28318548202514648f;
 constexpr float k2PiLo = -1.7484555e-7f;
 }  // namespace tcm
 
+// per-ray outputs of the compositing fused into the two-tile kernel (mlp_tc3.cu); weights / depth / acc / stats may be null
+struct CompositeOutputs { float* weights; float* ray_rgb; float* depth; float* acc; float* stats; };
+
 struct StageRef { uint32_t offset, bytes; };
 struct StageTable { StageRef s[pk::kStages]; };
 constexpr StageTable make_stage_table() {

@@ -10,6 +10,7 @@
 // Mapping: one warp per ray for everything that needs a running sum, a search or a sort (coalesced
 // 128-byte row loads, the serial chain broadcast through shuffles), one thread per element otherwise.
 #include "common.cuh"
+#include "composite_scan.cuh"
 
 namespace nerf {
 
@@ -81,25 +82,6 @@ __device__ __forceinline__ float chunk_exclusive_scan(float x, float& running, i
         running = __fadd_rn(running, v);
     }
     return mine;
-}
-
-// Exclusive running sum of x over 32 lanes as a 5-step shuffle scan (used by the fused composite, whose weights are
-// compared with the reference to 1e-6: the summation order differs from the CPU's by ~1 ulp of the partial sums, which is
-// far below what expf already contributes).  The sequential form above stays where the ORDER matters bit for bit: the
-// fine sampler's cdf (bin indices) and the stand-alone nerf_weights.
-__device__ __forceinline__ float chunk_exclusive_scan_tree(float x, float& running, int lane) {
-    float incl = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float up = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += up;
-    }
-    // exclusive = the previous lane's inclusive sum (NOT incl - x: the last sample's interval is 1e10 wide and would cancel
-    // every smaller term)
-    const float prev = __shfl_up_sync(kFull, incl, 1);
-    const float excl = running + (lane ? prev : 0.f);
-    running += __shfl_sync(kFull, incl, 31);
-    return excl;
 }
 
 // One warp per ray.  kind 0: weights from (sigma, deltas) [nerf_weights]; kind 1: full composite from

@@ -133,6 +133,40 @@ class NeRFModel(nn.Module):
         return self.forward(pts.contiguous(), d_rays)
 
 
+    def can_composite(self, S):
+        """True when render_rays can run (tensor-core shape, sample count the fused kernel supports)."""
+        return self.uses_tensor_cores() and bool(nat.lib().nerf_mlp_composite_tc_supported(int(S)))
+
+    def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False):
+        """Network + alpha compositing in ONE kernel (nerf_mlp_composite_tc): the per-sample sigma / rgb stay on the SM
+        unless `keep_samples` (or `save`, the training form, which also stores activations + ReLU sign words).
+        Returns the same dict as nerf_helpers.composite plus 'sigma', 'rgb_samples', 'saved' (None when not kept)."""
+        N, S = ts.shape[0], ts.shape[1]
+        dv = ts.device
+        keep = keep_samples or save
+        sigma = torch.empty((N, S, 1), device=dv, dtype=torch.float32) if keep else None
+        rgb = torch.empty((N, S, 3), device=dv, dtype=torch.float32) if keep else None
+        acts = masks = None
+        if save:
+            import training
+            rows = training.padded_rows(N * S)
+            acts = torch.empty((rows * training.ACT,), device=dv, dtype=torch.bfloat16)
+            masks = torch.empty((rows * (training.ACT // 64),), device=dv, dtype=torch.int64)
+        w = torch.empty((N, S, 1), device=dv, dtype=torch.float32) if want_weights else None
+        col = torch.empty((N, 3), device=dv, dtype=torch.float32)
+        depth = torch.empty((N,), device=dv, dtype=torch.float32)
+        acc = torch.empty((N,), device=dv, dtype=torch.float32)
+        stats = torch.zeros((4,), device=dv, dtype=torch.float32)
+        packed = self.packed_weights()
+        with nat.timed_kernel("mlp_tc_kernel(train)" if save else "mlp_tc_kernel", N * S):
+            nat.check(nat.lib().nerf_mlp_composite_tc(nat.ptr(packed), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(ts), N, S,
+                                                      nat.ptr(sigma), nat.ptr(rgb), nat.ptr(acts), nat.ptr(masks),
+                                                      nat.ptr(w), nat.ptr(col), nat.ptr(depth), nat.ptr(acc), nat.ptr(stats),
+                                                      nat.stream()), "nerf_mlp_composite_tc")
+        return {"weights": w, "rgb": col, "depth": depth, "acc": acc, "stats": stats[:2], "norm": stats[2],
+                "sigma": sigma, "rgb_samples": rgb, "saved": (acts, masks) if save else None}
+
+
 class NeRFNetwork(LightningModule):
     """Coarse + fine NeRF (the reference's Lightning module): forward(o_rays, d_rays) ->
     {'fine_rgb_rays': [N,3], 'coarse_rgb_rays': [N,3]}."""
@@ -148,6 +182,7 @@ class NeRFNetwork(LightningModule):
         self.im_idx, self.max_idx = 0, 1
         self.timer = timer()
         self.last = {}                      # depth / acc / weights of the most recent forward
+        self.keep_samples = False           # True: inference passes also materialise per-sample sigma / rgb in self.last
 
     def forward(self, o_rays, d_rays, rand=None):
         """rand = (u_c [N,C], eps [N,1], u_f [N,F,1]) replaces the three torch.rand draws when given.
@@ -162,7 +197,7 @@ class NeRFNetwork(LightningModule):
             ordered = self.coarse_network.ordered_params() + self.fine_network.ordered_params()
             c_rgb, f_rgb = training.RenderFunction.apply(self, o, d, u_c, eps, u_f, *ordered)
         else:
-            c_rgb, f_rgb, aux = training.forward_pass(self, o, d, rand, save=False)
+            c_rgb, f_rgb, aux = training.forward_pass(self, o, d, rand, save=False, keep_samples=self.keep_samples)
             self._publish(aux)
         return {'fine_rgb_rays': f_rgb, 'coarse_rgb_rays': c_rgb}
 

@@ -5,9 +5,9 @@ the same kernels as inference (stratified sampling, fused tcgen05 MLP, compositi
 sort) with the MLP launched in its training form, which also stores the bf16 activations every layer consumed
 ([samples, 1920] per network).  Backward =
   * hand-written compositing backward (`nerf_composite_backward`): dL/d ray colour -> dL/d(sigma, rgb) pre-activations
-  * the dgrad / wgrad chain through the 10 Linear layers of each network.  ROUND-1 STATUS: these GEMMs run as bf16
-    cuBLAS calls (`torch.mm(..., out_dtype=float32)`), i.e. library GEMMs, with fp32 accumulation; they are the
-    on-device reference the hand-written tcgen05 dgrad / wgrad kernels (next round) are validated against.
+  * the dgrad / wgrad chain through the 10 Linear layers of each network as hand-written tcgen05 kernels
+    (`nerf_mlp_backward_tc`, `nerf_wgrad_tc`); `mlp_backward_reference` keeps the same chain as bf16 cuBLAS GEMMs
+    (`torch.mm(..., out_dtype=float32)`) as the on-device reference those kernels are validated against.
 No gradient flows from the fine loss into the coarse network: the sampler's indices and depths carry none
 (nerf_model.py:114-120), so the two chains are independent.
 """
@@ -192,29 +192,42 @@ def mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray):
     return grads
 
 
-def forward_pass(net, o, d, rand, save):
-    """Shared by inference and training: returns (coarse_rgb, fine_rgb, aux dict)."""
+FUSE_COMPOSITE = True       # network + compositing in one kernel where the sample counts allow it (64 / 128 / 192 / 256)
+
+
+def forward_pass(net, o, d, rand, save, keep_samples=False):
+    """Shared by inference and training: returns (coarse_rgb, fine_rgb, aux dict).  With the fused kernel the per-sample
+    sigma / rgb of an inference pass are only materialised when `keep_samples` (aux['c_sigma'] ... are None otherwise)."""
     N, C, Fn = o.shape[0], net.coarse_samples, net.fine_samples
     dv = o.device
     if rand is None:        # the reference's draw order and shapes (nerf_helpers.py:52,139,154)
         rand = (torch.rand((N, C), device=dv), torch.rand((N, 1), device=dv), torch.rand((N, Fn, 1), device=dv))
     u_c, eps, u_f = rand
     c_ts = net._coarse_ts(o, d, u_c)
-    if save:
-        c_sigma, c_rgb, c_acts = mlp_forward_train(net.coarse_network, o, d, c_ts)
+    fused = FUSE_COMPOSITE and net.coarse_network.can_composite(C) and net.fine_network.can_composite(C + Fn)
+    if fused:       # network + compositing in one kernel; render keeps no per-sample outputs at all
+        c = net.coarse_network.render_rays(o, d, c_ts, want_weights=True, keep_samples=keep_samples, save=save)
+        c_sigma, c_rgb, c_acts = c["sigma"], c["rgb_samples"], c["saved"]
     else:
-        c_sigma, c_rgb = net.coarse_network.forward_rays(o, d, c_ts)
-        c_acts = None
-    c = nerf_helpers.composite(c_sigma, c_rgb, c_ts)
+        if save:
+            c_sigma, c_rgb, c_acts = mlp_forward_train(net.coarse_network, o, d, c_ts)
+        else:
+            c_sigma, c_rgb = net.coarse_network.forward_rays(o, d, c_ts)
+            c_acts = None
+        c = nerf_helpers.composite(c_sigma, c_rgb, c_ts)
     # near / far are NOT forwarded upstream (nerf_model.py:114-115): the sampler's 2.0 / 6.0 defaults apply
     _, f_ts = nerf_helpers.inverse_transform_sampling(o, d, c["weights"], c_ts, Fn, rand=(eps, u_f))
     _, ts = nerf_helpers.merge_samples(o, d, f_ts, c_ts, want_points=False)
-    if save:
-        f_sigma, f_rgb, f_acts = mlp_forward_train(net.fine_network, o, d, ts)
+    if fused:
+        f = net.fine_network.render_rays(o, d, ts, want_weights=False, keep_samples=keep_samples, save=save)
+        f_sigma, f_rgb, f_acts = f["sigma"], f["rgb_samples"], f["saved"]
     else:
-        f_sigma, f_rgb = net.fine_network.forward_rays(o, d, ts)
-        f_acts = None
-    f = nerf_helpers.composite(f_sigma, f_rgb, ts, want_weights=False)
+        if save:
+            f_sigma, f_rgb, f_acts = mlp_forward_train(net.fine_network, o, d, ts)
+        else:
+            f_sigma, f_rgb = net.fine_network.forward_rays(o, d, ts)
+            f_acts = None
+        f = nerf_helpers.composite(f_sigma, f_rgb, ts, want_weights=False)
     aux = {"c": c, "f": f, "c_ts": c_ts, "ts": ts, "c_sigma": c_sigma, "c_rgb": c_rgb, "f_sigma": f_sigma, "f_rgb": f_rgb,
            "c_acts": c_acts, "f_acts": f_acts}
     return c["rgb"], f["rgb"], aux

@@ -137,6 +137,21 @@ int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float*
 int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
                                int64_t N, int S, float* sigma, float* rgb, void* stream);
 
+/* ---- K8 + K2 fused: NeRFModel forward (nerf_model.py:362-389) with deltas, weights, ray colour, depth and opacity
+ * (nerf_helpers.py:58-104, generate_deltas / calculate_unnormalized_weights / estimate_ray_color) computed INSIDE the
+ * tensor-core kernel: every CTA owns whole rays, the per-sample (sigma, rgb) go through a shared-memory ring and are
+ * composited by warps of the same CTA while the next tiles are in the tensor pipe.  Replaces the pair
+ * nerf_mlp_forward_tc[_train] + nerf_composite; same arithmetic as those two calls (bit-identical outputs).
+ * Needs S % 32 == 0 and a ray group (smallest run of whole rays that is a whole number of 128-sample tiles) of at most 6
+ * tiles: nerf_mlp_composite_tc_supported(S) != 0, true for 64 / 128 / 192 / 256.
+ * sigma [N,S] / rgb [N,S,3]: nullable together (render does not need them); act_out / mask_out: non-NULL = training form
+ * (as nerf_mlp_forward_tc_train; needs sigma / rgb too).  weights [N,S], depth [N], acc [N]: nullable.  ray_rgb [N,3].
+ * stats4: nullable; as nerf_composite (zero it first). */
+int nerf_mlp_composite_tc_supported(int S);
+int nerf_mlp_composite_tc(const void* packed, const float* o, const float* d, const float* ts, int64_t N, int S,
+                          float* sigma, float* rgb, void* act_out, void* mask_out,
+                          float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream);
+
 /* ---- optimiser step.  nerf_model.py:134-143 (torch.optim.Adam, lr 5e-4, betas (0.9, 0.999), eps 1e-8, no weight decay)
  * over flat fp32 buffers of n elements (all parameters of both networks): params updated in place, exp_avg / exp_avg_sq
  * are the Adam moments, step >= 1 is the 1-based step count used for the bias corrections.  Same arithmetic and order as

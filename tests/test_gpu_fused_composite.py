@@ -1,0 +1,135 @@
+"""GPU parity of the compositing fused into the tensor-core MLP kernel (nerf_mlp_composite_tc, mlp_tc3.cu COMP form)
+against the two-launch path it replaces (nerf_mlp_forward_tc[_train] + nerf_composite), which is itself checked against
+the oracle in test_gpu_mlp_tc.py / test_gpu_samplers.py.  Both spell the same arithmetic in the same order, so every
+output is compared BIT FOR BIT; only the two atomically accumulated density statistics get a relative tolerance."""
+import pytest
+import torch
+
+import synthetic
+from util import T, bits_equal, rand_triple
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def make_net(seed=4, kind="dense"):
+    import nerf_model
+    net = nerf_model.NeRFNetwork(precision="bf16")
+    net.load_state_dict(synthetic.make_state_dict(seed, kind))
+    return net.to(DEV)
+
+
+def rays(N, S, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    o = torch.randn(N, 3, device=DEV, generator=g) * 0.3
+    d = torch.nn.functional.normalize(torch.randn(N, 3, device=DEV, generator=g), dim=1) * 1.07
+    ts = torch.sort(2.0 + 4.0 * torch.rand(N, S, 1, device=DEV, generator=g), dim=1).values.contiguous()
+    return o, d, ts
+
+
+# ray counts: many pairs per CTA / fewer groups than SMs / odd (partial last group) / single ray;
+# sample counts: the two the network uses (64, 192) + every other group shape (1, 2 and 4 rays per group; 1..5 tiles)
+@pytest.mark.parametrize("N,S", [(4096, 64), (4096, 192), (1024, 192), (301, 192), (301, 64), (1, 192), (1, 64), (2, 64),
+                                 (515, 128), (130, 256), (257, 32), (203, 96), (99, 160), (51, 320)])
+def test_fused_matches_two_launch_path(N, S):
+    import nerf_helpers as h
+    net = make_net().fine_network
+    assert net.can_composite(S)
+    o, d, ts = rays(N, S, 10 * S + N)
+    sg, rgb = net.forward_rays(o, d, ts)
+    ref = h.composite(sg, rgb, ts)
+    got = net.render_rays(o, d, ts, want_weights=True, keep_samples=True)
+    torch.cuda.synchronize()
+    assert bits_equal(got["sigma"], sg) and bits_equal(got["rgb_samples"], rgb)
+    for key in ("weights", "rgb", "depth", "acc"):
+        assert bits_equal(got[key], ref[key]), key
+    torch.testing.assert_close(got["stats"], ref["stats"], rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(got["norm"], ref["norm"], rtol=1e-5, atol=1e-3)
+    # render form: no per-sample outputs, no weights
+    lean = net.render_rays(o, d, ts, want_weights=False)
+    torch.cuda.synchronize()
+    assert lean["sigma"] is None and lean["weights"] is None
+    for key in ("rgb", "depth", "acc"):
+        assert bits_equal(lean[key], ref[key]), key
+
+
+@pytest.mark.parametrize("N,S", [(1024, 192), (301, 64)])
+def test_fused_training_form_saves_the_same_tensors(N, S):
+    import nerf_helpers as h
+    import training
+    net = make_net().coarse_network
+    o, d, ts = rays(N, S, 77 + N)
+    sg, rgb, (acts, masks) = training.mlp_forward_train(net, o, d, ts)
+    ref = h.composite(sg, rgb, ts)
+    got = net.render_rays(o, d, ts, want_weights=True, save=True)
+    torch.cuda.synchronize()
+    assert bits_equal(got["sigma"], sg) and bits_equal(got["rgb_samples"], rgb)
+    M = N * S
+    a0, a1 = training.untile(acts, M, training.ACT), training.untile(got["saved"][0], M, training.ACT)
+    assert torch.equal(a0.view(torch.int16), a1.view(torch.int16))
+    words = training.ACT // 64
+    tiles = training.padded_rows(M) // 128
+    m0 = masks.view(tiles, words, 128).permute(0, 2, 1).reshape(-1, words)[:M]
+    m1 = got["saved"][1].view(tiles, words, 128).permute(0, 2, 1).reshape(-1, words)[:M]
+    assert torch.equal(m0, m1)
+    for key in ("weights", "rgb", "depth", "acc"):
+        assert bits_equal(got[key], ref[key]), key
+
+
+def test_unsupported_sample_counts_are_rejected():
+    import _native as nat
+    lib = nat.lib()
+    assert [S for S in (32, 64, 96, 128, 160, 192, 256, 320) if not lib.nerf_mlp_composite_tc_supported(S)] == []
+    assert [S for S in (0, 5, 40, 77, 224, 448) if lib.nerf_mlp_composite_tc_supported(S)] == []
+    net = make_net().fine_network
+    o, d, ts = rays(8, 40, 1)
+    with pytest.raises(RuntimeError, match="not supported"):
+        net.render_rays(o, d, ts)
+
+
+def test_network_forward_identical_with_and_without_fusion(golden):
+    """NeRFNetwork.forward end to end (coarse -> fine sampling -> fine): fused and two-launch paths agree bit for bit,
+    so every oracle tolerance established for one holds for the other."""
+    import training
+    g = golden["network"]
+    net = make_net(4, "dense")
+    o, d = T(g["o"], DEV), T(g["d"], DEV)
+    rand = rand_triple(540, 64, device=DEV)
+    net.keep_samples = True
+    try:
+        training.FUSE_COMPOSITE = False
+        a = net.forward(o, d, rand=rand)
+        last_a = dict(net.last)
+        training.FUSE_COMPOSITE = True
+        b = net.forward(o, d, rand=rand)
+        last_b = dict(net.last)
+    finally:
+        training.FUSE_COMPOSITE = True
+    torch.cuda.synchronize()
+    for key in ("coarse_rgb_rays", "fine_rgb_rays"):
+        assert bits_equal(a[key], b[key]), key
+    for key in ("depth", "acc", "ts", "coarse_weights", "coarse_sigma", "fine_sigma", "fine_rgb"):
+        assert bits_equal(last_a[key], last_b[key]), key
+
+
+def test_training_gradients_identical_with_and_without_fusion():
+    import training
+    net = make_net(3, "init")
+    o, d, _ = rays(512, 64, 5)
+    target = torch.rand(512, 3, device=DEV)
+    rand = rand_triple(900, 512, device=DEV)
+    grads = []
+    try:
+        for fuse in (False, True):
+            training.FUSE_COMPOSITE = fuse
+            net.zero_grad(set_to_none=True)
+            out = net.forward(o, d, rand=rand)
+            loss = ((out["coarse_rgb_rays"] - target) ** 2).mean() + ((out["fine_rgb_rays"] - target) ** 2).mean()
+            loss.backward()
+            grads.append([p.grad.clone() for p in net.parameters()])
+    finally:
+        training.FUSE_COMPOSITE = True
+    torch.cuda.synchronize()
+    for ga, gb in zip(*grads):
+        # wgrad accumulates with atomics: equal up to summation order
+        torch.testing.assert_close(ga, gb, rtol=1e-4, atol=1e-6)
