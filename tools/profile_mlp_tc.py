@@ -37,6 +37,22 @@ if os.environ.get("NERF_PROF_PLAIN") == "1":
         torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / 20
         print(f"plain kernel N={N} S={S}: {ms:.4f} ms, {N*S*920832/ms/1e9:.1f} TFLOP/s")
+    # the same network with compositing fused into the kernel (render form: no per-sample outputs)
+    fused = nat.lib().nerf_mlp_composite_tc
+    ts_sorted = torch.sort(ts, dim=1).values.contiguous()
+    col, depth, acc, stats = torch.empty(N, 3, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev), torch.zeros(4, device=dev)
+    w = torch.empty(N, S, device=dev)
+    for want_w in (False, True):
+        for rep in range(3):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(20):
+                nat.check(fused(nat.ptr(packed), nat.ptr(o), nat.ptr(d), nat.ptr(ts_sorted), N, S, None, None, None, None,
+                                nat.ptr(w) if want_w else None, nat.ptr(col), nat.ptr(depth), nat.ptr(acc), nat.ptr(stats), nat.stream()), "fused")
+            t1.record()
+            torch.cuda.synchronize()
+            ms = t0.elapsed_time(t1) / 20
+            print(f"fused kernel (weights {'on' if want_w else 'off'}) N={N} S={S}: {ms:.4f} ms, {N*S*920832/ms/1e9:.1f} TFLOP/s")
     sys.exit(0)
 fn = nat.lib().nerf_debug_mlp_tc_profile
 fn.restype = ctypes.c_int
