@@ -96,8 +96,7 @@ class ClockSampler:
 
 def frame_setup(H, W, pose_index):
     import synthetic
-    from oracle import nerf_oracle as O      # pose + focal helpers only (host-side scalars)
-    focal = O.focal_from_fov(W, CAM_ANGLE_X)
+    focal = 0.5 * W / np.tan(0.5 * CAM_ANGLE_X)          # nerf_helpers.py:164 (product arm: nothing from oracle/)
     angle = float(np.linspace(-180, 180, 41)[:-1][pose_index % 40])
     return synthetic.orbit_pose(angle, -30.0, 4.0), focal
 

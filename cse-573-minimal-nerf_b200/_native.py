@@ -32,6 +32,7 @@ _PROTOTYPES = {
     "nerf_composite_backward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "nerf_fine_sample": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _f32, _f32, _vp, _vp, _vp, _vp]),
     "nerf_merge_sort": (_int, [_vp, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp, _vp]),
+    "nerf_fine_sample_merge": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _f32, _f32, _vp, _vp]),
     "nerf_positional_encoding": (_int, [_vp, _i64, _int, _int, _vp, _vp]),
     "nerf_mlp_forward_fp32": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "nerf_packed_bytes": (ctypes.c_size_t, []),

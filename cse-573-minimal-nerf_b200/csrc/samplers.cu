@@ -407,6 +407,93 @@ merge_sort256_kernel(const float* __restrict__ o, const float* __restrict__ d, c
     }
 }
 
+// ---------------------------------------------------------------------------- K3 + K4 in one launch
+// What NeRFNetwork.forward does between the two networks (nerf_model.py:114-120): inverse-CDF fine depths, concatenated
+// with the coarse depths (fine first) and sorted - without the round trip of the fine depths through HBM.  One warp per
+// ray; the same cdf / search / jitter arithmetic as fine_sample_kernel and the same register-resident bitonic network as
+// merge_sort256_kernel (C + F <= 256), so the sorted depths are bit-identical to the two-launch path.
+__global__ void __launch_bounds__(kThreads)
+fine_sample_merge_kernel(const float* __restrict__ w, const float* __restrict__ ts, const float* __restrict__ eps,
+                         const float* __restrict__ u, const float* __restrict__ q_base, int64_t N, int C, int F,
+                         float near_, float far_, float* __restrict__ ts_sorted) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* cdf = smem + (size_t)wib * (2 * C + 2);
+    float* bounds = cdf + C;
+    const int64_t warps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const float Ff = (float)F;
+    const int S = C + F;
+    for (int64_t n = blockIdx.x * (int64_t)kWarpsPerBlock + wib; n < N; n += warps) {
+        float running = 0.f;                                                      // nerf_helpers.py:137, sequential order
+        for (int base = 0; base < C; base += kWarp) {
+            const int i = base + lane;
+            const float x = (i < C) ? w[n * C + i] : 0.f;
+            const float excl = chunk_exclusive_scan(x, running, lane);
+            if (i < C) {
+                cdf[i] = __fadd_rn(excl, x);
+                bounds[i + 1] = ts[n * C + i];                                  // nerf_helpers.py:149
+            }
+        }
+        if (lane == 0) { bounds[0] = near_; bounds[C + 1] = far_; }
+        __syncwarp();
+        const float total = cdf[C - 1];
+        __syncwarp();
+        for (int i = lane; i < C; i += kWarp) cdf[i] = __fdiv_rn(cdf[i], total);   // nerf_helpers.py:138
+        __syncwarp();
+        const float e = __fdiv_rn(eps[n], Ff);                                      // nerf_helpers.py:139
+        float v[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = 32 * jj + lane;                                             // element index in cat([fine, coarse])
+            float t = __int_as_float(0x7f800000);
+            if (j < F) {
+                const float q = __fadd_rn(__ldg(q_base + j), e);                     // nerf_helpers.py:142
+                int lo = 0, hi = C;                                                   // torch.searchsorted, right=False
+                while (lo < hi) {
+                    const int mid = lo + ((hi - lo) >> 1);
+                    if (!(cdf[mid] >= q)) lo = mid + 1; else hi = mid;
+                }
+                const float b0 = bounds[lo], b1 = bounds[lo + 1];
+                t = __fadd_rn(b0, __fmul_rn(__fsub_rn(b1, b0), u[n * F + j]));       // nerf_helpers.py:154
+            } else if (j < S) {
+                t = bounds[j - F + 1];                                                // nerf_model.py:117 (fine first, then coarse)
+            }
+            v[jj] = t;
+        }
+#pragma unroll
+        for (int k = 2; k <= 256; k <<= 1) {
+#pragma unroll
+            for (int dist = k >> 1; dist >= 1; dist >>= 1) {
+                if (dist >= 32) {
+                    const int dj = dist >> 5;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if ((j & dj) == 0) {
+                            const bool up = (((32 * j + lane) & k) == 0);
+                            cmpx(v[j], v[j | dj], up);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int el = 32 * j + lane;
+                        const float other = __shfl_xor_sync(kFull, v[j], dist);
+                        const bool up = ((el & k) == 0);
+                        const bool lower = ((lane & dist) == 0);
+                        v[j] = (up == lower) ? fminf(v[j], other) : fmaxf(v[j], other);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int el = 32 * j + lane;
+            if (el < S) ts_sorted[n * S + el] = v[j];
+        }
+        __syncwarp();
+    }
+}
+
 // General path (A + B <= 1024): one warp per ray, enumeration sort in shared memory: rank(e) = #{j : v_j < v_e or (v_j == v_e and j < e)}.
 // Dynamic shared memory per warp: vals[S] then sorted[S].
 __global__ void __launch_bounds__(kThreads)
@@ -634,6 +721,17 @@ extern "C" int nerf_merge_sort(const float* o, const float* d, const float* ts_a
     merge_sort_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, smem, (cudaStream_t)stream>>>(
         o, d, ts_a, A, ts_b, B, N, ts_sorted, samples_sorted);
     return check_launch("nerf_merge_sort");
+}
+
+extern "C" int nerf_fine_sample_merge(const float* w, const float* ts, const float* eps, const float* u, const float* q_base,
+                                      int64_t N, int C, int F, float near_, float far_, float* ts_sorted, void* stream) {
+    NERF_REQUIRE(N >= 0 && C > 0 && F > 0 && C + F <= 256, "nerf_fine_sample_merge: bad size N=%lld C=%d F=%d (C + F <= 256)", (long long)N, C, F);
+    if (N == 0) return 0;
+    NERF_REQUIRE(w && ts && eps && u && q_base && ts_sorted, "nerf_fine_sample_merge: null pointer");
+    const size_t smem = (size_t)kWarpsPerBlock * (2 * C + 2) * sizeof(float);
+    fine_sample_merge_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, smem, (cudaStream_t)stream>>>(
+        w, ts, eps, u, q_base, N, C, F, near_, far_, ts_sorted);
+    return check_launch("nerf_fine_sample_merge");
 }
 
 extern "C" int nerf_composite_backward(const float* sigma, const float* rgb, const float* ts, const float* g_ray, int64_t N, int S,

@@ -128,6 +128,24 @@ def inverse_transform_sampling(o_rays, d_rays, weights, ts, num_samples, near=2.
     return (pts, fts, idx) if return_idx else (pts, fts)
 
 
+def fine_depths_sorted(weights, ts, num_samples, near=2.0, far=6.0, rand=None):
+    """inverse_transform_sampling + merge_samples in one launch, depths only (what NeRFNetwork.forward needs between the two
+    networks, nerf_model.py:114-120): returns the sorted [N, C+num_samples, 1] depths, bit-identical to the two calls.
+    C + num_samples <= 256."""
+    w, t = nat.dev(weights, "weights"), nat.dev(ts, "ts")
+    N, C, _ = t.shape
+    if rand is None:
+        eps = torch.rand((N, 1), device=t.device)
+        u = torch.rand((N, num_samples, 1), device=t.device)
+    else:
+        eps, u = nat.dev(rand[0], "rand[0]"), nat.dev(rand[1], "rand[1]")
+    q = _queries(num_samples, t.device)
+    out = torch.empty((N, C + num_samples, 1), device=t.device, dtype=torch.float32)
+    nat.check(nat.lib().nerf_fine_sample_merge(nat.ptr(w), nat.ptr(t), nat.ptr(eps), nat.ptr(u), nat.ptr(q), N, C, num_samples,
+                                               float(near), float(far), nat.ptr(out), nat.stream()), "nerf_fine_sample_merge")
+    return out
+
+
 def merge_samples(o_rays, d_rays, fine_ts, coarse_ts, want_points=True):
     """The concat + sort + gather of NeRFNetwork.forward (nerf_model.py:116-120) as one kernel.
     Returns (samples [N,A+B,3] or None, ts [N,A+B,1])."""

@@ -137,10 +137,11 @@ class NeRFModel(nn.Module):
         """True when render_rays can run (tensor-core shape, sample count the fused kernel supports)."""
         return self.uses_tensor_cores() and bool(nat.lib().nerf_mlp_composite_tc_supported(int(S)))
 
-    def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False):
+    def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False, stats=None):
         """Network + alpha compositing in ONE kernel (nerf_mlp_composite_tc): the per-sample sigma / rgb stay on the SM
         unless `keep_samples` (or `save`, the training form, which also stores activations + ReLU sign words).
-        Returns the same dict as nerf_helpers.composite plus 'sigma', 'rgb_samples', 'saved' (None when not kept)."""
+        Returns the same dict as nerf_helpers.composite plus 'sigma', 'rgb_samples', 'saved' (None when not kept).
+        `stats`: optional ZEROED [4] fp32 buffer for the density statistics (one is allocated otherwise)."""
         N, S = ts.shape[0], ts.shape[1]
         dv = ts.device
         keep = keep_samples or save
@@ -156,7 +157,8 @@ class NeRFModel(nn.Module):
         col = torch.empty((N, 3), device=dv, dtype=torch.float32)
         depth = torch.empty((N,), device=dv, dtype=torch.float32)
         acc = torch.empty((N,), device=dv, dtype=torch.float32)
-        stats = torch.zeros((4,), device=dv, dtype=torch.float32)
+        if stats is None:
+            stats = torch.zeros((4,), device=dv, dtype=torch.float32)
         packed = self.packed_weights()
         with nat.timed_kernel("mlp_tc_kernel(train)" if save else "mlp_tc_kernel", N * S):
             nat.check(nat.lib().nerf_mlp_composite_tc(nat.ptr(packed), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(ts), N, S,

@@ -206,7 +206,8 @@ def forward_pass(net, o, d, rand, save, keep_samples=False):
     c_ts = net._coarse_ts(o, d, u_c)
     fused = FUSE_COMPOSITE and net.coarse_network.can_composite(C) and net.fine_network.can_composite(C + Fn)
     if fused:       # network + compositing in one kernel; render keeps no per-sample outputs at all
-        c = net.coarse_network.render_rays(o, d, c_ts, want_weights=True, keep_samples=keep_samples, save=save)
+        stats8 = torch.zeros((8,), device=dv, dtype=F32)        # density statistics of both networks, one memset
+        c = net.coarse_network.render_rays(o, d, c_ts, want_weights=True, keep_samples=keep_samples, save=save, stats=stats8[:4])
         c_sigma, c_rgb, c_acts = c["sigma"], c["rgb_samples"], c["saved"]
     else:
         if save:
@@ -216,10 +217,13 @@ def forward_pass(net, o, d, rand, save, keep_samples=False):
             c_acts = None
         c = nerf_helpers.composite(c_sigma, c_rgb, c_ts)
     # near / far are NOT forwarded upstream (nerf_model.py:114-115): the sampler's 2.0 / 6.0 defaults apply
-    _, f_ts = nerf_helpers.inverse_transform_sampling(o, d, c["weights"], c_ts, Fn, rand=(eps, u_f))
-    _, ts = nerf_helpers.merge_samples(o, d, f_ts, c_ts, want_points=False)
+    if C + Fn <= 256:       # fine depths + merge sort in one launch
+        ts = nerf_helpers.fine_depths_sorted(c["weights"], c_ts, Fn, rand=(eps, u_f))
+    else:
+        _, f_ts = nerf_helpers.inverse_transform_sampling(o, d, c["weights"], c_ts, Fn, rand=(eps, u_f))
+        _, ts = nerf_helpers.merge_samples(o, d, f_ts, c_ts, want_points=False)
     if fused:
-        f = net.fine_network.render_rays(o, d, ts, want_weights=False, keep_samples=keep_samples, save=save)
+        f = net.fine_network.render_rays(o, d, ts, want_weights=False, keep_samples=keep_samples, save=save, stats=stats8[4:])
         f_sigma, f_rgb, f_acts = f["sigma"], f["rgb_samples"], f["saved"]
     else:
         if save:

@@ -85,6 +85,11 @@ int nerf_fine_sample(const float* o, const float* d, const float* w, const float
  * concatenated, sorted ascending per ray; samples_sorted [N,A+B,3] = o + t*d (nullable). A+B <= 1024. */
 int nerf_merge_sort(const float* o, const float* d, const float* ts_a, int A, const float* ts_b, int B,
                     int64_t N, float* ts_sorted, float* samples_sorted, void* stream);
+/* K3 + K4 in one launch: the sorted depths NeRFNetwork.forward feeds the fine network (nerf_model.py:114-120) straight from
+ * the coarse weights / depths: inverse-CDF fine depths (as nerf_fine_sample), concatenated fine-first with the coarse ones
+ * and sorted (as nerf_merge_sort), bit-identical to those two calls.  C + F <= 256.  ts_sorted [N, C+F]. */
+int nerf_fine_sample_merge(const float* w, const float* ts, const float* eps, const float* u, const float* q_base,
+                           int64_t N, int C, int F, float near_, float far_, float* ts_sorted, void* stream);
 
 /* ---- H7: positional encoding.  nerf_model.py:19-33.  x [n,c] -> out [n, 2*L*c];
  * per frequency i: cos(2^i pi x) for the c channels, then sin(2^i pi x). */

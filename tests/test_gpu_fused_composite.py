@@ -133,3 +133,23 @@ def test_training_gradients_identical_with_and_without_fusion():
     for ga, gb in zip(*grads):
         # wgrad accumulates with atomics: equal up to summation order
         torch.testing.assert_close(ga, gb, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("N,C,F", [(4096, 64, 128), (301, 64, 128), (77, 5, 7), (33, 100, 156), (9, 2, 3), (1, 64, 128)])
+def test_fine_depths_sorted_matches_sampler_plus_merge(N, C, F):
+    """nerf_fine_sample_merge (K3 + K4 in one launch) against nerf_fine_sample + nerf_merge_sort: bit-identical sorted
+    depths, including rays whose weights are all zero (NaN cdf, nerf_helpers.py:138)."""
+    import nerf_helpers as h
+    g = torch.Generator(device=DEV).manual_seed(N + C)
+    o, d, _ = rays(N, 32, 3)
+    _, c_ts = h.generate_coarse_samples(o, d, C, rand=torch.rand(N, C, device=DEV, generator=g))
+    w = torch.rand(N, C, 1, device=DEV, generator=g) ** 4
+    w[::7] = 0.0                                                  # dead rays
+    if N > 3:
+        w[3, : C // 2] = 0.0                                      # flat cdf prefix (ties in the search)
+    rand = (torch.rand(N, 1, device=DEV, generator=g), torch.rand(N, F, 1, device=DEV, generator=g))
+    _, f_ts = h.inverse_transform_sampling(o, d, w, c_ts, F, rand=rand)
+    _, ref = h.merge_samples(o, d, f_ts, c_ts, want_points=False)
+    got = h.fine_depths_sorted(w, c_ts, F, rand=rand)
+    torch.cuda.synchronize()
+    assert got.shape == (N, C + F, 1) and bits_equal(got, ref)
