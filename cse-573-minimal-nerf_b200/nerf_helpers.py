@@ -172,7 +172,9 @@ def generate_360_view_synthesis(model, save_dir: Path, epoch, height=800, width=
     for angle in np.linspace(-180, 180, num_poses + 1)[:-1]:
         o_rays, d_rays = dataloader.get_rays(height, width, focal, pose_spherical(angle, -30, radius), device=device)
         views.append(view_reconstruction(model, o_rays, d_rays, N=N))
-    dataloader.write_gif(Path(save_dir, f'{epoch}-360.gif'), views)
+    import multi_gpu
+    if multi_gpu.world()[0] == 0:           # every rank holds all frames (all-gathered slabs); one of them writes the file
+        dataloader.write_gif(Path(save_dir, f'{epoch}-360.gif'), views)
     return views
 
 
