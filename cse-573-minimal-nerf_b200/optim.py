@@ -76,9 +76,13 @@ class FlatAdam(torch.optim.Optimizer):
         nat.check(nat.lib().nerf_adam_step(nat.ptr(self.flat_params), nat.ptr(self.flat_grads), nat.ptr(self.flat_m),
                                            nat.ptr(self.flat_v), self._n, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
                                            float(g["eps"]), self._step, nat.stream()), "nerf_adam_step")
+        return loss
+
+    def state_dict(self):
+        """torch.optim.Adam's layout; the per-parameter `step` entries are refreshed here instead of 40 times per step."""
         for p in self._params:
             self.state[p]["step"] = torch.tensor(float(self._step))
-        return loss
+        return super().state_dict()
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)        # torch copies the saved tensors in; move them back into the flat buffers

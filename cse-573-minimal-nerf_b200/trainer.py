@@ -83,7 +83,13 @@ class Trainer:
         self.last_checkpoint = None
 
     def record(self, name, value):
-        self._metrics[name] = float(value.detach()) if torch.is_tensor(value) and value.numel() == 1 else value
+        """Keeps the device tensor: converting here would synchronise the stream on every `self.log` call (8 per training
+        step); the values are read back only when a line is actually written (`metrics()`)."""
+        self._metrics[name] = value.detach() if torch.is_tensor(value) else value
+
+    def metrics(self):
+        return {k: (float(v) if torch.is_tensor(v) and v.numel() == 1 else v) for k, v in self._metrics.items()
+                if not torch.is_tensor(v) or v.numel() == 1}
 
     def checkpoint_dir(self):
         run = getattr(self.logger, "name", "run") if self.logger is not None else "run"
@@ -135,7 +141,7 @@ class Trainer:
                 optimizer.step()
                 self.global_step += 1
                 if self.logger is not None and self.rank == 0 and self.global_step % self.log_every == 0:
-                    self.logger.log_metrics(dict(self._metrics, lr=optimizer.param_groups[0]["lr"], epoch=self.current_epoch),
+                    self.logger.log_metrics(dict(self.metrics(), lr=optimizer.param_groups[0]["lr"], epoch=self.current_epoch),
                                             self.global_step)
             if scheduler is not None:
                 scheduler.step()

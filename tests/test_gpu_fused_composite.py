@@ -153,3 +153,53 @@ def test_fine_depths_sorted_matches_sampler_plus_merge(N, C, F):
     got = h.fine_depths_sorted(w, c_ts, F, rand=rand)
     torch.cuda.synchronize()
     assert got.shape == (N, C + F, 1) and bits_equal(got, ref)
+
+
+def test_full_frame_is_independent_of_chunking_and_sharding():
+    """BASELINE configs[1] size (800 x 800 = 640 000 rays, 64 + 128 samples): with the uniforms fixed per ray, the image must not
+    depend on how the rays are cut into chunks (4096 as the reference, an odd 4095, 12 345) or into per-GPU slabs - every ray is
+    composited by exactly one CTA from its own samples, whatever tile range that CTA was given.  Also: opacity <= 1, expected
+    depth inside [near, far] where the ray hit anything, sorted merged depths."""
+    import dataloader
+    import multi_gpu
+    import nerf_helpers as h
+    net = make_net(5, "dense")
+    H = W = 800
+    n = H * W
+    focal = 0.5 * W / 0.36                                    # ~ the lego camera
+    o, d = dataloader.get_rays(H, W, focal, h.pose_spherical(35.0, -30.0, 4.0), device=DEV)
+    o, d = o.reshape(n, 3), d.reshape(n, 3)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    u_c = torch.rand(n, 64, device=DEV, generator=g)
+    eps = torch.rand(n, 1, device=DEV, generator=g)
+    u_f = torch.rand(n, 128, 1, device=DEV, generator=g)
+
+    def render(chunk, lo=0, hi=n):
+        out = torch.empty((hi - lo, 3), device=DEV)
+        depth = torch.empty((hi - lo,), device=DEV)
+        acc = torch.empty((hi - lo,), device=DEV)
+        with torch.no_grad():
+            for i in range(lo, hi, chunk):
+                j = min(i + chunk, hi)
+                out[i - lo:j - lo] = net.forward(o[i:j], d[i:j], rand=(u_c[i:j], eps[i:j], u_f[i:j]))["fine_rgb_rays"]
+                depth[i - lo:j - lo], acc[i - lo:j - lo] = net.last["depth"], net.last["acc"]
+                if i == lo:
+                    ts = net.last["ts"]
+                    assert bool((ts[:, 1:] >= ts[:, :-1]).all())
+        return out, depth, acc
+
+    ref, depth, acc = render(4096)
+    assert torch.isfinite(ref).all() and float(acc.max()) <= 1.0 + 1e-5 and float(acc.min()) >= 0.0
+    hit = acc > 0.5
+    assert bool(hit.any())
+    mean_depth = depth[hit] / acc[hit]
+    assert float(mean_depth.min()) >= 2.0 - 1e-3 and float(mean_depth.max()) <= 6.0 + 1e-3
+    for chunk in (4095, 12345):
+        got, _, _ = render(chunk)
+        assert bits_equal(got, ref), chunk
+    for ws in (3, 8):                                        # per-GPU slabs of multi_gpu.ray_slab, each rendered on its own
+        for rank in (0, ws - 1):
+            lo, hi = multi_gpu.ray_slab(n, rank, ws)
+            got, _, _ = render(4096, lo, hi)
+            assert bits_equal(got, ref[lo:hi]), (ws, rank)
+    torch.cuda.synchronize()
