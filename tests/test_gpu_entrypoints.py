@@ -71,3 +71,32 @@ def test_train_then_render(scene, tmp_path):
     assert views[0].shape == (64, 64, 3) and views[0].dtype == np.uint8
     epoch = str(ckpt)[str(ckpt).find("epoch="):]
     assert epoch[:epoch.find("-")] == "epoch=3"                                     # render.py:15-16 name parsing
+
+
+def test_score_metrics_match_oracle_and_entry_point(scene, tmp_path):
+    """score.py (score.py:20-41): device PSNR / SSIM against the scikit-image restatement in oracle/score_oracle.py on a random
+    pair and on a rendered-vs-ground-truth pair; then the `calculate_scores(ckpt, base_dir, rays)` entry point end to end."""
+    import dataloader
+    import nerf_helpers
+    import nerf_model
+    import score
+    from oracle import score_oracle as S
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, size=(96, 120, 3), dtype=np.uint8)
+    b = np.clip(a.astype(np.int16) + rng.integers(-20, 21, size=a.shape), 0, 255).astype(np.uint8)
+    assert abs(score.peak_signal_noise_ratio(a, b) - S.peak_signal_noise_ratio(a, b)) < 1e-9
+    assert abs(score.structural_similarity(a, b, multichannel=True) - S.structural_similarity(a, b)) < 1e-9
+    assert abs(score.structural_similarity(torch.from_numpy(a).cuda(), torch.from_numpy(a).cuda()) - 1.0) < 1e-12
+    net = nerf_model.NeRFNetwork()
+    net.load_state_dict(synthetic.make_state_dict(5, "dense"))
+    net = net.cuda()
+    item = dataloader.SyntheticDataset(scene, "test", 1024)[0]
+    o, d = item["all_origin"][300:420, 300:460].contiguous(), item["all_direc"][300:420, 300:460].contiguous()
+    recon = nerf_helpers.view_reconstruction(net, o, d, N=4096)
+    gt = (item["image"][300:420, 300:460] * 255).clamp(0, 255).to(torch.uint8)
+    assert abs(score.peak_signal_noise_ratio(gt, recon) - S.peak_signal_noise_ratio(gt.cpu().numpy(), recon)) < 1e-9
+    assert abs(score.structural_similarity(gt, recon) - S.structural_similarity(gt.cpu().numpy(), recon)) < 1e-9
+    ckpt = tmp_path / "model=synthetic-epoch=0-step=0.ckpt"
+    synthetic.make_checkpoint(ckpt, synthetic.make_state_dict(5, "dense"))
+    psnr, ssim = score.calculate_scores(str(ckpt), scene, 8192)
+    assert np.isfinite(psnr) and 0.0 < psnr < 60.0 and -1.0 <= ssim <= 1.0

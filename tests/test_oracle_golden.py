@@ -149,3 +149,24 @@ def test_render_100(golden):
     diff = np.abs(im.astype(np.int32) - g["image"].astype(np.int32))
     assert diff.max() <= 1 and (diff > 0).mean() < 0.01, (diff.max(), (diff > 0).mean())
     assert O.psnr_uint8(im, g["image"]) > 60.0
+
+
+def test_score_oracle_known_answers():
+    """oracle/score_oracle.py restates scikit-image 0.18.3's PSNR / SSIM (score.py:33-37); skimage is not installable here, so
+    the restatement is pinned by closed-form cases only."""
+    from oracle import score_oracle as S
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, size=(40, 52, 3), dtype=np.uint8)
+    b = np.clip(a.astype(np.int16) + 1, 0, 255).astype(np.uint8)
+    b[a == 255] = 254                                              # |a - b| == 1 everywhere
+    assert abs(S.peak_signal_noise_ratio(a, b) - 20 * np.log10(255.0)) < 1e-12
+    assert abs(S.structural_similarity(a, a) - 1.0) < 1e-12
+    assert abs(S.structural_similarity(a, b) - S.structural_similarity(b, a)) < 1e-12          # symmetric
+    # two constant images: variances vanish, S = (2 x y + C1) / (x^2 + y^2 + C1) in every window
+    x, y = np.full((16, 16, 3), 100, np.uint8), np.full((16, 16, 3), 140, np.uint8)
+    c1 = (0.01 * 255) ** 2
+    assert abs(S.structural_similarity(x, y) - (2 * 100 * 140 + c1) / (100 ** 2 + 140 ** 2 + c1)) < 1e-12
+    # uncorrelated noise scores far below a lightly perturbed copy
+    noisy = np.clip(a.astype(np.int16) + rng.integers(-3, 4, size=a.shape), 0, 255).astype(np.uint8)
+    other = rng.integers(0, 256, size=a.shape, dtype=np.uint8)
+    assert S.structural_similarity(a, noisy) > 0.98 > 0.2 > S.structural_similarity(a, other)
