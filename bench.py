@@ -289,10 +289,10 @@ def main():
         o, d = dataloader.get_rays(H, W, focal, c2w, device=dev)
         return o.reshape(nrays, 3), d.reshape(nrays, 3)
 
-    def render(o, d):
-        with torch.no_grad():
-            for i in range(0, nrays, CHUNK):
-                out[i:i + CHUNK] = net.forward(o[i:i + CHUNK], d[i:i + CHUNK])["fine_rgb_rays"]
+    import nerf_helpers
+
+    def render(o, d):                         # the chunk loop of view_reconstruction (public API), fine colours into `out`
+        nerf_helpers.render_rays_chunked(net, o, d, CHUNK, out=out)
 
     def barrier():
         if world > 1:

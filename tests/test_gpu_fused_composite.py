@@ -203,3 +203,23 @@ def test_full_frame_is_independent_of_chunking_and_sharding():
             got, _, _ = render(4096, lo, hi)
             assert bits_equal(got, ref[lo:hi]), (ws, rank)
     torch.cuda.synchronize()
+
+
+def test_uniform_prefetch_keeps_the_random_stream():
+    """render_rays_chunked draws chunk i+1's uniforms on a side stream: same generator, same order, so a seeded render is bit
+    for bit the render without the prefetch."""
+    import dataloader
+    import nerf_helpers as h
+    net = make_net(5, "dense")
+    H = W = 72
+    o, d = dataloader.get_rays(H, W, 0.5 * W / 0.36, h.pose_spherical(-60.0, -30.0, 4.0), device=DEV)
+    frames = []
+    try:
+        for prefetch in (False, True, True):
+            h.PREFETCH_UNIFORMS = prefetch
+            torch.manual_seed(123)
+            frames.append(h.view_reconstruction(net, o, d, N=1000))          # 5184 rays: 6 chunks, ragged last one
+    finally:
+        h.PREFETCH_UNIFORMS = False
+    assert frames[0].dtype.name == "uint8" and frames[0].shape == (H, W, 3)
+    assert (frames[0] == frames[1]).all() and (frames[1] == frames[2]).all()
