@@ -20,25 +20,54 @@ constexpr int kThreads = kWarpsPerBlock * kWarp;
 // ------------------------------------------------------------------------------------------ K0 raygen
 struct Pose { float r[3][3]; float t[3]; };
 
+__device__ __forceinline__ void raygen_one(const Pose& pose, int W, float half_w, float half_h, float focal,
+                                           const int64_t* __restrict__ xs, const int64_t* __restrict__ ys, int64_t i, float (&dir)[3]) {
+    float col, row;
+    if (xs) { col = (float)xs[i]; row = (float)ys[i]; }
+    else    { col = (float)(i % W); row = (float)(i / W); }
+    // dataloader.py:39: [(i - W/2)/focal, -(j - H/2)/focal, -1], true fp32 divisions
+    const float d0 = __fdiv_rn(__fsub_rn(col, half_w), focal);
+    const float d1 = -__fdiv_rn(__fsub_rn(row, half_h), focal);
+    const float d2 = -1.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)   // dataloader.py:40: sum_j dirs_j * c2w[k,j], left to right
+        dir[k] = __fadd_rn(__fadd_rn(__fmul_rn(d0, pose.r[k][0]), __fmul_rn(d1, pose.r[k][1])), __fmul_rn(d2, pose.r[k][2]));
+}
+
+// One thread per FOUR consecutive rays: their 12 direction floats (and the 12 floats of the repeated origin) leave as three
+// 16-byte stores each, consecutive threads writing consecutive 48-byte runs (a 4-byte store per component touched every
+// sector three times: 0.6 TB/s; this form is bound by the launch, not the stores).  VEC = false: scalar tail / unaligned bases.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 raygen_kernel(Pose pose, int H, int W, float half_w, float half_h, float focal,
-              const int64_t* __restrict__ xs, const int64_t* __restrict__ ys, int64_t n,
+              const int64_t* __restrict__ xs, const int64_t* __restrict__ ys, int64_t first, int64_t n,
               float* __restrict__ o, float* __restrict__ d) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float col, row;
-        if (xs) { col = (float)xs[i]; row = (float)ys[i]; }
-        else    { col = (float)(i % W); row = (float)(i / W); }
-        // dataloader.py:39: [(i - W/2)/focal, -(j - H/2)/focal, -1], true fp32 divisions
-        const float d0 = __fdiv_rn(__fsub_rn(col, half_w), focal);
-        const float d1 = -__fdiv_rn(__fsub_rn(row, half_h), focal);
-        const float d2 = -1.0f;
+    if (VEC) {
+        const int64_t quads = (n - first) >> 2;
+        for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t i0 = first + 4 * q;
+            float v[12];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            // dataloader.py:40: sum_j dirs_j * c2w[k,j], left to right
-            const float s = __fadd_rn(__fadd_rn(__fmul_rn(d0, pose.r[k][0]), __fmul_rn(d1, pose.r[k][1])),
-                                      __fmul_rn(d2, pose.r[k][2]));
-            d[i * 3 + k] = s;
-            o[i * 3 + k] = pose.t[k];
+            for (int r = 0; r < 4; ++r) {
+                float dir[3];
+                raygen_one(pose, W, half_w, half_h, focal, xs, ys, i0 + r, dir);
+                v[3 * r] = dir[0]; v[3 * r + 1] = dir[1]; v[3 * r + 2] = dir[2];
+            }
+            float4* dp = (float4*)(d + i0 * 3);
+            float4* op = (float4*)(o + i0 * 3);
+            dp[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dp[1] = make_float4(v[4], v[5], v[6], v[7]);
+            dp[2] = make_float4(v[8], v[9], v[10], v[11]);
+            op[0] = make_float4(pose.t[0], pose.t[1], pose.t[2], pose.t[0]);
+            op[1] = make_float4(pose.t[1], pose.t[2], pose.t[0], pose.t[1]);
+            op[2] = make_float4(pose.t[2], pose.t[0], pose.t[1], pose.t[2]);
+        }
+    } else {
+        for (int64_t i = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            float dir[3];
+            raygen_one(pose, W, half_w, half_h, focal, xs, ys, i, dir);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { d[i * 3 + k] = dir[k]; o[i * 3 + k] = pose.t[k]; }
         }
     }
 }
@@ -636,8 +665,15 @@ extern "C" int nerf_raygen(const float* c2w_host, int H, int W, float focal, con
         for (int c = 0; c < 3; ++c) p.r[r][c] = c2w_host[r * 4 + c];
         p.t[r] = c2w_host[r * 4 + 3];
     }
-    raygen_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, H, W, (float)(W * .5), (float)(H * .5), focal,
-                                                                     xs, ys, n, o, d);
+    // four rays per thread with 16-byte stores where the output bases allow it, the (< 4 ray) remainder one ray per thread
+    const bool vec = ((((uintptr_t)o) | ((uintptr_t)d)) & 15) == 0 && n >= 4;
+    const int64_t n_vec = vec ? (n & ~(int64_t)3) : 0;
+    if (n_vec)
+        raygen_kernel<true><<<grid_for(n_vec / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, H, W, (float)(W * .5), (float)(H * .5), focal,
+                                                                                     xs, ys, 0, n_vec, o, d);
+    if (n_vec < n)
+        raygen_kernel<false><<<grid_for(n - n_vec, 256), 256, 0, (cudaStream_t)stream>>>(p, H, W, (float)(W * .5), (float)(H * .5), focal,
+                                                                                      xs, ys, n_vec, n, o, d);
     return check_launch("nerf_raygen");
 }
 

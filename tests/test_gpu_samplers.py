@@ -36,6 +36,15 @@ def test_raygen(golden, mods):
     n = golden["network"]
     o, d = dl.get_rays_at(800, 800, float(n["focal"]), T(n["c2w"]), T(n["xs"], DEV), T(n["ys"], DEV))
     assert bits_equal(o, n["o"]) and bits_equal(d, n["d"])
+    # ragged sizes: the kernel takes four rays per thread with 16-byte stores and finishes the remainder one ray per thread
+    pose = T(g["poses"][1])
+    for (Hh, Ww) in ((7, 9), (1, 1), (3, 1), (5, 5)):
+        o, d = dl.get_rays(Hh, Ww, 31.5, pose)
+        ro, rd = O.get_rays(Hh, Ww, 31.5, pose)
+        assert bits_equal(d, rd) and bits_equal(o, ro.expand(Hh, Ww, 3).contiguous()), (Hh, Ww)
+    xs, ys = T(n["xs"], DEV)[:1023], T(n["ys"], DEV)[:1023]
+    o, d = dl.get_rays_at(800, 800, float(n["focal"]), T(n["c2w"]), xs, ys)
+    assert bits_equal(o, n["o"][:1023]) and bits_equal(d, n["d"][:1023])
 
 
 def test_coarse_samples(golden, mods):

@@ -37,7 +37,7 @@ sig2, rgb2 = torch.relu(torch.randn(N, S, 1, device=dev) * 3 - 2), torch.rand(N,
 g = torch.randn(N, 3, device=dev)
 c2w = synthetic.orbit_pose(10.0, -30.0, 4.0)
 rows = [
-    ("raygen_kernel (800x800 grid x 40)", lambda: [dataloader.get_rays(800, 800, 1111.1, c2w) for _ in range(40)], 40 * 640000 * 24),
+    ("raygen_kernel (800x800 grid x 40; host-call bound: ~26 us per get_rays call)", lambda: [dataloader.get_rays(800, 800, 1111.1, c2w) for _ in range(40)], 40 * 640000 * 24),
     ("coarse_sample_kernel (ts only)", lambda: training and __import__("nerf_model"), 0),
 ]
 import nerf_model
@@ -48,6 +48,8 @@ rows += [
     ("composite_kernel<1> S=192", lambda: h.composite(sig2, rgb2, ts_all, want_weights=False), N * (20 * S + 20)),
     ("fine_sample_kernel (ts only would be less; writes pts+ts)", lambda: h.inverse_transform_sampling(o, d, w, ts, F, rand=(eps, u_f)),
      N * (24 + 4 * (2 * C + 1 + F) + 16 * F)),
+    ("fine_sample_merge_kernel (K3 + K4 in one launch, sorted ts only)", lambda: h.fine_depths_sorted(w, ts, F, rand=(eps, u_f)),
+     N * (4 * (2 * C + 1 + F) + 4 * S)),
     ("merge_sort_kernel (ts only)", lambda: h.merge_samples(o, d, fts, ts, want_points=False), N * (4 * S + 4 * S)),
     ("composite_backward_kernel S=192", lambda: training.composite_backward(sig2, rgb2, ts_all, g), N * (20 * S + 12 + 16 * S)),
 ]
@@ -55,4 +57,4 @@ print(f"HBM copy peak (measured): {peak:.0f} GB/s; N = {N} rays per launch")
 for name, fn, nbytes in rows:
     ms = timed(fn)
     gbs = nbytes / ms / 1e6
-    print(f"{name:58s} {ms:8.3f} ms  {gbs:8.1f} GB/s  {gbs/peak*100:5.1f} % of peak")
+    print(f"{name:80s} {ms:8.3f} ms  {gbs:8.1f} GB/s  {gbs/peak*100:5.1f} % of peak")
