@@ -37,6 +37,7 @@ _PROTOTYPES = {
     "nerf_mlp_forward_fp32": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "nerf_packed_bytes": (ctypes.c_size_t, []),
     "nerf_pack_weights": (_int, [_vp, _vp, _vp]),
+    "nerf_pack_weights_all": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "nerf_mlp_forward_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "nerf_mlp_forward_tc_train": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     "nerf_packed_t_bytes": (ctypes.c_size_t, []),

@@ -11,9 +11,7 @@ __constant__ pk::LayoutT c_pack_layout_t = pk::kLayoutT;
 
 struct PackParams { const float* p[20]; };
 
-__global__ void __launch_bounds__(256)
-pack_weights_kernel(PackParams P, uint8_t* __restrict__ packed) {
-    const int s = blockIdx.x;
+__device__ __forceinline__ void pack_forward_block(const PackParams& P, uint8_t* __restrict__ packed, int s) {
     if (s < pk::kStages) {
         const pk::Stage st = c_pack_layout.st[s];
         const float* W = P.p[2 * st.param];
@@ -38,8 +36,9 @@ pack_weights_kernel(PackParams P, uint8_t* __restrict__ packed) {
 }
 
 __global__ void __launch_bounds__(256)
-pack_weights_t_kernel(PackParams P, uint8_t* __restrict__ packed) {
-    const int s = blockIdx.x;
+pack_weights_kernel(PackParams P, uint8_t* __restrict__ packed) { pack_forward_block(P, packed, blockIdx.x); }
+
+__device__ __forceinline__ void pack_transposed_block(const PackParams& P, uint8_t* __restrict__ packed, int s) {
     if (s < pk::kStagesT) {
         const pk::Stage st = c_pack_layout_t.st[s];
         const float* W = P.p[2 * st.param];
@@ -56,9 +55,39 @@ pack_weights_t_kernel(PackParams P, uint8_t* __restrict__ packed) {
     }
 }
 
+__global__ void __launch_bounds__(256)
+pack_weights_t_kernel(PackParams P, uint8_t* __restrict__ packed) { pack_transposed_block(P, packed, blockIdx.x); }
+
+// Both images of both networks in one launch (after an optimiser step): blocks [0, 64) forward image of network 0,
+// [64, 117) its W^T image, then the same for network 1.
+struct PackAllParams { PackParams net[2]; uint8_t* fwd[2]; uint8_t* tr[2]; };
+constexpr int kPackBlocksPerNet = (pk::kStages + 1) + (pk::kStagesT + 1);
+
+__global__ void __launch_bounds__(256)
+pack_weights_all_kernel(PackAllParams A) {
+    const int net = blockIdx.x / kPackBlocksPerNet, b = blockIdx.x % kPackBlocksPerNet;
+    if (b <= pk::kStages) pack_forward_block(A.net[net], A.fwd[net], b);
+    else pack_transposed_block(A.net[net], A.tr[net], b - (pk::kStages + 1));
+}
+
 }  // namespace nerf
 
 using namespace nerf;
+
+extern "C" int nerf_pack_weights_all(const float* const* params40_host, void* packed0, void* packed_t0, void* packed1,
+                                     void* packed_t1, void* stream) {
+    NERF_REQUIRE(params40_host && packed0 && packed_t0 && packed1 && packed_t1, "nerf_pack_weights_all: null pointer");
+    NERF_REQUIRE(((((uintptr_t)packed0) | ((uintptr_t)packed_t0) | ((uintptr_t)packed1) | ((uintptr_t)packed_t1)) & 127) == 0,
+                 "nerf_pack_weights_all: buffers must be 128-byte aligned");
+    PackAllParams A;
+    for (int i = 0; i < 40; ++i) {
+        NERF_REQUIRE(params40_host[i], "nerf_pack_weights_all: params40_host[%d] is NULL", i);
+        A.net[i / 20].p[i % 20] = params40_host[i];
+    }
+    A.fwd[0] = (uint8_t*)packed0; A.tr[0] = (uint8_t*)packed_t0; A.fwd[1] = (uint8_t*)packed1; A.tr[1] = (uint8_t*)packed_t1;
+    pack_weights_all_kernel<<<2 * kPackBlocksPerNet, 256, 0, (cudaStream_t)stream>>>(A);
+    return check_launch("nerf_pack_weights_all");
+}
 
 extern "C" size_t nerf_packed_t_bytes(void) { return pk::kLayoutT.total_bytes; }
 

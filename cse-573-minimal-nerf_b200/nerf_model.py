@@ -214,6 +214,27 @@ class NeRFNetwork(LightningModule):
                      "coarse_weights": c["weights"], "coarse_sigma": aux["c_sigma"], "fine_sigma": aux["f_sigma"],
                      "coarse_rgb": aux["c_rgb"], "fine_rgb": aux["f_rgb"]}
 
+    def repack_all(self):
+        """All four bf16 weight images (forward + W^T, both networks) in one launch; called after every optimiser step, whose
+        in-place update does not bump the parameters' version counters (the keys the cached images are checked against)."""
+        nets = (self.coarse_network, self.fine_network)
+        if not all(n.uses_tensor_cores() for n in nets):
+            return self.invalidate_packed_weights()
+        params = nets[0].ordered_params() + nets[1].ordered_params()
+        keep = [nat.dev(p.detach(), "parameter") for p in params]
+        arr = (ctypes.c_void_p * 40)(*[p.data_ptr() for p in keep])
+        dev = params[0].device
+        for n in nets:
+            if n._packed is None or n._packed.device != dev:
+                n._packed = torch.empty(nat.lib().nerf_packed_bytes(), dtype=torch.uint8, device=dev)
+            if n._packed_t is None or n._packed_t.device != dev:
+                n._packed_t = torch.empty(nat.lib().nerf_packed_t_bytes(), dtype=torch.uint8, device=dev)
+        nat.check(nat.lib().nerf_pack_weights_all(arr, nat.ptr(nets[0]._packed), nat.ptr(nets[0]._packed_t), nat.ptr(nets[1]._packed),
+                                                  nat.ptr(nets[1]._packed_t), nat.stream()), "nerf_pack_weights_all")
+        for n in nets:
+            key = tuple((p.data_ptr(), p._version) for p in n.ordered_params())
+            n._packed_key = n._packed_t_key = key
+
     def invalidate_packed_weights(self):
         """Force a re-pack of the bf16 weight images on the next forward / backward (call after changing parameters
         through anything that does not bump tensor versions)."""
@@ -235,9 +256,9 @@ class NeRFNetwork(LightningModule):
         import optim
         # one hand-written kernel over flat parameter / gradient / moment buffers (csrc/adam.cu) instead of torch's
         # multi-tensor Adam.  It updates the parameters in place without bumping their version counters, which is what
-        # the packed bf16 weight images are keyed on: drop them explicitly after every step
+        # the packed bf16 weight images are keyed on: re-pack all four of them (one launch) after every step
         optimizer = optim.FlatAdam(self.parameters(), lr=start_lr)
-        optimizer.register_step_post_hook(lambda *args, **kwargs: self.invalidate_packed_weights())
+        optimizer.register_step_post_hook(lambda *args, **kwargs: self.repack_all())
         lr_decay = torch.optim.lr_scheduler.ExponentialLR(optimizer=optimizer, gamma=gamma)
         return {'optimizer': optimizer, 'lr_scheduler': lr_decay}
 

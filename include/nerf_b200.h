@@ -160,6 +160,12 @@ int nerf_mlp_composite_tc(const void* packed, const float* o, const float* d, co
                           float* sigma, float* rgb, void* act_out, void* mask_out,
                           float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream);
 
+/* Both weight images (nerf_pack_weights + nerf_pack_weights_t) of both networks in ONE launch - what a training step needs
+ * after the optimiser has changed the parameters.  params40_host: the 40 tensors of NeRFNetwork's state_dict order (coarse
+ * network's 20, then the fine network's 20). */
+int nerf_pack_weights_all(const float* const* params40_host, void* packed0, void* packed_t0, void* packed1, void* packed_t1,
+                          void* stream);
+
 /* ---- optimiser step.  nerf_model.py:134-143 (torch.optim.Adam, lr 5e-4, betas (0.9, 0.999), eps 1e-8, no weight decay)
  * over flat fp32 buffers of n elements (all parameters of both networks): params updated in place, exp_avg / exp_avg_sq
  * are the Adam moments, step >= 1 is the 1-based step count used for the bias corrections.  Same arithmetic and order as

@@ -171,3 +171,25 @@ def test_flat_adam_matches_torch_adam():
     run(5, opt_c, opt_b, sch_c, sch_b)
     for (name, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
         torch.testing.assert_close(pa.detach(), pb.detach(), rtol=5e-6, atol=1e-7, msg=lambda m: f"{name} after resume: {m}")
+
+
+def test_repack_all_matches_individual_packs():
+    """nerf_pack_weights_all (the optimiser's post-step hook: four images, one launch) writes exactly what the per-image packers
+    write, and the cached images are picked up by the next forward / backward."""
+    import nerf_model
+    net = nerf_model.NeRFNetwork()
+    net.load_state_dict(synthetic.make_state_dict(4, "dense"))
+    net = net.to(DEV)
+    nets = (net.coarse_network, net.fine_network)
+    before = [n.packed_weights().clone() for n in nets]
+    with torch.no_grad():
+        for p in net.parameters():
+            p.data.mul_(1.03)                       # in place through .data: no version bump, like the flat Adam kernel
+    net.repack_all()
+    got = [t.clone() for n in nets for t in (n._packed, n._packed_t)]
+    assert all(n.packed_weights() is n._packed for n in nets)               # keys are current: no re-pack on use
+    net.invalidate_packed_weights()
+    ref = [t.clone() for n in nets for t in (n.packed_weights(), n.packed_weights_t())]
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(got, ref))
+    assert not torch.equal(got[0], before[0]) and not torch.equal(got[2], before[1])
