@@ -149,13 +149,15 @@ __device__ __forceinline__ float dot_bf16x32(const uint32_t (&p)[16], const floa
 
 // training, 32 features of one row: bf16 activations (four 16-byte chunks, tiled chunk-major) + the 32-bit word of sign bits
 // pack32 collected (two-tile kernels only; pair j = features (2j, 2j+1) of the group -> bit 15-j / 31-j, 1 = pre-activation
-// negative = ReLU inactive).  `act_row` / `mask_row` point at this row's feature 0 / group 0.
-__device__ __forceinline__ void save_act32(__nv_bfloat16* __restrict__ act_row, uint32_t* __restrict__ mask_row, int feature,
+// negative = ReLU inactive).  `act` / `mask` point at this row's first feature of the group / its sign word: the callers keep
+// ONE running pointer pair per thread and reach both halves of a layer and both tiles through immediate offsets (the epilogue
+// warps are instruction-issue bound in the training form; a 64-bit address computation per store group was ~10 % of a task).
+__device__ __forceinline__ void save_act32(__nv_bfloat16* __restrict__ act, uint32_t* __restrict__ mask,
                                            const uint32_t (&p)[16], uint32_t signs) {
-    uint4* chunk = (uint4*)(act_row + (size_t)(feature >> 3) * 1024);
+    uint4* chunk = (uint4*)act;
 #pragma unroll
     for (int j = 0; j < 4; ++j) chunk[j * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-    mask_row[(size_t)(feature >> 5) * 128] = signs;
+    *mask = signs;
 }
 
 // dbg counters (PROFILE), per CTA x 16: 0 MMA warp total, 1 wait weights, 2 wait dfree, 3 wait alo/ahi, 4 wait PE,
@@ -456,10 +458,13 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             const int64_t row0 = (int64_t)tile_x * t3::kTileM + r;   // this thread's row in tile X (tile Y: + 128)
             const bool save0 = TRAIN, save1 = TRAIN && (tile_x + 1 < tile_end);
             // this thread's rows in the tiled chunk-major training tensors (pack_layout.cuh): feature 0 / sign-word group 0
-            __nv_bfloat16* const act_row0 = act_out + pk::tiled_offset(row0, 0, pk::kActChunks);
-            __nv_bfloat16* const act_row1 = act_row0 + (size_t)pk::kActChunks * 1024;
-            uint32_t* const mask_row0 = (uint32_t*)mask_out + ((row0 >> 7) * (2 * pk::kMaskWords)) * 128 + (row0 & 127);
-            uint32_t* const mask_row1 = mask_row0 + (size_t)(2 * pk::kMaskWords) * 128;
+            // running pointers: this thread's 32-feature group of the current layer in tile X; tile Y and the layer's second
+            // half (features + 128) sit at constant offsets, a layer advances them by 256 features
+            constexpr int kTileActStride = pk::kActChunks * 1024;            // elements between the same row of tiles X and Y
+            constexpr int kTileMaskStride = 2 * pk::kMaskWords * 128;        // 32-bit words
+            constexpr int kHalfActStride = (128 / 8) * 1024, kHalfMaskStride = (128 / 32) * 128;
+            __nv_bfloat16* ap = act_out + pk::tiled_offset(row0, 0, pk::kActChunks) + (size_t)(cq * 4) * 1024;
+            uint32_t* mp = (uint32_t*)mask_out + ((row0 >> 7) * (2 * pk::kMaskWords)) * 128 + (row0 & 127) + cq * 128;
             float sig_part[2] = {0.f, 0.f};
             // one hidden layer (both halves, both tiles); LAST = feature_fn.4: linear (nerf_model.py:347) and feeds density_fn.0
             auto hidden_layer = [&](auto last_tag, int layer) {
@@ -477,7 +482,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
                     const uint32_t sg0 = pack32<!LAST, TRAIN>(v, bias_s, hold[t]);
                     if (PROFILE && t == 0) { asm volatile("" ::"r"(hold[0][0]), "r"(hold[0][15])); tp[3] += clock64() - t_h0; }
-                    if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, layer * 256 + cq * 32, hold[t], sg0);
+                    if (t == 0 ? save0 : save1) save_act32(ap + t * kTileActStride, mp + t * kTileMaskStride, hold[t], sg0);
                     if (LAST) sig_part[t] = dot_bf16x32(hold[t], sW7 + cq * 32, sig_part[t]);
                 }
 #pragma unroll
@@ -500,9 +505,10 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     umma::tmem_wait_st();
                     warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
                     if (PROFILE && t == 0) tp[2] += clock64() - t_h1;
-                    if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, layer * 256 + 128 + cq * 32, p, sg1);
+                    if (t == 0 ? save0 : save1) save_act32(ap + t * kTileActStride + kHalfActStride, mp + t * kTileMaskStride + kHalfMaskStride, p, sg1);
                     if (LAST) sig_part[t] = dot_bf16x32(p, sW7 + 128 + cq * 32, sig_part[t]);
                 }
+                if (TRAIN) { ap += 2 * kHalfActStride; mp += 2 * kHalfMaskStride; }       // next layer: + 256 features
             };
 #pragma unroll 1
             for (int layer = 0; layer < 6; ++layer) hidden_layer(std::false_type{}, layer);
@@ -525,7 +531,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 umma::tmem_st16(a_addr, p);                           // r features 0..127 -> A columns 0..63
                 umma::tmem_wait_st();
                 warp_arrive(bars + 8u * (t3::kBarALo + t), lane);
-                if (t == 0 ? save0 : save1) save_act32(t ? act_row1 : act_row0, t ? mask_row1 : mask_row0, 1792 + cq * 32, p, sgr);
+                if (t == 0 ? save0 : save1) save_act32(ap + t * kTileActStride, mp + t * kTileMaskStride, p, sgr);   // feature 1792 + cq * 32
             }
             // ---- rgb_fn.2: columns 0..2 -> sigmoid(. + b) (nerf_model.py:358-359); sigma = relu(feat . w7 + b7)
 #pragma unroll

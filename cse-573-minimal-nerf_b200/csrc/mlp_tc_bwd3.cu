@@ -25,6 +25,13 @@ __device__ __forceinline__ uint32_t drop_mask(uint32_t s) {
     asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(r) : "r"(s));
     return r;
 }
+// the same from bits 7 / 23 (the msbs of bytes 0 and 2): pair 8 + k of a sign word needs only the shift by k that pair k needs,
+// so 16 pairs cost 7 shifts instead of 15
+__device__ __forceinline__ uint32_t drop_mask_lo(uint32_t s) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xAA88;" : "=r"(r) : "r"(s));
+    return r;
+}
 
 namespace b3 {
 constexpr uint32_t kOffDr = 0;                                    // dr tiles of X and Y: 2 x 2 K-blocks x [128 x 64] bf16
@@ -171,8 +178,8 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
             umma::tc_fence_after();
             ++nd[t];
         };
-        auto store_dz = [&](__nv_bfloat16* dz_row, int feature, const uint32_t* p) {
-            uint4* dst = (uint4*)(dz_row + (size_t)(feature >> 3) * 1024);
+        auto store_dz = [&](__nv_bfloat16* dz_at, const uint32_t* p) {
+            uint4* dst = (uint4*)dz_at;
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i * 128] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
         };
@@ -183,11 +190,13 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
             float dsg[2];
             dsg[0] = (row0 < total) ? dsigma_pre[row0] : 0.f;
             dsg[1] = (row0 + 128 < total) ? dsigma_pre[row0 + 128] : 0.f;
-            // this thread's rows in the tiled chunk-major tensors: feature 0 of dz, sign-word group 0 of the masks
-            __nv_bfloat16* const dz_row0 = dz_out + pk::tiled_offset(row0, 0, pk::kDzChunks);
-            __nv_bfloat16* const dz_row1 = dz_row0 + (size_t)pk::kDzChunks * 1024;
-            const uint32_t* const mask_row0 = masks32 + ((row0 >> 7) * (2 * pk::kMaskWords)) * 128 + (row0 & 127);
-            const uint32_t* const mask_row1 = mask_row0 + (size_t)(2 * pk::kMaskWords) * 128;
+            // this thread's place in the tiled chunk-major tensors as ONE running pointer pair (the epilogue is instruction-issue
+            // bound): its 32-feature group of layer 6 in tile X; tile Y and a layer's second half sit at constant offsets, every
+            // chain step moves the pointers back by 256 features
+            constexpr int kTileDzStride = pk::kDzChunks * 1024, kHalfDzStride = (128 / 8) * 1024;       // bf16 elements
+            constexpr int kTileMaskStride = 2 * pk::kMaskWords * 128, kHalfMaskStride = (128 / 32) * 128;   // 32-bit words
+            __nv_bfloat16* dzp = dz_out + pk::tiled_offset(row0, 0, pk::kDzChunks) + (size_t)(6 * 32 + cq * 4) * 1024;
+            const uint32_t* mkp = masks32 + ((row0 >> 7) * (2 * pk::kMaskWords)) * 128 + (row0 & 127) + (6 * 8 + cq) * 128;
             // one step of the chain (both halves, both tiles).  FIRST: dz6 = accumulator + dsigma_pre (x) w7 (density head,
             // nerf_model.py:351), no mask (feature_fn.4 is linear); otherwise the ReLU mask of layer j's saved output is applied
             // to the packed pair (bits 15-i / 31-i of the sign word -> 0xFFFF fields).  j > 0: dz_j is the next A operand.
@@ -201,7 +210,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                         const bool st = (t == 0) || st1;
                         const int col0 = h * 128 + cq * 32;
                         uint32_t mb = 0xFFFFFFFFu;
-                        if (!FIRST && st) mb = __ldg((t ? mask_row1 : mask_row0) + (size_t)((j * 256 + col0) >> 5) * 128);
+                        if (!FIRST && st) mb = __ldg(mkp + t * kTileMaskStride + h * kHalfMaskStride);
                         const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
                         const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(cq * 16);
                         wait_d(t);
@@ -226,17 +235,22 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                             }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                p[i] = umma::pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & ~drop_mask(mb << i);
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t sh = mb << i;
+                                p[i] = umma::pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & ~drop_mask(sh);
+                                p[i + 8] = umma::pack_bf16(__uint_as_float(v[2 * i + 16]), __uint_as_float(v[2 * i + 17])) & ~drop_mask_lo(sh);
+                            }
                         }
                         if (h == 1 && j > 0) {
                             umma::tmem_st16(a_addr + 64, pk_);
                             umma::tmem_wait_st();
                             warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
                         }
-                        if (st) store_dz(t ? dz_row1 : dz_row0, j * 256 + col0, p);     // rows past `total` carry zeros
+                        if (st) store_dz(dzp + t * kTileDzStride + h * kHalfDzStride, p);     // rows past `total` carry zeros
                     }
                 }
+                dzp -= 2 * kHalfDzStride;
+                mkp -= 2 * kHalfMaskStride;
             };
             chain_step(std::true_type{}, 6);
 #pragma unroll 1
