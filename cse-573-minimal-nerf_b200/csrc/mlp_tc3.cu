@@ -244,7 +244,13 @@ __device__ __forceinline__ void composite_groups(const FusedComposite& fc, const
     }
 }
 
-template <bool PROFILE, bool TRAIN, bool COMP>
+// MC form (COMP only; launched as 2-CTA clusters): the two CTAs of a cluster share every weight stage - each fetches HALF of it
+// from L2 and multicasts that half into both shared memories (`cp.async.bulk ... .multicast::cluster`), which halves the
+// L2 -> SM weight stream once more (0.46 MB per tile pair and CTA).  Nothing else is shared: MMAs, TMEM and epilogues stay
+// per CTA; the only cross-CTA dependency is the recycling of a ring slot, whose release commits go to both CTAs' `empty`
+// barriers (count 4) - eight slots deep, off the MMA -> epilogue -> MMA loop that sank the cta_group::2 kernel (mlp_tc2.cu).
+// Both CTAs run the same number of pairs (the one with fewer tiles ends on a fully masked pair).
+template <bool PROFILE, bool TRAIN, bool COMP, bool MC>
 __global__ void __launch_bounds__(t3::kThreads, 1)
 mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_rays, const float* __restrict__ d_rays,
                const float* __restrict__ ts, const float* __restrict__ samples, int64_t total, int S,
@@ -267,7 +273,22 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
     // (tile indices are 32-bit: 2^32 tiles would be 5 x 10^11 samples)
     uint32_t tile0, tile_stride, tile_end, n_local;
     int64_t g0 = 0;
-    if (COMP) {
+    const uint32_t rank = MC ? (blockIdx.x & 1u) : 0u;          // CTA rank in its 2-CTA cluster (1-D grid: blocks 2c, 2c + 1)
+    if (COMP && MC) {
+        // the cluster's groups [G0, G1) are cut in the middle; both CTAs run max(own, peer) pairs
+        const int64_t nc = gridDim.x >> 1, c = blockIdx.x >> 1;
+        const int64_t G0 = fc.num_groups * c / nc, G1 = fc.num_groups * (c + 1) / nc, mid = G0 + (G1 - G0 + 1) / 2;
+        auto tiles_of = [&](int64_t a, int64_t b) -> int64_t {
+            int64_t e = b * fc.group_tiles < num_tiles ? b * fc.group_tiles : num_tiles;
+            return e > a * fc.group_tiles ? e - a * fc.group_tiles : 0;
+        };
+        g0 = rank ? mid : G0;
+        const int64_t own = tiles_of(rank ? mid : G0, rank ? G1 : mid), peer = tiles_of(rank ? G0 : mid, rank ? mid : G1);
+        tile0 = (uint32_t)(g0 * fc.group_tiles);
+        tile_end = tile0 + (uint32_t)own;
+        tile_stride = 2;
+        n_local = (uint32_t)(((own > peer ? own : peer) + 1) / 2);
+    } else if (COMP) {
         g0 = fc.num_groups * blockIdx.x / gridDim.x;
         const int64_t g1 = fc.num_groups * (blockIdx.x + 1) / gridDim.x;
         tile0 = (uint32_t)(g0 * fc.group_tiles);
@@ -285,7 +306,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
     if (tid == 0) {
         uint64_t* b = (uint64_t*)(smem + t3::kOffBars);
         for (int i = 0; i < t3::kOutSlots; ++i) { umma::mbar_init(&b[t3::kBarOutFull + i], 4); umma::mbar_init(&b[t3::kBarOutEmpty + i], t3::kPEWarps); }
-        for (int i = 0; i < t3::kSlots; ++i) { umma::mbar_init(&b[t3::kBarFull + i], 1); umma::mbar_init(&b[t3::kBarEmpty + i], 2); }
+        for (int i = 0; i < t3::kSlots; ++i) { umma::mbar_init(&b[t3::kBarFull + i], 1); umma::mbar_init(&b[t3::kBarEmpty + i], MC ? 4 : 2); }
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&b[t3::kBarDFull + i], 1);
             umma::mbar_init(&b[t3::kBarDFree + i], t3::kEpiWarps);
@@ -312,6 +333,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
     }
     umma::tc_fence_before();
     __syncthreads();
+    if (MC) umma::cluster_sync_all();          // the peer's barriers exist before anything is multicast at them
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
@@ -334,7 +356,13 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     if (leader) {
                         const StageRef st = c_stages3.s[s];
                         umma::mbar_arrive_expect_tx_u32(bars + 8u * (t3::kBarFull + slot), st.bytes);
-                        umma::bulk_g2s_u32(ring + slot * t3::kSlotBytes, packed + st.offset, st.bytes, bars + 8u * (t3::kBarFull + slot));
+                        if (MC) {          // this CTA's half of the stage, into both CTAs' slots
+                            const uint32_t half = st.bytes >> 1;
+                            umma::bulk_g2s_mc_u32(ring + slot * t3::kSlotBytes + rank * half, packed + st.offset + rank * half, half,
+                                                  bars + 8u * (t3::kBarFull + slot), (uint16_t)3);
+                        } else {
+                            umma::bulk_g2s_u32(ring + slot * t3::kSlotBytes, packed + st.offset, st.bytes, bars + 8u * (t3::kBarFull + slot));
+                        }
                     }
                     __syncwarp();
                 }
@@ -345,7 +373,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             const bool elected = umma::elect_one();
             const long long t_begin = PROFILE ? clock64() : 0;
             if (warp == 1) {
-                MmaTile<0, PROFILE> m;
+                MmaTile<0, PROFILE, MC> m;
                 m.init(bars, sbase + t3::kOffRing, tmem, elected);
                 if (PROFILE) m.detail = sbase + t3::kOffDetail;
                 m.run(sbase, n_local);
@@ -358,7 +386,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     dbg[blockIdx.x * 16 + 8] = n_local;
                 }
             } else {
-                MmaTile<1, PROFILE> m;
+                MmaTile<1, PROFILE, MC> m;
                 m.init(bars, sbase + t3::kOffRing, tmem, elected);
                 m.run(sbase, n_local);
             }
@@ -376,7 +404,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
             // pair, everything that is left
             if (COMP)
                 composite_groups(fc, ts, S, g0, smem, bars, comp_lt,
-                                 it == n_local ? ntl + (uint32_t)fc.group_tiles - 1u : (it >= 2u ? 2u * (it - 1u) : 0u), ntl,
+                                 it == n_local ? ntl + (uint32_t)fc.group_tiles - 1u : (it >= 2u ? min(2u * (it - 1u), ntl) : 0u), ntl,
                                  warp - 20, lane, sStat + 2 * (warp - 20));
             if (it == n_local) break;
 #pragma unroll 1
@@ -456,7 +484,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
         for (uint32_t it = 0; it < n_local; ++it) {
             const uint32_t tile_x = tile0 + it * tile_stride;
             const int64_t row0 = (int64_t)tile_x * t3::kTileM + r;   // this thread's row in tile X (tile Y: + 128)
-            const bool save0 = TRAIN, save1 = TRAIN && (tile_x + 1 < tile_end);
+            const bool save0 = TRAIN && (tile_x < tile_end), save1 = TRAIN && (tile_x + 1 < tile_end);
             // this thread's rows in the tiled chunk-major training tensors (pack_layout.cuh): feature 0 / sign-word group 0
             // running pointers: this thread's 32-feature group of the current layer in tile X; tile Y and the layer's second
             // half (features + 128) sit at constant offsets, a layer advances them by 256 features
@@ -581,7 +609,14 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
     }
     umma::tc_fence_before();
     __syncthreads();
+    if (MC) umma::cluster_sync_all();          // neither CTA leaves while its peer can still write into its ring / signal its barriers
     if (warp == 2) umma::tmem_dealloc(tmem, 512);
+}
+
+// NERF_TC_MULTICAST=0 turns the 2-CTA-cluster weight multicast of the COMP form off (diagnostic A/B)
+static bool use_multicast() {
+    static const bool v = [] { const char* e = getenv("NERF_TC_MULTICAST"); return !(e && e[0] == '0'); }();
+    return v;
 }
 
 // Fused compositing needs whole 32-sample chunks per ray and a ray group (whole rays = whole tiles) that fits the output ring
@@ -601,15 +636,19 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
                    const CompositeOutputs* comp) {
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
         if (e != cudaSuccess) { set_error("nerf_mlp_forward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
         attr_set = true;
     }
@@ -631,11 +670,29 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
         // at least two tiles per CTA where possible, so that both halves of a pair do useful work
         int64_t want = (tiles + 1) / 2;
         if (want > fc.num_groups) want = fc.num_groups;
-        const int grid = (int)(want < num_sms() ? want : num_sms());
+        int grid = (int)(want < num_sms() ? want : num_sms());
+        if (use_multicast() && grid >= 2) {               // 2-CTA clusters sharing every weight stage by multicast
+            grid &= ~1;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(t3::kThreads); cfg.dynamicSmemBytes = t3::kSmemBytes; cfg.stream = st;
+            cudaLaunchAttribute attr{};
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            const float* no_samples = nullptr;
+            long long* no_dbg = nullptr;
+            __nv_bfloat16* no_act = nullptr;
+            unsigned long long* no_mask = nullptr;
+            cudaError_t e = act_out
+                ? cudaLaunchKernelEx(&cfg, mlp_tc3_kernel<false, true, true, true>, pw, o, d, ts, no_samples, total, S, sigma, rgb, ao, mo, no_dbg, fc)
+                : cudaLaunchKernelEx(&cfg, mlp_tc3_kernel<false, false, true, true>, pw, o, d, ts, no_samples, total, S, sigma, rgb, no_act, no_mask, no_dbg, fc);
+            if (e != cudaSuccess) { set_error("nerf_mlp_composite_tc: cluster launch: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
+            return check_launch("nerf_mlp_composite_tc");
+        }
         if (act_out)
-            mlp_tc3_kernel<false, true, true><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, nullptr, total, S, sigma, rgb, ao, mo, nullptr, fc);
+            mlp_tc3_kernel<false, true, true, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, nullptr, total, S, sigma, rgb, ao, mo, nullptr, fc);
         else
-            mlp_tc3_kernel<false, false, true><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, nullptr, total, S, sigma, rgb, nullptr, nullptr, nullptr, fc);
+            mlp_tc3_kernel<false, false, true, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, nullptr, total, S, sigma, rgb, nullptr, nullptr, nullptr, fc);
         return check_launch("nerf_mlp_composite_tc");
     }
     int grid = (int)(pairs < num_sms() ? pairs : num_sms());
@@ -644,11 +701,11 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
         if (e && atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
     }
     if (dbg)
-        mlp_tc3_kernel<true, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, dbg, fc);
+        mlp_tc3_kernel<true, false, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, dbg, fc);
     else if (act_out)                                 // training form: also stores activations + sign words
-        mlp_tc3_kernel<false, true, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, ao, mo, nullptr, fc);
+        mlp_tc3_kernel<false, true, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, ao, mo, nullptr, fc);
     else
-        mlp_tc3_kernel<false, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, nullptr, fc);
+        mlp_tc3_kernel<false, false, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, nullptr, fc);
     return check_launch("nerf_mlp_forward_tc");
 }
 

@@ -57,7 +57,9 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {     // TME
 // BOTH warps have committed it (empty barriers count 2), so every stage is still fetched once per tile pair.
 // Every address is a 32-bit shared-memory / TMEM address held in a register.
 // PROFILE counters: prof[1] wait weights, [2] wait dfree, [3] wait alo/ahi, [4] wait PE, [0] time inside issue blocks.
-template <int T, bool PROFILE>
+// MC: the weight ring is filled by multicast copies shared with the peer CTA of a 2-CTA cluster (mlp_tc3.cu); a slot may be
+// refilled only when BOTH CTAs are done with it, so the stage-release commits go to both CTAs' empty barriers.
+template <int T, bool PROFILE, bool MC = false>
 struct MmaTile {
     static constexpr uint32_t kI128 = umma::make_idesc_bf16(128, 128);
     static constexpr uint32_t kI16 = umma::make_idesc_bf16(128, 16);
@@ -124,6 +126,10 @@ struct MmaTile {
         ++n_step;
     }
     __device__ __forceinline__ void pass_turn() { umma::mbar_arrive_u32(bar(t3::kBarTurn + T)); }   // leader lane, after its MMAs
+    __device__ __forceinline__ void release(uint32_t empty_bar_addr) {                              // weight stage consumed
+        if (MC) umma::mma_commit_mc_u32(empty_bar_addr, (uint16_t)3);
+        else umma::mma_commit_u32(empty_bar_addr);
+    }
     // a hidden layer's second-half task stores K blocks 0,1 of the new operand (and waits for the store) BEFORE it signals
     // dfree: after begin_step() they are known to be written; alo is only signalled by rgb_fn.0's task (for rgb_fn.2)
     __device__ __forceinline__ void lo_implied() {}
@@ -168,7 +174,7 @@ struct MmaTile {
         fence();
         issue([&] {
             mma_pe<4>(descPE, b);
-            umma::mma_commit_u32(empty_bar(0));
+            release(empty_bar(0));
             umma::mma_commit_u32(bar(t3::kBarDFull + T));
             pass_turn();
         });
@@ -193,17 +199,17 @@ struct MmaTile {
             if (PE) {
                 mma_pe<NK>(descA, bP);
                 if (pe_done_idx) umma::mma_commit_u32(bar(pe_done_idx + T));
-                umma::mma_commit_u32(e_p);
+                release(e_p);
             }
             mma8(0, k0, k1, PE ? 1u : 0u);
-            umma::mma_commit_u32(e_0);
-            umma::mma_commit_u32(e_1);
+            release(e_0);
+            release(e_1);
             if (!FIRST_HALF) {
                 mma4(64, k2, 1u);
-                umma::mma_commit_u32(e_2);
+                release(e_2);
                 pass_turn();            // early: the other issuer needs ~200 clk to wake up; this tile's last 4 MMAs cover it
                 mma4(96, k3, 1u);
-                umma::mma_commit_u32(e_3);
+                release(e_3);
                 umma::mma_commit_u32(bar(t3::kBarDFull + T));
             }
         });
@@ -214,10 +220,10 @@ struct MmaTile {
             fence();
             issue([&] {
                 mma4(64, k2, 1u);
-                umma::mma_commit_u32(e_2);
+                release(e_2);
                 pass_turn();
                 mma4(96, k3, 1u);
-                umma::mma_commit_u32(e_3);
+                release(e_3);
                 umma::mma_commit_u32(bar(t3::kBarDFull + T));
             });
         }
@@ -238,7 +244,7 @@ struct MmaTile {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma::mma_ts(d, a + 32u * kb + 8u * k, bdesc + (uint64_t)(kb * 128 + 2 * k), kI16, (kb | k) ? 1u : 0u);
             }
-            umma::mma_commit_u32(empty_bar(0));
+            release(empty_bar(0));
             umma::mma_commit_u32(bar(t3::kBarDFull + T));
             pass_turn();
         });
@@ -259,8 +265,8 @@ struct MmaTile {
                 for (int k = 0; k < 4; ++k)
                     umma::mma_ss(d, descDr + (uint64_t)(kb * 1024 + 2 * k), bdesc + (uint64_t)(2 * k), kI128, (kb | k) ? 1u : 0u);
             }
-            umma::mma_commit_u32(e_0);
-            umma::mma_commit_u32(e_1);
+            release(e_0);
+            release(e_1);
             if (last) umma::mma_commit_u32(bar(t3::kBarPexEmpty + T));          // dr tile no longer read
             umma::mma_commit_u32(bar(t3::kBarDFull + T));
             pass_turn();

@@ -219,6 +219,18 @@ __device__ __forceinline__ void bulk_g2s_u32(uint32_t smem_dst, const void* gmem
 __device__ __forceinline__ void mma_commit_u32(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// the same arrive on the barrier at this offset in EVERY CTA of `mask` (1-CTA MMAs whose operand slots are shared by a cluster)
+__device__ __forceinline__ void mma_commit_mc_u32(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+// bulk copy global -> the same shared-memory offset of every CTA in `mask`; each destination CTA's barrier (same offset) gets
+// the complete_tx of the bytes it received
+__device__ __forceinline__ void bulk_g2s_mc_u32(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar), "h"(mask)
+                 : "memory");
+}
 
 // ------------------------------------------------------------------ CTA-pair (cta_group::2) / cluster variants
 __device__ __forceinline__ uint32_t cluster_ctarank() {
