@@ -223,3 +223,17 @@ def test_uniform_prefetch_keeps_the_random_stream():
         h.PREFETCH_UNIFORMS = False
     assert frames[0].dtype.name == "uint8" and frames[0].shape == (H, W, 3)
     assert (frames[0] == frames[1]).all() and (frames[1] == frames[2]).all()
+
+
+def test_single_cta_form_without_multicast():
+    """NERF_TC_MULTICAST=0 selects the COMP kernel without 2-CTA clusters (read once per process): the same parity cases in a
+    subprocess, so both launch forms stay covered."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, NERF_TC_MULTICAST="0")
+    here = os.path.abspath(__file__)
+    res = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-k",
+                          "fused_matches_two_launch_path or training_form_saves"], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "passed" in res.stdout
