@@ -10,9 +10,10 @@
 // Work decomposition (one launch per network, one CTA per SM):
 //   a "job" = up to four 128-row A blocks (halves of a layer's dz, or halves of feat / r for the two small heads) that all
 //   multiply the SAME B operand (a 256-wide activation block and / or a recomputed PE tile); block i accumulates into its
-//   own TMEM region D_i[128 x (b_cols + pe_cols)] (fp32).  10 jobs (table below); each is split-K over the 128-sample
-//   tiles among a fixed group of CTAs.  Per tile a CTA reads every operand once: ~1.1 MB per tile over all jobs against
-//   0.96 MB of acts + dz, the minimum.  At the end every CTA adds its partial D (and bias sums) to the fp32 gradients with
+//   own TMEM region D_i[128 x (b_cols + pe_cols)] (fp32).  9 jobs (table below); each is split-K over the 128-sample
+//   tiles among a fixed group of CTAs.  Per tile a CTA reads every operand once: 1.03 MB per tile over all jobs against
+//   0.96 MB of acts + dz, the minimum (dz of feature_fn.0 is read by two jobs; feat used to be, until the density head's
+//   product feat^T . dsigma moved into the rgb_fn.0 job, where feat is resident as the B tile).  At the end every CTA adds its partial D (and bias sums) to the fp32 gradients with
 //   atomics.
 // Per CTA: warp 0 issues the A-block bulk copies (2 x 32 KB ring), warp 2 the B-tile copies (2 x 64 KB ring), warp 1 issues
 // tcgen05.mma (M128 x N<=256 x K16, both operands MN-major from shared memory), warps 4-7 sum the dz blocks' columns for
@@ -32,7 +33,9 @@ constexpr uint32_t kPEBytes = 16384;       // [128 samples x 64] recomputed enco
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffB = kSlots * kABytes;                       // 65536
 constexpr uint32_t kOffPE = kOffB + kSlots * kBBytes;              // 196608
-constexpr uint32_t kOffBars = kOffPE + kPEBytes;                   // 212992 (single PE buffer)
+constexpr uint32_t kHeadsBytes = 4096;     // [128 samples x 16] dz heads block (density job folded into rgb_fn.0's)
+constexpr uint32_t kOffHeads = kOffPE + kPEBytes;                  // 212992 (single PE buffer), 2 x 4 KB
+constexpr uint32_t kOffBars = kOffHeads + kSlots * kHeadsBytes;    // 221184
 constexpr uint32_t kOffTmemHolder = kOffBars + 16 * 8;
 constexpr uint32_t kSmemBytes = kOffTmemHolder + 16 + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -61,28 +64,30 @@ struct Job {
     uint8_t out_kind;
     uint8_t heads_bias;   // 1: db of the two heads = column sums of the B tile (the dz heads block)
     uint8_t ctas;         // CTAs that split this job's tiles
+    uint8_t dens;         // 1: the B tile is feat: its two 128-feature halves, used as A operands against the dz heads block
+                          //    (4 KB more per tile), also give dW(density_fn.0) - feat is not read a second time by a job of its own
 };
 
 // dz feature offsets: layer k's pre-activation gradient at 256 k (k = 0..6), rgb_fn.0 at 1792, heads block at 1920.
 // acts feature offsets: output of layer k at 256 k, rgb_fn.0 output r at 1792.
 #define NB {0, 0, 0, 0, 0, 0, 0}
-__constant__ Job c_jobs[10] = {
+__constant__ Job c_jobs[9] = {
     // dz0 and dz4 halves x PE(x): dW(mlp.0)[:, 0:60] and dW(feature_fn.0)[:, 256:316], and both layers' biases
     {4, {{SRC_DZ, 0, 0, 0, 60, 0, 1}, {SRC_DZ, 128, 0, 128, 60, 0, 1}, {SRC_DZ, 1024, 4, 0, 316, 256, 1}, {SRC_DZ, 1152, 4, 128, 316, 256, 1}},
-     0, SRC_ACTS, 0, PE_X, 60, OUT_NORMAL, 0, 23},
-    {2, {{SRC_DZ, 256, 1, 0, 256, 0, 1}, {SRC_DZ, 384, 1, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 0, PE_NONE, 0, OUT_NORMAL, 0, 17},      // mlp.2
-    {2, {{SRC_DZ, 512, 2, 0, 256, 0, 1}, {SRC_DZ, 640, 2, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 256, PE_NONE, 0, OUT_NORMAL, 0, 17},    // mlp.4
-    {2, {{SRC_DZ, 768, 3, 0, 256, 0, 1}, {SRC_DZ, 896, 3, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 512, PE_NONE, 0, OUT_NORMAL, 0, 17},    // mlp.6
-    {2, {{SRC_DZ, 1024, 4, 0, 316, 0, 0}, {SRC_DZ, 1152, 4, 128, 316, 0, 0}, NB, NB}, 16, SRC_ACTS, 768, PE_NONE, 0, OUT_NORMAL, 0, 16},  // feature_fn.0 (h3 part)
-    {2, {{SRC_DZ, 1280, 5, 0, 256, 0, 1}, {SRC_DZ, 1408, 5, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1024, PE_NONE, 0, OUT_NORMAL, 0, 16}, // feature_fn.2
-    {2, {{SRC_DZ, 1536, 6, 0, 256, 0, 1}, {SRC_DZ, 1664, 6, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1280, PE_NONE, 0, OUT_NORMAL, 0, 16}, // feature_fn.4
-    {1, {{SRC_DZ, 1792, 8, 0, 280, 256, 1}, NB, NB, NB}, 16, SRC_ACTS, 1536, PE_DIR, 24, OUT_NORMAL, 0, 10},                             // rgb_fn.0: [feat | PE(dir)]
-    {2, {{SRC_ACTS, 1536, 7, 0, 256, 0, 0}, {SRC_ACTS, 1664, 7, 128, 256, 0, 0}, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_DENSITY, 0, 10},  // density_fn.0: feat^T . heads
-    {1, {{SRC_ACTS, 1792, 9, 0, 128, 0, 0}, NB, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_RGB, 1, 6},                                    // rgb_fn.2: r^T . heads (+ head biases)
+     0, SRC_ACTS, 0, PE_X, 60, OUT_NORMAL, 0, 25, 0},
+    {2, {{SRC_DZ, 256, 1, 0, 256, 0, 1}, {SRC_DZ, 384, 1, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 0, PE_NONE, 0, OUT_NORMAL, 0, 17, 0},      // mlp.2
+    {2, {{SRC_DZ, 512, 2, 0, 256, 0, 1}, {SRC_DZ, 640, 2, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 256, PE_NONE, 0, OUT_NORMAL, 0, 17, 0},    // mlp.4
+    {2, {{SRC_DZ, 768, 3, 0, 256, 0, 1}, {SRC_DZ, 896, 3, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 512, PE_NONE, 0, OUT_NORMAL, 0, 18, 0},    // mlp.6
+    {2, {{SRC_DZ, 1024, 4, 0, 316, 0, 0}, {SRC_DZ, 1152, 4, 128, 316, 0, 0}, NB, NB}, 16, SRC_ACTS, 768, PE_NONE, 0, OUT_NORMAL, 0, 17, 0},  // feature_fn.0 (h3 part)
+    {2, {{SRC_DZ, 1280, 5, 0, 256, 0, 1}, {SRC_DZ, 1408, 5, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1024, PE_NONE, 0, OUT_NORMAL, 0, 18, 0}, // feature_fn.2
+    {2, {{SRC_DZ, 1536, 6, 0, 256, 0, 1}, {SRC_DZ, 1664, 6, 128, 256, 0, 1}, NB, NB}, 16, SRC_ACTS, 1280, PE_NONE, 0, OUT_NORMAL, 0, 17, 0}, // feature_fn.4
+    // rgb_fn.0: dz_r^T . [feat | PE(dir)], and with feat resident also density_fn.0: feat^T . heads (column 0 = dsigma)
+    {1, {{SRC_DZ, 1792, 8, 0, 280, 256, 1}, NB, NB, NB}, 16, SRC_ACTS, 1536, PE_DIR, 24, OUT_NORMAL, 0, 12, 1},
+    {1, {{SRC_ACTS, 1792, 9, 0, 128, 0, 0}, NB, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_RGB, 1, 7, 0},                                 // rgb_fn.2: r^T . heads (+ head biases)
 };
 #undef NB
-constexpr int kNumJobs = 10;
-constexpr int kGridCtas = 23 + 3 * 17 + 3 * 16 + 10 + 10 + 6;     // 148: CTA shares follow the measured per-tile cost of each job
+constexpr int kNumJobs = 9;
+constexpr int kGridCtas = 25 + (17 + 17 + 18) + (17 + 18 + 17) + 12 + 7;          // 148: CTA shares follow the measured per-tile cost of each job
                                                                  // (tools/profile_wgrad.py: the PE(x) job recomputes 60 sin/cos per row and is
                                                                  // issue-bound, the 256-wide jobs are HBM-bound), not its bytes
 }  // namespace wg
@@ -169,8 +174,11 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
                 const uint32_t slot = it & 1, ph = (it >> 1) & 1;
                 umma::mbar_wait(&emptyB[slot], ph ^ 1);
                 if (leader) {
-                    umma::mbar_arrive_expect_tx(&fullB[slot], b_bytes);
+                    umma::mbar_arrive_expect_tx(&fullB[slot], b_bytes + (job.dens ? wg::kHeadsBytes : 0u));
                     umma::bulk_g2s(smem + wg::kOffB + slot * wg::kBBytes, b_base + tile * (int64_t)bsrc_chunks * 1024, b_bytes, &fullB[slot]);
+                    if (job.dens)          // the dz heads block [128 x 16] of the same tile
+                        umma::bulk_g2s(smem + wg::kOffHeads + slot * wg::kHeadsBytes, dz + (tile * pk::kDzChunks + (1920 >> 3)) * 1024,
+                                       wg::kHeadsBytes, &fullB[slot]);
                 }
                 __syncwarp();
             }
@@ -210,6 +218,18 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
                 __syncwarp();
             }
             if (leader) {
+                if (job.dens) {            // density_fn.0: the two 128-feature halves of the resident feat tile as A operands, N = 16
+                    const uint32_t b_addr = umma::smem_u32(smem + wg::kOffB + bslot * wg::kBBytes);
+                    const uint32_t h_addr = umma::smem_u32(smem + wg::kOffHeads + bslot * wg::kHeadsBytes);
+                    const uint32_t idesc16 = umma::make_idesc_bf16(128, 16) | kMN;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma::mma_ss(tmem + (uint32_t)(nA * region_cols + 16 * h),
+                                         umma::make_desc_mn_interleave(b_addr + h * 32768 + k * 256, 2048, 128),
+                                         umma::make_desc_mn_interleave(h_addr + k * 256, 2048, 128), idesc16, (it | (uint32_t)k) != 0);
+                }
                 if (b_cols > 0) umma::mma_commit(&emptyB[bslot]);
                 if (has_pe) umma::mma_commit(pe_empty);
             }
@@ -363,6 +383,15 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
 #pragma unroll
                         for (int c = 0; c < 3; ++c) atomicAdd(dW + c * 128 + m, __uint_as_float(v[1 + c]));   // rgb_fn.2.weight [3,128]
                     }
+                }
+            }
+            if (job.dens) {                // density_fn.0.weight [1,256]: column 0 (dsigma) of the two feat halves' products
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[4];
+                    umma::tmem_ld4(tmem + lane_base + (uint32_t)(nA * region_cols + 16 * h), v);
+                    umma::tmem_wait_ld();
+                    atomicAdd(G.p[14] + h * 128 + m, __uint_as_float(v[0]));
                 }
             }
         }
