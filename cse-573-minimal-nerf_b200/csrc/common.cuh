@@ -23,6 +23,25 @@ constexpr unsigned kFull = 0xffffffffu;
         }                                           \
     } while (0)
 
+// 16-byte / 4-byte stores of the training tensors (activations, sign words, dz): written once, read by a later kernel
+#ifndef NERF_STREAMING_STORES
+#define NERF_STREAMING_STORES 1
+#endif
+__device__ __forceinline__ void store_once(uint4* p, uint4 v) {
+#if NERF_STREAMING_STORES
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void store_once(uint32_t* p, uint32_t v) {
+#if NERF_STREAMING_STORES
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

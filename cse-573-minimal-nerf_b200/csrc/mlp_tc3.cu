@@ -65,8 +65,13 @@ constexpr uint32_t kDensityStageOffset = make_merged_table().s[31].offset;     /
 // `signs` (training form): one funnel shift per element collects the SIGN bits of the biased pre-activations - even elements
 // (low bf16 halves) into bits 15..0, odd elements into bits 31..16, pair j at bit 15-j / 31-j - i.e. the complement of the
 // ReLU mask, which the dgrad kernel applies as p & ~mask.
+#ifndef NERF_INTERLEAVE_STORES
+#define NERF_INTERLEAVE_STORES 1
+#endif
+// `early` (training form, may be null): the 16-byte chunk of 8 features is stored to the saved-activation tensor as soon as it
+// is packed, so that a task's stores trickle into the memory pipe instead of arriving as one 16-warp burst at its end.
 template <bool RELU, bool SIGNS>
-__device__ __forceinline__ uint32_t pack32(const uint32_t (&v)[32], uint32_t bias_saddr, uint32_t* p) {
+__device__ __forceinline__ uint32_t pack32(const uint32_t (&v)[32], uint32_t bias_saddr, uint32_t* p, uint4* early = nullptr) {
     uint32_t s_lo = 0u, s_hi = 0u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -88,6 +93,8 @@ __device__ __forceinline__ uint32_t pack32(const uint32_t (&v)[32], uint32_t bia
         }
         p[2 * j + 0] = RELU ? umma::pack_bf16_relu(x0, x1) : umma::pack_bf16(x0, x1);
         p[2 * j + 1] = RELU ? umma::pack_bf16_relu(x2, x3) : umma::pack_bf16(x2, x3);
+        if (NERF_INTERLEAVE_STORES && early && (j & 1))
+            store_once(early + (j >> 1) * 128, make_uint4(p[2 * j - 2], p[2 * j - 1], p[2 * j], p[2 * j + 1]));
     }
     return (s_hi << 16) | s_lo;
 }
@@ -154,10 +161,12 @@ __device__ __forceinline__ float dot_bf16x32(const uint32_t (&p)[16], const floa
 // warps are instruction-issue bound in the training form; a 64-bit address computation per store group was ~10 % of a task).
 __device__ __forceinline__ void save_act32(__nv_bfloat16* __restrict__ act, uint32_t* __restrict__ mask,
                                            const uint32_t (&p)[16], uint32_t signs) {
-    uint4* chunk = (uint4*)act;
+    if (!NERF_INTERLEAVE_STORES) {         // (otherwise pack32 has stored the four chunks already)
+        uint4* chunk = (uint4*)act;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) chunk[j * 128] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-    *mask = signs;
+        for (int j = 0; j < 4; ++j) store_once(chunk + j * 128, make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]));
+    }
+    store_once(mask, signs);
 }
 
 // dbg counters (PROFILE), per CTA x 16: 0 MMA warp total, 1 wait weights, 2 wait dfree, 3 wait alo/ahi, 4 wait PE,
@@ -508,7 +517,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     umma::tmem_ld32(d_addr, v);
                     umma::tmem_wait_ld();
                     warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
-                    const uint32_t sg0 = pack32<!LAST, TRAIN>(v, bias_s, hold[t]);
+                    const uint32_t sg0 = pack32<!LAST, TRAIN>(v, bias_s, hold[t], (t == 0 ? save0 : save1) ? (uint4*)(ap + t * kTileActStride) : nullptr);
                     if (PROFILE && t == 0) { asm volatile("" ::"r"(hold[0][0]), "r"(hold[0][15])); tp[3] += clock64() - t_h0; }
                     if (t == 0 ? save0 : save1) save_act32(ap + t * kTileActStride, mp + t * kTileMaskStride, hold[t], sg0);
                     if (LAST) sig_part[t] = dot_bf16x32(hold[t], sW7 + cq * 32, sig_part[t]);
@@ -528,7 +537,7 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                     warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);       // = accumulator free AND K blocks 0,1 of the new operand written
                     if (PROFILE && t == 0) { asm volatile("" ::"r"(v[31])); tp[1] += clock64() - t_h1; }
                     uint32_t p[16];
-                    const uint32_t sg1 = pack32<!LAST, TRAIN>(v, bias_s + 512u, p);
+                    const uint32_t sg1 = pack32<!LAST, TRAIN>(v, bias_s + 512u, p, (t == 0 ? save0 : save1) ? (uint4*)(ap + t * kTileActStride + kHalfActStride) : nullptr);
                     umma::tmem_st16(a_addr + 64, p);                  // features 128..255 -> A columns 64..127
                     umma::tmem_wait_st();
                     warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
@@ -555,7 +564,8 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                 umma::tmem_ld32(d_addr, v);
                 umma::tmem_wait_ld();
                 warp_arrive(bars + 8u * (t3::kBarDFree + t), lane);
-                const uint32_t sgr = pack32<true, TRAIN>(v, sbase + t3::kOffBias + 4u * (uint32_t)(pk::kBiasR0 + cq * 32), p);
+                const uint32_t sgr = pack32<true, TRAIN>(v, sbase + t3::kOffBias + 4u * (uint32_t)(pk::kBiasR0 + cq * 32), p,
+                                                         (t == 0 ? save0 : save1) ? (uint4*)(ap + t * kTileActStride) : nullptr);
                 umma::tmem_st16(a_addr, p);                           // r features 0..127 -> A columns 0..63
                 umma::tmem_wait_st();
                 warp_arrive(bars + 8u * (t3::kBarALo + t), lane);

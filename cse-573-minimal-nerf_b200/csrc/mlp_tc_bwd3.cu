@@ -33,6 +33,12 @@ __device__ __forceinline__ uint32_t drop_mask_lo(uint32_t s) {
     return r;
 }
 
+// Storing every dz chunk as soon as it is packed (instead of the task's four chunks at its end) helps the forward kernel's
+// training form by 1 % and costs this kernel 0.7 % (tools/ab_build_flag.sh): off here.
+#ifndef NERF_INTERLEAVE_STORES_BWD
+#define NERF_INTERLEAVE_STORES_BWD 0
+#endif
+
 namespace b3 {
 constexpr uint32_t kOffDr = 0;                                    // dr tiles of X and Y: 2 x 2 K-blocks x [128 x 64] bf16
 constexpr uint32_t kOffRing = t3::kOffRing;                       // 65536
@@ -181,7 +187,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
         auto store_dz = [&](__nv_bfloat16* dz_at, const uint32_t* p) {
             uint4* dst = (uint4*)dz_at;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i * 128] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) store_once(dst + i * 128, make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]));
         };
 
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
@@ -239,6 +245,13 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                                 const uint32_t sh = mb << i;
                                 p[i] = umma::pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & ~drop_mask(sh);
                                 p[i + 8] = umma::pack_bf16(__uint_as_float(v[2 * i + 16]), __uint_as_float(v[2 * i + 17])) & ~drop_mask_lo(sh);
+#if NERF_INTERLEAVE_STORES_BWD
+                                if (st && (i & 3) == 3) {       // chunks i / 4 and i / 4 + 2 are complete: let them go now
+                                    uint4* dst = (uint4*)(dzp + t * kTileDzStride + h * kHalfDzStride);
+                                    store_once(dst + (i >> 2) * 128, make_uint4(p[i - 3], p[i - 2], p[i - 1], p[i]));
+                                    store_once(dst + ((i >> 2) + 2) * 128, make_uint4(p[i + 5], p[i + 6], p[i + 7], p[i + 8]));
+                                }
+#endif
                             }
                         }
                         if (h == 1 && j > 0) {
@@ -246,7 +259,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                             umma::tmem_wait_st();
                             warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
                         }
-                        if (st) store_dz(dzp + t * kTileDzStride + h * kHalfDzStride, p);     // rows past `total` carry zeros
+                        if (st && (FIRST || !NERF_INTERLEAVE_STORES_BWD)) store_dz(dzp + t * kTileDzStride + h * kHalfDzStride, p);     // rows past `total` carry zeros
                     }
                 }
                 dzp -= 2 * kHalfDzStride;
