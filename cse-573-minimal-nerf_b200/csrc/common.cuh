@@ -27,16 +27,14 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef NERF_STREAMING_STORES
 #define NERF_STREAMING_STORES 1
 #endif
-__device__ __forceinline__ void store_once(uint4* p, uint4 v) {
-#if NERF_STREAMING_STORES
+// (NERF_STREAMING_STORES: 0 plain st.global, 1 st.global.cs, 2 st.global.wt, 3 st.global.cg - A/B with tools/ab_build_flag.sh)
+template <class T> __device__ __forceinline__ void store_once(T* p, T v) {
+#if NERF_STREAMING_STORES == 1
     __stcs(p, v);
-#else
-    *p = v;
-#endif
-}
-__device__ __forceinline__ void store_once(uint32_t* p, uint32_t v) {
-#if NERF_STREAMING_STORES
-    __stcs(p, v);
+#elif NERF_STREAMING_STORES == 2
+    __stwt(p, v);
+#elif NERF_STREAMING_STORES == 3
+    __stcg(p, v);
 #else
     *p = v;
 #endif
