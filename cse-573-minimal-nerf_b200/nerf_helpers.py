@@ -193,7 +193,8 @@ def render_rays_chunked(model, o, d, N=4096, out=None):
     if out is None:
         out = torch.empty((n, 3), device=o.device, dtype=torch.float32)
     C, Fn = getattr(model, "coarse_samples", None), getattr(model, "fine_samples", None)
-    prefetch = PREFETCH_UNIFORMS and C is not None and Fn is not None and n > N
+    direct = C is not None and Fn is not None and hasattr(model, "coarse_network") and out.is_contiguous()
+    prefetch = PREFETCH_UNIFORMS and direct and n > N
     main = torch.cuda.current_stream(o.device)
     side = _side_stream(o.device) if prefetch else None
 
@@ -216,7 +217,9 @@ def render_rays_chunked(model, o, d, N=4096, out=None):
                 if i + N < n:
                     nxt = draw(min(N, n - i - N))
                 main.wait_event(ev)
-                out[i:i + N] = model.forward(o[i:i + N], d[i:i + N], rand=rand)['fine_rgb_rays']
+                model.forward(o[i:i + N], d[i:i + N], rand=rand, fine_out=out[i:i + N])
+            elif direct:
+                model.forward(o[i:i + N], d[i:i + N], fine_out=out[i:i + N])          # the kernel writes into the frame buffer
             else:
                 out[i:i + N] = model.forward(o[i:i + N], d[i:i + N])['fine_rgb_rays']
     return out

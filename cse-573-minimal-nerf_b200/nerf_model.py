@@ -137,11 +137,12 @@ class NeRFModel(nn.Module):
         """True when render_rays can run (tensor-core shape, sample count the fused kernel supports)."""
         return self.uses_tensor_cores() and bool(nat.lib().nerf_mlp_composite_tc_supported(int(S)))
 
-    def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False, stats=None):
+    def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False, stats=None, out=None):
         """Network + alpha compositing in ONE kernel (nerf_mlp_composite_tc): the per-sample sigma / rgb stay on the SM
         unless `keep_samples` (or `save`, the training form, which also stores activations + ReLU sign words).
         Returns the same dict as nerf_helpers.composite plus 'sigma', 'rgb_samples', 'saved' (None when not kept).
-        `stats`: optional ZEROED [4] fp32 buffer for the density statistics (one is allocated otherwise)."""
+        `stats`: optional ZEROED [4] fp32 buffer for the density statistics (one is allocated otherwise); `out`: optional
+        contiguous [N,3] fp32 tensor the ray colours are written into (e.g. a slice of the frame buffer)."""
         N, S = ts.shape[0], ts.shape[1]
         dv = ts.device
         keep = keep_samples or save
@@ -154,7 +155,9 @@ class NeRFModel(nn.Module):
             acts = torch.empty((rows * training.ACT,), device=dv, dtype=torch.bfloat16)
             masks = torch.empty((rows * (training.ACT // 64),), device=dv, dtype=torch.int64)
         w = torch.empty((N, S, 1), device=dv, dtype=torch.float32) if want_weights else None
-        col = torch.empty((N, 3), device=dv, dtype=torch.float32)
+        if out is not None and (out.shape != (N, 3) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dv):
+            raise ValueError("render_rays: `out` must be a contiguous [N,3] fp32 tensor on the rays' device")
+        col = out if out is not None else torch.empty((N, 3), device=dv, dtype=torch.float32)
         depth = torch.empty((N,), device=dv, dtype=torch.float32)
         acc = torch.empty((N,), device=dv, dtype=torch.float32)
         if stats is None:
@@ -186,8 +189,10 @@ class NeRFNetwork(LightningModule):
         self.last = {}                      # depth / acc / weights of the most recent forward
         self.keep_samples = False           # True: inference passes also materialise per-sample sigma / rgb in self.last
 
-    def forward(self, o_rays, d_rays, rand=None):
+    def forward(self, o_rays, d_rays, rand=None, fine_out=None):
         """rand = (u_c [N,C], eps [N,1], u_f [N,F,1]) replaces the three torch.rand draws when given.
+        fine_out (inference only): contiguous [N,3] fp32 tensor that receives 'fine_rgb_rays' directly (a slice of a frame
+        buffer: saves the copy of view_reconstruction's chunk loop).
         With gradients enabled the result is differentiable w.r.t. the 40 parameters (training.RenderFunction)."""
         import training
         o, d = nat.dev(o_rays, "o_rays"), nat.dev(d_rays, "d_rays")
@@ -199,7 +204,7 @@ class NeRFNetwork(LightningModule):
             ordered = self.coarse_network.ordered_params() + self.fine_network.ordered_params()
             c_rgb, f_rgb = training.RenderFunction.apply(self, o, d, u_c, eps, u_f, *ordered)
         else:
-            c_rgb, f_rgb, aux = training.forward_pass(self, o, d, rand, save=False, keep_samples=self.keep_samples)
+            c_rgb, f_rgb, aux = training.forward_pass(self, o, d, rand, save=False, keep_samples=self.keep_samples, fine_out=fine_out)
             self._publish(aux)
         return {'fine_rgb_rays': f_rgb, 'coarse_rgb_rays': c_rgb}
 

@@ -195,7 +195,23 @@ def mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray):
 FUSE_COMPOSITE = True       # network + compositing in one kernel where the sample counts allow it (64 / 128 / 192 / 256)
 
 
-def forward_pass(net, o, d, rand, save, keep_samples=False):
+_stats_pool = {}            # (device, stream) -> [zeroed fp32 block, next free float]: one memset per 64 forwards instead of one each
+
+
+def _zeroed_stats8(dv):
+    """8 zeroed floats (the density statistics of both networks) cut from a pooled block.  Views handed out earlier keep their
+    block alive, so the logged statistics of earlier forwards stay valid."""
+    key = (dv, torch.cuda.current_stream(dv).cuda_stream)      # the memset is ordered on the stream that will use the floats
+    ent = _stats_pool.get(key)
+    if ent is None or ent[1] + 8 > ent[0].numel():
+        ent = [torch.zeros((8 * 64,), device=dv, dtype=F32), 0]
+        _stats_pool[key] = ent
+    out = ent[0][ent[1]:ent[1] + 8]
+    ent[1] += 8
+    return out
+
+
+def forward_pass(net, o, d, rand, save, keep_samples=False, fine_out=None):
     """Shared by inference and training: returns (coarse_rgb, fine_rgb, aux dict).  With the fused kernel the per-sample
     sigma / rgb of an inference pass are only materialised when `keep_samples` (aux['c_sigma'] ... are None otherwise)."""
     N, C, Fn = o.shape[0], net.coarse_samples, net.fine_samples
@@ -206,7 +222,7 @@ def forward_pass(net, o, d, rand, save, keep_samples=False):
     c_ts = net._coarse_ts(o, d, u_c)
     fused = FUSE_COMPOSITE and net.coarse_network.can_composite(C) and net.fine_network.can_composite(C + Fn)
     if fused:       # network + compositing in one kernel; render keeps no per-sample outputs at all
-        stats8 = torch.zeros((8,), device=dv, dtype=F32)        # density statistics of both networks, one memset
+        stats8 = _zeroed_stats8(dv)                              # density statistics of both networks
         c = net.coarse_network.render_rays(o, d, c_ts, want_weights=True, keep_samples=keep_samples, save=save, stats=stats8[:4])
         c_sigma, c_rgb, c_acts = c["sigma"], c["rgb_samples"], c["saved"]
     else:
@@ -223,7 +239,8 @@ def forward_pass(net, o, d, rand, save, keep_samples=False):
         _, f_ts = nerf_helpers.inverse_transform_sampling(o, d, c["weights"], c_ts, Fn, rand=(eps, u_f))
         _, ts = nerf_helpers.merge_samples(o, d, f_ts, c_ts, want_points=False)
     if fused:
-        f = net.fine_network.render_rays(o, d, ts, want_weights=False, keep_samples=keep_samples, save=save, stats=stats8[4:])
+        f = net.fine_network.render_rays(o, d, ts, want_weights=False, keep_samples=keep_samples, save=save, stats=stats8[4:],
+                                         out=fine_out)
         f_sigma, f_rgb, f_acts = f["sigma"], f["rgb_samples"], f["saved"]
     else:
         if save:
@@ -234,6 +251,8 @@ def forward_pass(net, o, d, rand, save, keep_samples=False):
         f = nerf_helpers.composite(f_sigma, f_rgb, ts, want_weights=False)
     aux = {"c": c, "f": f, "c_ts": c_ts, "ts": ts, "c_sigma": c_sigma, "c_rgb": c_rgb, "f_sigma": f_sigma, "f_rgb": f_rgb,
            "c_acts": c_acts, "f_acts": f_acts}
+    if fine_out is not None and f["rgb"] is not fine_out:      # two-launch path: the compositing kernel allocated its own output
+        fine_out.copy_(f["rgb"])
     return c["rgb"], f["rgb"], aux
 
 
