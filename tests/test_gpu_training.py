@@ -112,6 +112,7 @@ def test_short_optimisation_reduces_loss():
 def test_dgrad_kernel_matches_library_chain():
     """Hand-written tcgen05 dgrad chain vs the same chain as cuBLAS GEMMs + elementwise ops, several tiles per CTA and a
     ragged last tile: all 20 gradients of one network."""
+    import library_backward
     import training
     torch.manual_seed(1)
     net = make_net(4, "dense")
@@ -123,8 +124,8 @@ def test_dgrad_kernel_matches_library_chain():
     sigma, rgb, acts = training.mlp_forward_train(model, o, d, ts)
     g_ray = torch.randn(N, 3, device=DEV) / N
     got = training.mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray)                   # tcgen05 dgrad + tcgen05 wgrad
-    mid = training.mlp_backward_library_wgrad(model, o, d, ts, sigma, rgb, acts, g_ray)     # tcgen05 dgrad + cuBLAS wgrad
-    ref = training.mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray)         # everything as library ops
+    mid = library_backward.mlp_backward_library_wgrad(model, o, d, ts, sigma, rgb, acts, g_ray)     # tcgen05 dgrad + cuBLAS wgrad
+    ref = library_backward.mlp_backward_reference(model, o, d, ts, sigma, rgb, acts, g_ray)         # everything as library ops
     torch.cuda.synchronize()
     names = [n for n, _ in model.named_parameters()]
     for name, a, m, b in zip(names, got, mid, ref):
