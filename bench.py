@@ -108,10 +108,15 @@ def run_reference(args, rank, world):
     import synthetic
     from oracle import nerf_oracle as O
     torch.set_num_threads(os.cpu_count())
+    on_gpu = args.reference_device == "cuda"
     sd = synthetic.make_state_dict(5, "dense")
     c2w, focal = frame_setup(args.hw, args.hw, 0)
     o, d = O.get_rays(args.hw, args.hw, focal, c2w)
     o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+    if on_gpu:                                         # the port's factory calls (arange, full, ...) follow the default device
+        torch.set_default_device("cuda")
+        sd = {k: v.cuda() for k, v in sd.items()}
+        o, d = o.cuda(), d.cuda()
     n = min(CHUNK, o.shape[0])                         # bounded sample: one 4096-ray chunk per step
 
     def step(k):
@@ -119,6 +124,8 @@ def run_reference(args, rank, world):
         rand = (torch.rand(n, COARSE), torch.rand(n, 1), torch.rand(n, FINE, 1))
         with torch.no_grad():
             O.network_forward(sd, o[lo:lo + n], d[lo:lo + n], *rand)
+        if on_gpu:
+            torch.cuda.synchronize()
     for k in range(args.warmup):
         step(k)
     t0 = time.perf_counter()
@@ -126,13 +133,16 @@ def run_reference(args, rank, world):
         step(args.warmup + k)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     v = n / dt
-    sample = f"one {n}-ray chunk of the {args.hw}x{args.hw} frame per step (no_grad), CPU oracle port of the reference"
+    sample = (f"one {n}-ray chunk of the {args.hw}x{args.hw} frame per step (no_grad), oracle port of the reference "
+              + ("as eager PyTorch fp32 on the GPU (torch ops, cuBLAS GEMMs; wall clock with a synchronize per step)" if on_gpu
+                 else "on the CPU"))
     emit({
         "impl": "reference", "metric": "rays/sec render (device-timed)", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": 0 if on_gpu else os.cpu_count(), "kind": "port", "sample": sample},
+        "reference_device": args.reference_device,
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -250,6 +260,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hw", type=int, default=800, help="frame height = width")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' runs the same eager-PyTorch port of the reference on the GPU (what the "
+                         "reference itself does when a GPU is present); the contract arm is the default, 'cpu'")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
