@@ -133,6 +133,27 @@ def run_reference(args, rank, world):
         step(args.warmup + k)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     v = n / dt
+    train = None
+    if on_gpu:          # the reference's training step (forward, loss, autograd, torch.optim.Adam) in eager PyTorch on the GPU
+        leaf = {k: t.clone().requires_grad_(True) for k, t in sd.items()}
+        opt = torch.optim.Adam(list(leaf.values()), lr=5e-4)
+        target = torch.rand(n, 3)
+
+        def tstep():
+            rand = (torch.rand(n, COARSE), torch.rand(n, 1), torch.rand(n, FINE, 1))
+            loss, _ = O.training_loss(leaf, o[:n], d[:n], target, *rand)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            torch.cuda.synchronize()
+        for _ in range(2):
+            tstep()
+        t1 = time.perf_counter()
+        for _ in range(max(args.steps, 1)):
+            tstep()
+        tdt = (time.perf_counter() - t1) / max(args.steps, 1)
+        train = {"metric": "rays/sec train", "value": n / tdt, "unit": "rays/s", "ms_per_step": tdt * 1e3,
+                 "what": "forward + MSE losses + autograd backward + torch.optim.Adam on one 4096-ray batch, eager PyTorch fp32"}
     sample = (f"one {n}-ray chunk of the {args.hw}x{args.hw} frame per step (no_grad), oracle port of the reference "
               + ("as eager PyTorch fp32 on the GPU (torch ops, cuBLAS GEMMs; wall clock with a synchronize per step)" if on_gpu
                  else "on the CPU"))
@@ -142,7 +163,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": 0 if on_gpu else os.cpu_count(), "kind": "port", "sample": sample},
-        "reference_device": args.reference_device,
+        "reference_device": args.reference_device, "train": train,
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
