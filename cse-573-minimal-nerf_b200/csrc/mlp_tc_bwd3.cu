@@ -35,6 +35,11 @@ __device__ __forceinline__ uint32_t drop_mask_lo(uint32_t s) {
 
 // Storing every dz chunk as soon as it is packed (instead of the task's four chunks at its end) helps the forward kernel's
 // training form by 1 % and costs this kernel 0.7 % (tools/ab_build_flag.sh): off here.
+// 1: a chain step requests its four sign words up front (dgrad 0.976 -> 0.964 ms; requesting them a whole step ahead
+// measured the same and is not kept)
+#ifndef NERF_BWD_MASK_PREFETCH
+#define NERF_BWD_MASK_PREFETCH 1
+#endif
 #ifndef NERF_INTERLEAVE_STORES_BWD
 #define NERF_INTERLEAVE_STORES_BWD 0
 #endif
@@ -209,14 +214,29 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
             auto chain_step = [&](auto first_tag, int j) {
                 constexpr bool FIRST = decltype(first_tag)::value;
                 uint32_t hold[2][16];
+#if NERF_BWD_MASK_PREFETCH
+                // the step's four sign words are requested up front: only the first task can still see their (HBM) latency
+                uint32_t mbq[2][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}};
+                if (!FIRST) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int t = 0; t < 2; ++t)
+                            if (t == 0 || st1) mbq[h][t] = __ldg(mkp + t * kTileMaskStride + h * kHalfMaskStride);
+                }
+#endif
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
                         const bool st = (t == 0) || st1;
                         const int col0 = h * 128 + cq * 32;
+#if NERF_BWD_MASK_PREFETCH
+                        const uint32_t mb = mbq[h][t];
+#else
                         uint32_t mb = 0xFFFFFFFFu;
                         if (!FIRST && st) mb = __ldg(mkp + t * kTileMaskStride + h * kHalfMaskStride);
+#endif
                         const uint32_t d_addr = tmem + lane_base + t3::kColD + 128u * (uint32_t)t + (uint32_t)(cq * 32);
                         const uint32_t a_addr = tmem + lane_base + t3::kColA + 128u * (uint32_t)t + (uint32_t)(cq * 16);
                         wait_d(t);
