@@ -20,7 +20,12 @@
 // 16 epilogue warps on every task.
 //
 // Warps (768 threads): 0,3 weight producers | 1 MMA issuer of tile X | 2 TMEM allocation + MMA issuer of tile Y |
-// 4-19 epilogue (both tiles) | 20-23 PE producers (both tiles).  Register budgets are re-balanced with setmaxnreg.
+// 4-19 epilogue (both tiles) | 20-23 PE producers (both tiles; in the COMP form they also composite finished rays).
+// Register budgets are re-balanced with setmaxnreg.
+//
+// Template forms: PROFILE (cycle counters), TRAIN (also stores bf16 activations + ReLU sign words), COMP (alpha compositing
+// inside the kernel: CTAs own whole ray groups, see FusedComposite below), MC (COMP launched as 2-CTA clusters that share
+// every weight stage through multicast bulk copies).  The render / training paths use <false, false|true, true, true>.
 //
 // Steps per tile (16): mlp.0 h0,h1 | mlp.2/4/6, feature_fn.0/2/4 h0,h1 | rgb_fn.0 | rgb_fn.2 (density_fn.0: CUDA cores, see below).
 // Barriers per tile t: dfull[t] (MMA -> epilogue, accumulator complete), dfree[t] (accumulator read into registers),
