@@ -516,6 +516,26 @@ extern "C" int nerf_mlp_composite_tc(const void* packed, const float* o, const f
     NERF_REQUIRE(nerf_mlp_composite_tc_supported(S),
                  "nerf_mlp_composite_tc: S = %d is not supported (needs S %% 32 == 0 and a ray group of at most 6 tiles); "
                  "use nerf_mlp_forward_tc + nerf_composite", S);
-    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4};
+    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4, nullptr, nullptr, 0.f, nullptr};
     return launch_mlp_tc3(packed, o, d, ts, nullptr, N * S, S, sigma, rgb, act_out, mask_out, stream, nullptr, &comp);
+}
+
+// The coarse network's form: K1 (generate_coarse_samples, nerf_helpers.py:28-56) runs inside the kernel too.  u [N,S] uniforms,
+// t_base [S] = the reference's torch.arange(near, far, step), ts_out [N,S] receives the depths t = t_base[i] + u * step (bit-identical
+// to nerf_coarse_sample); everything else as nerf_mlp_composite_tc.
+extern "C" int nerf_mlp_composite_tc_strata(const void* packed, const float* o, const float* d, const float* u, const float* t_base,
+                                            float step, int64_t N, int S, float* ts_out, float* sigma, float* rgb, void* act_out,
+                                            void* mask_out, float* weights, float* ray_rgb, float* depth, float* acc, float* stats4,
+                                            void* stream) {
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_composite_tc_strata: bad size N=%lld S=%d", (long long)N, S);
+    if (N == 0) return 0;
+    NERF_REQUIRE(packed && o && d && u && t_base && ts_out && ray_rgb, "nerf_mlp_composite_tc_strata: null pointer");
+    NERF_REQUIRE((sigma == nullptr) == (rgb == nullptr), "nerf_mlp_composite_tc_strata: sigma and rgb go together");
+    NERF_REQUIRE((act_out == nullptr) == (mask_out == nullptr), "nerf_mlp_composite_tc_strata: act_out and mask_out go together");
+    NERF_REQUIRE(!act_out || sigma, "nerf_mlp_composite_tc_strata: the training form also needs sigma / rgb");
+    NERF_REQUIRE(((uintptr_t)packed & 127) == 0, "nerf_mlp_composite_tc_strata: packed buffer must be 128-byte aligned");
+    NERF_REQUIRE(!act_out || ((uintptr_t)act_out & 15) == 0, "nerf_mlp_composite_tc_strata: act_out must be 16-byte aligned");
+    NERF_REQUIRE(nerf_mlp_composite_tc_supported(S), "nerf_mlp_composite_tc_strata: S = %d is not supported", S);
+    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4, u, t_base, step, ts_out};
+    return launch_mlp_tc3(packed, o, d, nullptr, nullptr, N * S, S, sigma, rgb, act_out, mask_out, stream, nullptr, &comp);
 }

@@ -193,7 +193,20 @@ struct FusedComposite {
     float* stats;        // [4] or null: sum sigma^2, count sigma != 0, sqrt(sum sigma^2) (published by the last CTA), ticket
     int group_rays, group_tiles;
     int64_t num_groups, N;
+    // K1 inside the kernel (coarse network): when u_c is given the PE warps form the stratified depths themselves,
+    // t = t_base[i] + u_c[n, i] * step (nerf_helpers.py:52-53, the arithmetic of coarse_sample_kernel), store them to ts_gen
+    // [N,S] for the fine sampler, and the compositing reads them back from there
+    const float* u_c;
+    const float* t_base;
+    float step;
+    float* ts_gen;
 };
+
+__device__ __forceinline__ float ld_coherent(const float* p) {      // depths written earlier by another warp of this CTA
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 
 // COMP form, run by each of the four PE warps: composite every ray group whose local tiles lie below `limit`, starting at
 // local tile `next_lt` (advanced; `last` = number of local tiles that exist).  A group's rays are dealt round-robin to the warps; all four warps wait for the group's
@@ -212,16 +225,16 @@ __device__ __forceinline__ void composite_groups(const FusedComposite& fc, const
         for (int j = 0; j < fc.group_rays; ++j) {
             const int64_t n = n_first + j;
             if (((int)n & 3) != w || n >= fc.N) continue;                               // ray n -> warp n % 4
-            const float* tp = ts + n * S;
+            const float* tp = (fc.u_c ? fc.ts_gen : ts) + n * S;
             float* wp = fc.weights ? fc.weights + n * S : nullptr;
             const uint32_t grow0 = lt0 * t3::kTileM + (uint32_t)(j * S);                // CTA-local row of the ray's first sample
             float running = 0.f;       // sum_{j<i} -sigma_j delta_j, nerf_helpers.py:86-89
             float cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f, st_sq = 0.f, st_nz = 0.f;
-            float t_n = __ldg(tp + lane);                                                // S is a multiple of 32
+            float t_n = ld_coherent(tp + lane);                                          // S is a multiple of 32
             for (int base = 0; base < S; base += kWarp) {
                 const int i = base + lane;
                 const float t = t_n;
-                if (base + kWarp < S) t_n = __ldg(tp + base + kWarp + lane);             // next chunk's depths in flight
+                if (base + kWarp < S) t_n = ld_coherent(tp + base + kWarp + lane);       // next chunk's depths in flight
                 const uint32_t grow = grow0 + (uint32_t)i;
                 const float4 v = sOut[((grow >> 7) & (t3::kOutSlots - 1)) * t3::kTileM + (grow & 127u)];
                 const float s = v.x;
@@ -431,7 +444,14 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
                         for (int k = 0; k < 3; ++k) x[k] = samples[row * 3 + k];
                     } else {
                         const int64_t n = row / S;
-                        const float tt = ts[row];                     // d * t + o (nerf_helpers.py:55)
+                        float tt;
+                        if (COMP && fc.u_c) {                         // stratified depth formed here (nerf_helpers.py:52-53)
+                            tt = __fadd_rn(__ldg(fc.t_base + (int)(row - n * S)), __fmul_rn(__ldg(fc.u_c + row), fc.step));
+                            fc.ts_gen[row] = tt;
+                        } else {
+                            tt = ts[row];
+                        }
+                        // d * t + o (nerf_helpers.py:55)
 #pragma unroll
                         for (int k = 0; k < 3; ++k) x[k] = __fadd_rn(__fmul_rn(__ldg(d_rays + n * 3 + k), tt), __ldg(o_rays + n * 3 + k));
                     }
@@ -675,11 +695,12 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
     cudaStream_t st = (cudaStream_t)stream;
     FusedComposite fc{};
     if (comp) {                                         // fused compositing: contiguous ray groups per CTA, 25 warps
-        if (!mlp_tc3_can_composite(S, &fc.group_rays, &fc.group_tiles) || !ts || samples || dbg) {
+        if (!mlp_tc3_can_composite(S, &fc.group_rays, &fc.group_tiles) || !(ts || comp->u_c) || samples || dbg) {
             set_error("nerf_mlp_composite_tc: S = %d cannot be composited inside the kernel (needs S %% 32 == 0, rays + depths input)", S);
             return NERF_E_ARG;
         }
         fc.weights = comp->weights; fc.ray_rgb = comp->ray_rgb; fc.depth = comp->depth; fc.acc = comp->acc; fc.stats = comp->stats;
+        fc.u_c = comp->u_c; fc.t_base = comp->t_base; fc.step = comp->step; fc.ts_gen = comp->ts_gen;
         fc.N = total / S;
         fc.num_groups = (fc.N + fc.group_rays - 1) / fc.group_rays;
         // at least two tiles per CTA where possible, so that both halves of a pair do useful work

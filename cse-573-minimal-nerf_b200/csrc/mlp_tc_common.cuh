@@ -15,7 +15,10 @@ constexpr float k2PiLo = -1.7484555e-7f;
 }  // namespace tcm
 
 // per-ray outputs of the compositing fused into the two-tile kernel (mlp_tc3.cu); weights / depth / acc / stats may be null
-struct CompositeOutputs { float* weights; float* ray_rgb; float* depth; float* acc; float* stats; };
+struct CompositeOutputs {
+    float* weights; float* ray_rgb; float* depth; float* acc; float* stats;
+    const float* u_c; const float* t_base; float step; float* ts_gen;      // non-null u_c: stratified depths formed in the kernel
+};
 
 struct StageRef { uint32_t offset, bytes; };
 struct StageTable { StageRef s[pk::kStages]; };

@@ -137,14 +137,23 @@ class NeRFModel(nn.Module):
         """True when render_rays can run (tensor-core shape, sample count the fused kernel supports)."""
         return self.uses_tensor_cores() and bool(nat.lib().nerf_mlp_composite_tc_supported(int(S)))
 
-    def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False, stats=None, out=None):
+    def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False, stats=None, out=None, strata=None):
         """Network + alpha compositing in ONE kernel (nerf_mlp_composite_tc): the per-sample sigma / rgb stay on the SM
         unless `keep_samples` (or `save`, the training form, which also stores activations + ReLU sign words).
         Returns the same dict as nerf_helpers.composite plus 'sigma', 'rgb_samples', 'saved' (None when not kept).
         `stats`: optional ZEROED [4] fp32 buffer for the density statistics (one is allocated otherwise); `out`: optional
-        contiguous [N,3] fp32 tensor the ray colours are written into (e.g. a slice of the frame buffer)."""
-        N, S = ts.shape[0], ts.shape[1]
-        dv = ts.device
+        contiguous [N,3] fp32 tensor the ray colours are written into (e.g. a slice of the frame buffer).
+        `strata` = (u [N,S], t_base [S], step) with ts=None: the stratified depths of generate_coarse_samples are formed inside
+        the kernel as well (returned as 'ts', bit-identical to nerf_coarse_sample)."""
+        if strata is not None:
+            u, t_base, step = strata
+            u = nat.dev(u, "u")
+            N, S = u.shape[0], u.shape[1]
+            dv = u.device
+            ts = torch.empty((N, S, 1), device=dv, dtype=torch.float32)
+        else:
+            N, S = ts.shape[0], ts.shape[1]
+            dv = ts.device
         keep = keep_samples or save
         sigma = torch.empty((N, S, 1), device=dv, dtype=torch.float32) if keep else None
         rgb = torch.empty((N, S, 3), device=dv, dtype=torch.float32) if keep else None
@@ -164,12 +173,18 @@ class NeRFModel(nn.Module):
             stats = torch.zeros((4,), device=dv, dtype=torch.float32)
         packed = self.packed_weights()
         with nat.timed_kernel("mlp_tc_kernel(train)" if save else "mlp_tc_kernel", N * S):
-            nat.check(nat.lib().nerf_mlp_composite_tc(nat.ptr(packed), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(ts), N, S,
-                                                      nat.ptr(sigma), nat.ptr(rgb), nat.ptr(acts), nat.ptr(masks),
-                                                      nat.ptr(w), nat.ptr(col), nat.ptr(depth), nat.ptr(acc), nat.ptr(stats),
-                                                      nat.stream()), "nerf_mlp_composite_tc")
+            if strata is not None:
+                nat.check(nat.lib().nerf_mlp_composite_tc_strata(nat.ptr(packed), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(u), nat.ptr(t_base),
+                                                                 float(step), N, S, nat.ptr(ts), nat.ptr(sigma), nat.ptr(rgb), nat.ptr(acts),
+                                                                 nat.ptr(masks), nat.ptr(w), nat.ptr(col), nat.ptr(depth), nat.ptr(acc),
+                                                                 nat.ptr(stats), nat.stream()), "nerf_mlp_composite_tc_strata")
+            else:
+                nat.check(nat.lib().nerf_mlp_composite_tc(nat.ptr(packed), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(ts), N, S,
+                                                          nat.ptr(sigma), nat.ptr(rgb), nat.ptr(acts), nat.ptr(masks),
+                                                          nat.ptr(w), nat.ptr(col), nat.ptr(depth), nat.ptr(acc), nat.ptr(stats),
+                                                          nat.stream()), "nerf_mlp_composite_tc")
         return {"weights": w, "rgb": col, "depth": depth, "acc": acc, "stats": stats[:2], "norm": stats[2],
-                "sigma": sigma, "rgb_samples": rgb, "saved": (acts, masks) if save else None}
+                "sigma": sigma, "rgb_samples": rgb, "saved": (acts, masks) if save else None, "ts": ts}
 
 
 class NeRFNetwork(LightningModule):

@@ -90,6 +90,7 @@ def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray, accumulate_into_grad=
     return [None] * 20 if direct else grads
 
 
+FUSE_STRATA = True          # K1 (stratified depths) inside the coarse network's kernel as well
 FUSE_COMPOSITE = True       # network + compositing in one kernel where the sample counts allow it (64 / 128 / 192 / 256)
 
 
@@ -117,13 +118,20 @@ def forward_pass(net, o, d, rand, save, keep_samples=False, fine_out=None):
     if rand is None:        # the reference's draw order and shapes (nerf_helpers.py:52,139,154)
         rand = (torch.rand((N, C), device=dv), torch.rand((N, 1), device=dv), torch.rand((N, Fn, 1), device=dv))
     u_c, eps, u_f = rand
-    c_ts = net._coarse_ts(o, d, u_c)
     fused = FUSE_COMPOSITE and net.coarse_network.can_composite(C) and net.fine_network.can_composite(C + Fn)
     if fused:       # network + compositing in one kernel; render keeps no per-sample outputs at all
         stats8 = _zeroed_stats8(dv)                              # density statistics of both networks
-        c = net.coarse_network.render_rays(o, d, c_ts, want_weights=True, keep_samples=keep_samples, save=save, stats=stats8[:4])
+        if FUSE_STRATA:                                          # ... and the stratified depths are formed in that kernel too
+            t_base, step = nerf_helpers._strata(net.near, net.far, C, dv)
+            c = net.coarse_network.render_rays(o, d, None, want_weights=True, keep_samples=keep_samples, save=save, stats=stats8[:4],
+                                               strata=(nat.dev(u_c, "u_c").reshape(N, C), t_base, step))
+            c_ts = c["ts"]
+        else:
+            c_ts = net._coarse_ts(o, d, u_c)
+            c = net.coarse_network.render_rays(o, d, c_ts, want_weights=True, keep_samples=keep_samples, save=save, stats=stats8[:4])
         c_sigma, c_rgb, c_acts = c["sigma"], c["rgb_samples"], c["saved"]
     else:
+        c_ts = net._coarse_ts(o, d, u_c)
         if save:
             c_sigma, c_rgb, c_acts = mlp_forward_train(net.coarse_network, o, d, c_ts)
         else:

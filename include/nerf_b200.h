@@ -160,6 +160,13 @@ int nerf_mlp_composite_tc(const void* packed, const float* o, const float* d, co
                           float* sigma, float* rgb, void* act_out, void* mask_out,
                           float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream);
 
+/* The coarse network's form of nerf_mlp_composite_tc: K1 (generate_coarse_samples, nerf_helpers.py:28-56) runs inside the kernel
+ * too.  u [N,S] uniforms, t_base [S] = the reference's torch.arange(near, far, step) on the device, ts_out [N,S] receives the depths
+ * t = t_base[i] + u * step (bit-identical to nerf_coarse_sample); everything else as nerf_mlp_composite_tc. */
+int nerf_mlp_composite_tc_strata(const void* packed, const float* o, const float* d, const float* u, const float* t_base, float step,
+                                 int64_t N, int S, float* ts_out, float* sigma, float* rgb, void* act_out, void* mask_out,
+                                 float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream);
+
 /* Both weight images (nerf_pack_weights + nerf_pack_weights_t) of both networks in ONE launch - what a training step needs
  * after the optimiser has changed the parameters.  params40_host: the 40 tensors of NeRFNetwork's state_dict order (coarse
  * network's 20, then the fine network's 20). */

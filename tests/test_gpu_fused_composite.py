@@ -112,6 +112,38 @@ def test_network_forward_identical_with_and_without_fusion(golden):
         assert bits_equal(last_a[key], last_b[key]), key
 
 
+def test_strata_inside_the_kernel_are_bit_identical(golden):
+    """nerf_mlp_composite_tc_strata forms the stratified depths in the coarse kernel's producer warps: depths, weights and every
+    output of NeRFNetwork.forward are bit for bit those of nerf_coarse_sample + nerf_mlp_composite_tc."""
+    import nerf_helpers as h
+    import training
+    net = make_net(4, "dense")
+    for N in (4096, 301, 2):
+        o, d, _ = rays(N, 64, 40 + N)
+        u = torch.rand(N, 64, device=DEV)
+        t_base, step = h._strata(2.0, 6.0, 64, o.device)
+        _, ts = h.generate_coarse_samples(o, d, 64, rand=u)
+        ref = net.coarse_network.render_rays(o, d, ts, keep_samples=True)
+        got = net.coarse_network.render_rays(o, d, None, keep_samples=True, strata=(u, t_base, step))
+        torch.cuda.synchronize()
+        assert bits_equal(got["ts"], ts)
+        for key in ("weights", "rgb", "depth", "acc", "sigma", "rgb_samples"):
+            assert bits_equal(got[key], ref[key]), (N, key)
+    g = golden["network"]
+    o, d = T(g["o"], DEV), T(g["d"], DEV)
+    rand = rand_triple(540, 64, device=DEV)
+    outs = []
+    try:
+        for flag in (False, True):
+            training.FUSE_STRATA = flag
+            out = net.forward(o, d, rand=rand)
+            outs.append((out["coarse_rgb_rays"].clone(), out["fine_rgb_rays"].clone(), net.last["ts"].clone(), net.last["coarse_ts"].clone()))
+    finally:
+        training.FUSE_STRATA = True
+    torch.cuda.synchronize()
+    assert all(bits_equal(a, b) for a, b in zip(*outs))
+
+
 def test_training_gradients_identical_with_and_without_fusion():
     import training
     net = make_net(3, "init")
