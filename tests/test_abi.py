@@ -49,6 +49,18 @@ def test_no_cpu_fallback():
     assert "oracle" not in src
 
 
+def test_render_entry_point_surface():
+    """render.py keeps the reference's call (render.py:14) and command line (render.py:20-25); the epoch tag is cut out of the
+    checkpoint name the way upstream does it."""
+    import render
+    assert list(inspect.signature(render.render).parameters) == ["ckpt", "save_dir", "rays", "num_poses"]
+    ns = render.build_parser().parse_args(["-c", "models/model=lego-epoch=1089-step=108999.ckpt"])
+    assert (ns.rays, ns.num_poses, str(ns.save_dir)) == (4096, 40, "recons")
+    assert render.epoch_tag(ns.ckpt) == "epoch=1089" and render.epoch_tag("x/epoch=3-step=11.ckpt") == "epoch=3"
+    with pytest.raises(SystemExit):
+        render.build_parser().parse_args([])                       # -c is required
+
+
 def test_call_surface_matches_reference():
     """Names, positional parameters and defaults of the reference's public functions."""
     import dataloader

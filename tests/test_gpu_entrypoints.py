@@ -70,7 +70,12 @@ def test_train_then_render(scene, tmp_path):
     assert (out / "epoch=3-360.gif").exists() and len(views) == 2
     assert views[0].shape == (64, 64, 3) and views[0].dtype == np.uint8
     epoch = str(ckpt)[str(ckpt).find("epoch="):]
-    assert epoch[:epoch.find("-")] == "epoch=3"                                     # render.py:15-16 name parsing
+    assert epoch[:epoch.find("-")] == "epoch=3" == render.epoch_tag(ckpt)           # render.py:15-16 name parsing
+    # the entry point itself: render(ckpt, save_dir, rays, num_poses) at the reference's 800 x 800 (one pose)
+    out2 = tmp_path / "recons2"
+    out2.mkdir()
+    frames = render.render(str(ckpt), out2, 4096, 1)
+    assert (out2 / "epoch=3-360.gif").exists() and len(frames) == 1 and frames[0].shape == (800, 800, 3)
 
 
 def test_score_metrics_match_oracle_and_entry_point(scene, tmp_path):
