@@ -59,27 +59,40 @@ def structural_similarity(gt_im, recon, multichannel=True):
 
 
 def calculate_scores(ckpt, base_dir, rays):
-    model = nerf_model.NeRFNetwork.load_from_checkpoint(ckpt).to(device)
-    test_dl = SyntheticDataset(base_dir, 'test', rays, cropping=False)
-    ssim_sum = 0.0
-    psnr_sum = 0.0
-    for i in range(len(test_dl)):
-        batch = test_dl[i]
-        gt_im = (batch['image'] * 255).clamp(0, 255).to(torch.uint8)                       # score.py:31 (astype truncates)
-        recon = nerf_helpers.view_reconstruction(model, batch['all_origin'], batch['all_direc'], N=rays)
-        ssim_sum += structural_similarity(gt_im, recon, multichannel=True)
-        psnr_sum += peak_signal_noise_ratio(gt_im, recon)
+    """Mean PSNR / SSIM of the checkpoint's renders over the scene's test split (score.py:20-41); prints upstream's three
+    lines and returns (psnr, ssim)."""
+    network = nerf_model.NeRFNetwork.load_from_checkpoint(str(ckpt)).to(device)
+    views = SyntheticDataset(base_dir, 'test', rays, cropping=False)
+    totals = {"psnr": 0.0, "ssim": 0.0}
+    for index in range(len(views)):
+        view = views[index]
+        # ground truth as upstream forms it: float image * 255, clipped, truncated to uint8 (score.py:31)
+        truth = (view['image'] * 255).clamp(0, 255).to(torch.uint8)
+        frame = nerf_helpers.view_reconstruction(network, view['all_origin'], view['all_direc'], N=rays)
+        totals["psnr"] += peak_signal_noise_ratio(truth, frame)
+        totals["ssim"] += structural_similarity(truth, frame, multichannel=True)
+    count = max(len(views), 1)
+    psnr, ssim = totals["psnr"] / count, totals["ssim"] / count
     print("==============Calculate Scores==============")
-    print(f"average psnr score: {psnr_sum / len(test_dl)}")
-    print(f"average ssim score: {ssim_sum / len(test_dl)}")
-    return psnr_sum / len(test_dl), ssim_sum / len(test_dl)
+    print(f"average psnr score: {psnr}")
+    print(f"average ssim score: {ssim}")
+    return psnr, ssim
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description='Calculate score metrics for NeRF Models.')
+    for flags, kw in ((('-c', '--ckpt'), dict(type=str, required=True, help='checkpoint (.ckpt) to score')),
+                      (('-r', '--rays'), dict(type=int, default=4096, help='rays per rendered chunk')),
+                      (('-b', '--base_dir'), dict(type=Path, default='/content/CSEP573-NeRF/data/nerf_synthetic/lego/',
+                                                  help='Blender-synthetic scene directory (its test split is scored)'))):
+        parser.add_argument(*flags, **kw)
+    return parser
+
+
+def main(argv=None):
+    opts = build_parser().parse_args(argv)
+    return calculate_scores(opts.ckpt, opts.base_dir, opts.rays)
 
 
 if __name__ == '__main__':
-    parser = argparse.ArgumentParser(description='Calculate score metrics for NeRF Models.')
-    parser.add_argument('-c', '--ckpt', type=str, required=True, help='ckpt path for model')
-    parser.add_argument('-r', '--rays', type=int, default=4096, help='number of rays per batch')
-    parser.add_argument('-b', '--base_dir', type=Path, default='/content/CSEP573-NeRF/data/nerf_synthetic/lego/',
-                        help='where to save the resulting gif')
-    args = parser.parse_args()
-    calculate_scores(args.ckpt, args.base_dir, args.rays)
+    main()
