@@ -12,7 +12,8 @@ import torch
 
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libnerf_b200.so"
-ABI_VERSION = 1
+DEBUG_LIB_PATH = HERE.parent / "tools" / "libnerf_b200_debug.so"      # probes + cycle-counter kernel forms; tools/ and tests only
+ABI_VERSION = 2
 
 _c_f32p = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -54,9 +55,10 @@ _PROTOTYPES = {
 _lib = None
 
 
-def build(verbose=False):
-    """Compile csrc/*.cu for sm_100a into libnerf_b200.so (nvcc cross-compiles without a GPU)."""
-    cmd = ["make", "-C", str(HERE / "csrc"), "-j8"]
+def build(verbose=False, target="all"):
+    """Compile csrc/*.cu for sm_100a into libnerf_b200.so, and the diagnostic library (same sources with
+    -DNERF_DEBUG_BUILD + csrc/debug/*.cu) into tools/libnerf_b200_debug.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", str(HERE / "csrc"), "-j8", target]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
@@ -84,6 +86,20 @@ def lib():
 
 def exported_symbols():
     return list(_PROTOTYPES)
+
+
+_debug_lib = None
+
+
+def debug_lib():
+    """tools/libnerf_b200_debug.so: the product sources built with -DNERF_DEBUG_BUILD plus the tcgen05 / TMEM / copy-engine /
+    HBM probes (`nerf_debug_*`).  Never loaded by the product path; callers set restype / argtypes themselves."""
+    global _debug_lib
+    if _debug_lib is None:
+        if not DEBUG_LIB_PATH.exists():
+            raise RuntimeError(f"{DEBUG_LIB_PATH} not found: build it with `make -C {HERE / 'csrc'} debug`")
+        _debug_lib = ctypes.CDLL(str(DEBUG_LIB_PATH))
+    return _debug_lib
 
 
 launches = 0          # kernels launched through this module (bench.py reports it as gpu_launches)

@@ -34,6 +34,17 @@ int num_sms() {
     return cached > 0 ? cached : 148;
 }
 
+bool attrs_pending(unsigned long long mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    return ((mask >> dev) & 1ull) == 0;
+}
+
+void attrs_done(unsigned long long& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev <= 63) mask |= 1ull << dev;
+}
+
 }  // namespace nerf
 
 extern "C" int nerf_abi_version(void) { return NERF_ABI_VERSION; }

@@ -12,6 +12,14 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);     // cudaGetLastError() -> 0 / NERF_E_CUDA
 int num_sms();                           // SM count of the current device (cached)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: callers keep one bit per device ordinal in a
+// thread-local mask and (re)apply their attributes the first time a thread launches on a device.
+bool attrs_pending(unsigned long long mask);      // true when the current device's bit is not yet set
+void attrs_done(unsigned long long& mask);        // set it
+template <class Kernel> inline cudaError_t allow_smem(Kernel k, size_t bytes) {
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

@@ -2,8 +2,8 @@
 // D[128,N] = A[128,K] * B[N,K]^T with A either staged in 128B-swizzled shared memory (mode 0, SS) or
 // written to TMEM with tcgen05.st (mode 1, TS), B always in swizzled shared memory.  Used by
 // tests/test_umma_probe.py to validate descriptor encodings on the device independently of the fused kernel.
-#include "common.cuh"
-#include "umma.cuh"
+#include "../common.cuh"
+#include "../umma.cuh"
 
 namespace nerf {
 
@@ -105,7 +105,7 @@ umma_probe_kernel(int mode, const __nv_bfloat16* __restrict__ A, const __nv_bflo
 }  // namespace nerf
 
 // Test-only entry point (declared in tests, not in include/nerf_b200.h).
-extern "C" int nerf_debug_umma(int mode, const void* A_bf16, const void* B_bf16, int K, int N, int d_col, float* D,
+extern "C" NERF_API int nerf_debug_umma(int mode, const void* A_bf16, const void* B_bf16, int K, int N, int d_col, float* D,
                                void* stream) {
     using namespace nerf;
     NERF_REQUIRE(A_bf16 && B_bf16 && D, "nerf_debug_umma: null pointer");
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(512, 1) tmem_bw_probe_kernel(int iters, int mo
 }
 }  // namespace nerf
 
-extern "C" int nerf_debug_tmem_bw(int nwarps, int iters, int mode, long long* out, void* stream) {
+extern "C" NERF_API int nerf_debug_tmem_bw(int nwarps, int iters, int mode, long long* out, void* stream) {
     nerf::tmem_bw_probe_kernel<<<1, nwarps * 32, 0, (cudaStream_t)stream>>>(iters, mode, out);
     return nerf::check_launch("nerf_debug_tmem_bw");
 }
@@ -257,7 +257,7 @@ tmem_contention_probe_kernel(int n_mma, int N, int d_col, int a_col, int nw, int
 }
 }  // namespace nerf
 
-extern "C" int nerf_debug_tmem_contention(int n_mma, int N, int d_col, int a_col, int nw, int ld_mode, int ld_col, int ld_span,
+extern "C" NERF_API int nerf_debug_tmem_contention(int n_mma, int N, int d_col, int a_col, int nw, int ld_mode, int ld_col, int ld_span,
                                           int commit_every, int alt_every, long long* out, void* stream) {
     using namespace nerf;
     NERF_REQUIRE(nw >= 0 && nw <= 28 && N >= 16 && N <= 256 && d_col >= 0 && d_col + N <= 512 && ld_span >= 32, "tmem_contention: bad args");
@@ -320,7 +320,7 @@ copy_stream_probe_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t
 }
 }  // namespace nerf
 
-extern "C" int nerf_debug_copy_stream(const void* src, uint32_t src_bytes, int mode, uint32_t bytes, int slots, int nstages, int grid,
+extern "C" NERF_API int nerf_debug_copy_stream(const void* src, uint32_t src_bytes, int mode, uint32_t bytes, int slots, int nstages, int grid,
                                       int nprod, long long* out, void* stream) {
     using namespace nerf;
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(512) write_tiled_kernel(uint4* __restrict__ ds
 }
 }  // namespace nerf
 
-extern "C" int nerf_debug_hbm_bw(void* buf, int64_t bytes, int mode, int blocks_per_sm, void* sink, void* stream) {
+extern "C" NERF_API int nerf_debug_hbm_bw(void* buf, int64_t bytes, int mode, int blocks_per_sm, void* sink, void* stream) {
     using namespace nerf;
     const int grid = num_sms() * blocks_per_sm;
     if (mode == 2) {

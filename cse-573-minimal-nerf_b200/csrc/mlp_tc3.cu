@@ -1,9 +1,9 @@
 // mlp_tc3.cu - K8, two-tile form: NeRFModel.forward (nerf_model.py:362-389) for TWO 128-sample tiles ("X" and "Y") per
-// CTA at a time.  Same arithmetic, weight image and TMEM-resident activations as mlp_tc.cu; what changes is the schedule:
+// CTA at a time, bf16 weight image streamed through shared memory, activations resident in TMEM.  The schedule:
 //
 //   * every weight stage fetched from L2 into the shared-memory ring is used by both tiles before it is released, so the
-//     L2 -> SM weight stream per sample is halved (mlp_tc.cu streams 0.92 MB per tile at ~36 B/clk/SM, close to the
-//     ~42 B/clk/SM the L2 can deliver to all 148 SMs at once);
+//     L2 -> SM weight stream per sample is halved (a one-tile schedule streams 0.92 MB per tile at ~36 B/clk/SM, close to
+//     the ~42 B/clk/SM the L2 can deliver to all 148 SMs at once);
 //   * the MMA -> epilogue -> MMA dependency of one tile (a layer needs the previous layer's ReLU'd output) is hidden
 //     behind the other tile's MMAs: steps alternate X, Y, X, Y (turn token between the two issuing warps).
 //
@@ -30,7 +30,6 @@
 // Steps per tile (16): mlp.0 h0,h1 | mlp.2/4/6, feature_fn.0/2/4 h0,h1 | rgb_fn.0 | rgb_fn.2 (density_fn.0: CUDA cores, see below).
 // Barriers per tile t: dfull[t] (MMA -> epilogue, accumulator complete), dfree[t] (accumulator read into registers),
 // alo[t] / ahi[t] (K-blocks 0,1 / 2,3 of the next A operand written), pex_full/empty[t], ped_full/empty[t], turn[t].
-#include <stdlib.h>
 #include <type_traits>
 #include "mlp_tc3_common.cuh"
 #include "composite_scan.cuh"
@@ -40,8 +39,8 @@ namespace nerf {
 
 // Stages of this kernel: the 63 K = 64 weight blocks of the packed image in consumption order (one ring slot each) without
 // density_fn.0's four, and rgb_fn.2's two 2 KB blocks fetched as one request.  sigma is a 256-long dot product per sample;
-// the epilogue of feature_fn.4 takes it on the CUDA cores from the bf16 feat values it has in registers (same operands as
-// the N = 16 MMA of mlp_tc.cu, fp32 accumulation), which removes one step and its accumulator hand-over per tile.
+// the epilogue of feature_fn.4 takes it on the CUDA cores from the bf16 feat values it has in registers (the operands an
+// N = 16 MMA step would see, fp32 accumulation), which removes one step and its accumulator hand-over per tile.
 constexpr int kStages3 = pk::kStages - 4 - 1;          // 58
 struct StageTable3 { StageRef s[kStages3]; };
 constexpr StageTable3 make_stage_table3() {
@@ -62,7 +61,7 @@ constexpr StageTable3 make_stage_table3() {
 static __constant__ StageTable3 c_stages3 = make_stage_table3();
 static_assert(make_stage_table3().s[kStages3 - 1].bytes == 2u * pk::kStageBytesSmall && make_stage_table3().s[kStages3 - 2].bytes == 16384u,
               "stage table of the two-tile kernel");
-constexpr uint32_t kDensityStageOffset = make_merged_table().s[31].offset;     // 4 blocks of [16 x 64] bf16, row 0 = w7
+constexpr uint32_t kDensityStageOffset = density_stage_offset();               // 4 blocks of [16 x 64] bf16, row 0 = w7
 
 // 32 accumulator columns (registers) -> + bias, (ReLU), 16 registers of bf16 pairs
 // RELU is a template parameter (a run-time flag makes nvcc convert both ways and select) and the bias comes through a
@@ -275,7 +274,8 @@ __device__ __forceinline__ void composite_groups(const FusedComposite& fc, const
 // from L2 and multicasts that half into both shared memories (`cp.async.bulk ... .multicast::cluster`), which halves the
 // L2 -> SM weight stream once more (0.46 MB per tile pair and CTA).  Nothing else is shared: MMAs, TMEM and epilogues stay
 // per CTA; the only cross-CTA dependency is the recycling of a ring slot, whose release commits go to both CTAs' `empty`
-// barriers (count 4) - eight slots deep, off the MMA -> epilogue -> MMA loop that sank the cta_group::2 kernel (mlp_tc2.cu).
+// barriers (count 4) - eight slots deep, off the MMA -> epilogue -> MMA loop (a cta_group::2 CTA-pair schedule put its
+// cross-CTA signalling on that loop and measured slower, profiles/r01_notes.md).
 // Both CTAs run the same number of pairs (the one with fewer tiles ends on a fully masked pair).
 template <bool PROFILE, bool TRAIN, bool COMP, bool MC>
 __global__ void __launch_bounds__(t3::kThreads, 1)
@@ -648,12 +648,6 @@ mlp_tc3_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o_r
     if (warp == 2) umma::tmem_dealloc(tmem, 512);
 }
 
-// NERF_TC_MULTICAST=0 turns the 2-CTA-cluster weight multicast of the COMP form off (diagnostic A/B)
-static bool use_multicast() {
-    static const bool v = [] { const char* e = getenv("NERF_TC_MULTICAST"); return !(e && e[0] == '0'); }();
-    return v;
-}
-
 // Fused compositing needs whole 32-sample chunks per ray and a ray group (whole rays = whole tiles) that fits the output ring
 bool mlp_tc3_can_composite(int S, int* group_rays, int* group_tiles) {
     if (S <= 0 || S % 32 != 0) return false;
@@ -669,23 +663,19 @@ bool mlp_tc3_can_composite(int S, int* group_rays, int* group_tiles) {
 int launch_mlp_tc3(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
                    int64_t total, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream, long long* dbg,
                    const CompositeOutputs* comp) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc3_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::kSmemBytes);
+    static thread_local unsigned long long attr_mask = 0;
+    if (attrs_pending(attr_mask)) {
+        cudaError_t e = allow_smem(mlp_tc3_kernel<false, false, false, false>, t3::kSmemBytes);
+        if (e == cudaSuccess) e = allow_smem(mlp_tc3_kernel<false, true, false, false>, t3::kSmemBytes);
+        if (e == cudaSuccess) e = allow_smem(mlp_tc3_kernel<false, false, true, false>, t3::kSmemBytes);
+        if (e == cudaSuccess) e = allow_smem(mlp_tc3_kernel<false, true, true, false>, t3::kSmemBytes);
+        if (e == cudaSuccess) e = allow_smem(mlp_tc3_kernel<false, false, true, true>, t3::kSmemBytes);
+        if (e == cudaSuccess) e = allow_smem(mlp_tc3_kernel<false, true, true, true>, t3::kSmemBytes);
+#ifdef NERF_DEBUG_BUILD
+        if (e == cudaSuccess) e = allow_smem(mlp_tc3_kernel<true, false, false, false>, t3::kSmemBytes);
+#endif
         if (e != cudaSuccess) { set_error("nerf_mlp_forward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
-        attr_set = true;
+        attrs_done(attr_mask);
     }
     const int64_t tiles = (total + t3::kTileM - 1) / t3::kTileM;
     const int64_t pairs = (tiles + 1) / 2;
@@ -707,7 +697,8 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
         int64_t want = (tiles + 1) / 2;
         if (want > fc.num_groups) want = fc.num_groups;
         int grid = (int)(want < num_sms() ? want : num_sms());
-        if (use_multicast() && grid >= 2) {               // 2-CTA clusters sharing every weight stage by multicast
+        if (grid >= 2) {                                  // 2-CTA clusters sharing every weight stage by multicast (a single ray group
+                                                          // runs as one plain CTA below)
             grid &= ~1;
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(t3::kThreads); cfg.dynamicSmemBytes = t3::kSmemBytes; cfg.stream = st;
@@ -732,13 +723,15 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
         return check_launch("nerf_mlp_composite_tc");
     }
     int grid = (int)(pairs < num_sms() ? pairs : num_sms());
-    if (dbg) {                                        // diagnostic runs only: NERF_TC_MAX_CTAS limits the grid
-        const char* e = getenv("NERF_TC_MAX_CTAS");
-        if (e && atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
-    }
-    if (dbg)
+#ifdef NERF_DEBUG_BUILD
+    if (dbg) {                                        // diagnostic library only: per-CTA cycle counters
         mlp_tc3_kernel<true, false, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, dbg, fc);
-    else if (act_out)                                 // training form: also stores activations + sign words
+        return check_launch("nerf_debug_mlp_tc_profile");
+    }
+#else
+    if (dbg) { set_error("nerf_mlp_forward_tc: cycle counters exist in the diagnostic library only"); return NERF_E_ARG; }
+#endif
+    if (act_out)                                      // training form: also stores activations + sign words
         mlp_tc3_kernel<false, true, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, ao, mo, nullptr, fc);
     else
         mlp_tc3_kernel<false, false, false, false><<<grid, t3::kThreads, t3::kSmemBytes, st>>>(pw, o, d, ts, samples, total, S, sigma, rgb, nullptr, nullptr, nullptr, fc);
@@ -746,3 +739,88 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
 }
 
 }  // namespace nerf
+
+using namespace nerf;
+
+static int launch_mlp_tc(const void* packed, const float* o, const float* d, const float* ts, const float* samples,
+                         int64_t N, int S, float* sigma, float* rgb, void* stream, long long* dbg = nullptr,
+                         void* act_out = nullptr, void* mask_out = nullptr) {
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_forward_tc: bad size N=%lld S=%d", (long long)N, S);
+    if (N == 0) return 0;
+    NERF_REQUIRE(packed && d && sigma && rgb, "nerf_mlp_forward_tc: null pointer");
+    NERF_REQUIRE(samples || (o && ts), "nerf_mlp_forward_tc: need either samples or (o, ts)");
+    NERF_REQUIRE(((uintptr_t)packed & 127) == 0, "nerf_mlp_forward_tc: packed buffer must be 128-byte aligned");
+    NERF_REQUIRE(!act_out || ((uintptr_t)act_out & 15) == 0, "nerf_mlp_forward_tc: act_out must be 16-byte aligned");
+    return launch_mlp_tc3(packed, o, d, ts, samples, N * S, S, sigma, rgb, act_out, mask_out, stream, dbg, nullptr);
+}
+
+#ifdef NERF_DEBUG_BUILD
+// Diagnostic library only (tools/, not in include/nerf_b200.h): same kernel with per-CTA cycle counters, dbg = [grid,16] int64.
+extern "C" NERF_API int nerf_debug_mlp_tc_profile(const void* packed, const float* o, const float* d, const float* ts,
+                                                  int64_t N, int S, float* sigma, float* rgb, long long* dbg, void* stream) {
+    return launch_mlp_tc(packed, o, d, ts, nullptr, N, S, sigma, rgb, stream, dbg);
+}
+#endif
+
+extern "C" int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, const float* ts,
+                                   int64_t N, int S, float* sigma, float* rgb, void* stream) {
+    return launch_mlp_tc(packed, o, d, ts, nullptr, N, S, sigma, rgb, stream);
+}
+
+// Points form: samples [N,S,3] given explicitly (the NeRFModel.forward(samples, direc) call surface).
+extern "C" int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
+                                          int64_t N, int S, float* sigma, float* rgb, void* stream) {
+    return launch_mlp_tc(packed, nullptr, d, nullptr, samples, N, S, sigma, rgb, stream);
+}
+
+// Training form: also writes the bf16 activations every layer consumed (outputs of mlp.0, mlp.2, mlp.4, mlp.6,
+// feature_fn.0, feature_fn.2, feature_fn.4 at feature 256*k, rgb_fn.0 at 1792) in the tiled chunk-major layout of
+// pack_layout.cuh; act_out holds ceil(N*S/128)*128 rows x 1920 features.
+extern "C" int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
+                                         int64_t N, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream) {
+    NERF_REQUIRE(N == 0 || (act_out && mask_out), "nerf_mlp_forward_tc_train: act_out / mask_out is NULL");
+    return launch_mlp_tc(packed, o, d, ts, nullptr, N, S, sigma, rgb, stream, nullptr, act_out, mask_out);
+}
+
+// ---- K8 + K2: the same network with alpha compositing (nerf_helpers.py:58-104) done inside the kernel (COMP form above).
+// sigma / rgb may be NULL (render: the per-sample outputs never leave the SM); act_out / mask_out non-NULL selects the
+// training form, which needs sigma and rgb as well (the compositing backward reads them).
+extern "C" int nerf_mlp_composite_tc_supported(int S) { return mlp_tc3_can_composite(S, nullptr, nullptr) ? 1 : 0; }
+
+extern "C" int nerf_mlp_composite_tc(const void* packed, const float* o, const float* d, const float* ts, int64_t N, int S,
+                                     float* sigma, float* rgb, void* act_out, void* mask_out,
+                                     float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream) {
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_composite_tc: bad size N=%lld S=%d", (long long)N, S);
+    if (N == 0) return 0;
+    NERF_REQUIRE(packed && o && d && ts && ray_rgb, "nerf_mlp_composite_tc: null pointer");
+    NERF_REQUIRE((sigma == nullptr) == (rgb == nullptr), "nerf_mlp_composite_tc: sigma and rgb go together");
+    NERF_REQUIRE((act_out == nullptr) == (mask_out == nullptr), "nerf_mlp_composite_tc: act_out and mask_out go together");
+    NERF_REQUIRE(!act_out || sigma, "nerf_mlp_composite_tc: the training form also needs sigma / rgb");
+    NERF_REQUIRE(((uintptr_t)packed & 127) == 0, "nerf_mlp_composite_tc: packed buffer must be 128-byte aligned");
+    NERF_REQUIRE(!act_out || ((uintptr_t)act_out & 15) == 0, "nerf_mlp_composite_tc: act_out must be 16-byte aligned");
+    NERF_REQUIRE(nerf_mlp_composite_tc_supported(S),
+                 "nerf_mlp_composite_tc: S = %d is not supported (needs S %% 32 == 0 and a ray group of at most 6 tiles); "
+                 "use nerf_mlp_forward_tc + nerf_composite", S);
+    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4, nullptr, nullptr, 0.f, nullptr};
+    return launch_mlp_tc3(packed, o, d, ts, nullptr, N * S, S, sigma, rgb, act_out, mask_out, stream, nullptr, &comp);
+}
+
+// The coarse network's form: K1 (generate_coarse_samples, nerf_helpers.py:28-56) runs inside the kernel too.  u [N,S] uniforms,
+// t_base [S] = the reference's torch.arange(near, far, step), ts_out [N,S] receives the depths t = t_base[i] + u * step (bit-identical
+// to nerf_coarse_sample); everything else as nerf_mlp_composite_tc.
+extern "C" int nerf_mlp_composite_tc_strata(const void* packed, const float* o, const float* d, const float* u, const float* t_base,
+                                            float step, int64_t N, int S, float* ts_out, float* sigma, float* rgb, void* act_out,
+                                            void* mask_out, float* weights, float* ray_rgb, float* depth, float* acc, float* stats4,
+                                            void* stream) {
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_composite_tc_strata: bad size N=%lld S=%d", (long long)N, S);
+    if (N == 0) return 0;
+    NERF_REQUIRE(packed && o && d && u && t_base && ts_out && ray_rgb, "nerf_mlp_composite_tc_strata: null pointer");
+    NERF_REQUIRE((sigma == nullptr) == (rgb == nullptr), "nerf_mlp_composite_tc_strata: sigma and rgb go together");
+    NERF_REQUIRE((act_out == nullptr) == (mask_out == nullptr), "nerf_mlp_composite_tc_strata: act_out and mask_out go together");
+    NERF_REQUIRE(!act_out || sigma, "nerf_mlp_composite_tc_strata: the training form also needs sigma / rgb");
+    NERF_REQUIRE(((uintptr_t)packed & 127) == 0, "nerf_mlp_composite_tc_strata: packed buffer must be 128-byte aligned");
+    NERF_REQUIRE(!act_out || ((uintptr_t)act_out & 15) == 0, "nerf_mlp_composite_tc_strata: act_out must be 16-byte aligned");
+    NERF_REQUIRE(nerf_mlp_composite_tc_supported(S), "nerf_mlp_composite_tc_strata: S = %d is not supported", S);
+    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4, u, t_base, step, ts_out};
+    return launch_mlp_tc3(packed, o, d, nullptr, nullptr, N * S, S, sigma, rgb, act_out, mask_out, stream, nullptr, &comp);
+}

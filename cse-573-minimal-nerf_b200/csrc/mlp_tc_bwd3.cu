@@ -1,6 +1,6 @@
 // mlp_tc_bwd3.cu - dgrad chain of one NeRFModel (autograd of nerf_model.py:362-389), two 128-sample tiles per CTA: the
 // schedule of mlp_tc3.cu (shared W^T stages, one MMA-issuing warp per tile with a turn token, in-place TMEM operands, all
-// 16 epilogue warps on every task) applied to the arithmetic of mlp_tc_bwd.cu:
+// 16 epilogue warps on every task) run in reverse:
 //   per tile, given the gradients w.r.t. the head pre-activations (from composite_backward_kernel)
 //     dr   = (drgb_pre . W9) * [r > 0]                         CUDA cores, producer warps 20-23 -> smem A tile (K = 128)
 //     dz6  = dr . W8[:, :256] + dsigma_pre (x) w7              steps 0,1   (A = dr tile in shared memory, SS)
@@ -297,11 +297,11 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
 
 int launch_mlp_tc_bwd3(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre, int64_t total,
                        void* dz_out, void* stream) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b3::kSmemBytes);
+    static thread_local unsigned long long attr_mask = 0;
+    if (attrs_pending(attr_mask)) {
+        cudaError_t e = allow_smem(mlp_tc_bwd3_kernel, b3::kSmemBytes);
         if (e != cudaSuccess) { set_error("nerf_mlp_backward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
-        attr_set = true;
+        attrs_done(attr_mask);
     }
     const int64_t tiles = (total + t3::kTileM - 1) / t3::kTileM;
     const int64_t pairs = (tiles + 1) / 2;
@@ -312,3 +312,15 @@ int launch_mlp_tc_bwd3(const void* packed_t, const void* masks, const float* dsi
 }
 
 }  // namespace nerf
+
+using namespace nerf;
+
+extern "C" int nerf_mlp_backward_tc(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre,
+                                    int64_t N, int S, void* dz_out, void* stream) {
+    NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_backward_tc: bad size");
+    if (N == 0) return 0;
+    NERF_REQUIRE(packed_t && masks && dsigma_pre && drgb_pre && dz_out, "nerf_mlp_backward_tc: null pointer");
+    NERF_REQUIRE(((uintptr_t)packed_t & 127) == 0 && ((uintptr_t)masks & 7) == 0 && ((uintptr_t)dz_out & 15) == 0,
+                 "nerf_mlp_backward_tc: misaligned buffer");
+    return launch_mlp_tc_bwd3(packed_t, masks, dsigma_pre, drgb_pre, N * S, dz_out, stream);
+}

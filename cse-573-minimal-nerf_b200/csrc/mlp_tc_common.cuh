@@ -1,5 +1,5 @@
-// mlp_tc_common.cuh - device helpers shared by the 1-CTA (mlp_tc.cu) and CTA-pair (mlp_tc2.cu) tensor-core kernels:
-// the weight-stage table, the range-reduced MUFU sin/cos, and the swizzled PE tile writers.
+// mlp_tc_common.cuh - device helpers shared by the tensor-core kernels (forward mlp_tc3.cu, dgrad mlp_tc_bwd3.cu, wgrad
+// wgrad_tc.cu): weight-stage references, the range-reduced MUFU sin/cos, and the positional-encoding row encoder.
 #pragma once
 #include "common.cuh"
 #include "pack_layout.cuh"
@@ -21,47 +21,13 @@ struct CompositeOutputs {
 };
 
 struct StageRef { uint32_t offset, bytes; };
-struct StageTable { StageRef s[pk::kStages]; };
-constexpr StageTable make_stage_table() {
-    StageTable t{};
-    for (int i = 0; i < pk::kStages; ++i) {
-        t.s[i].offset = pk::kLayout.st[i].offset;
-        t.s[i].bytes = (uint32_t)pk::kLayout.st[i].rows * 128u;
-    }
-    return t;
+// offset of density_fn.0's four [16 x 64] bf16 blocks in the packed image (row 0 of each = w7, the only row the kernels read:
+// sigma is taken on the CUDA cores): the stages are laid out in consumption order, density_fn.0 sits between rgb_fn.0 and rgb_fn.2
+constexpr uint32_t density_stage_offset() {
+    for (int i = 0; i < pk::kStages; ++i)
+        if (pk::kLayout.st[i].param == 7) return pk::kLayout.st[i].offset;
+    return 0;
 }
-static __constant__ StageTable c_stages = make_stage_table();
-
-// Merged stages for the 1-CTA forward kernel: the copy engine completes about one request per ~550 clk per issuing
-// lane whatever its size (profiles/r01_notes.md), so K-blocks that are consumed back to back are fetched as ONE bulk copy
-// of up to 32 KB (the packed image is contiguous in consumption order; only this table changes):
-//   mlp.0: 1 block per half | 256-wide layers: 2 + 2 blocks per half | feature_fn.0 / rgb_fn.0: PE block, then 2 + 2 |
-//   density_fn.0: its 4 small blocks | rgb_fn.2: its 2 small blocks.
-constexpr int kMergedStages = 33;
-struct MergedTable { StageRef s[kMergedStages]; };
-constexpr MergedTable make_merged_table() {
-    MergedTable t{};
-    int m = 0, i = 0;
-    auto take = [&](int nblocks) {
-        t.s[m].offset = pk::kLayout.st[i].offset;
-        uint32_t bytes = 0;
-        for (int j = 0; j < nblocks; ++j) bytes += (uint32_t)pk::kLayout.st[i + j].rows * 128u;
-        t.s[m].bytes = bytes;
-        i += nblocks;
-        ++m;
-    };
-    take(1); take(1);                                            // mlp.0
-    for (int l = 0; l < 3; ++l) for (int h = 0; h < 2; ++h) { take(2); take(2); }      // mlp.2/4/6
-    for (int h = 0; h < 2; ++h) { take(1); take(2); take(2); }                        // feature_fn.0
-    for (int l = 0; l < 2; ++l) for (int h = 0; h < 2; ++h) { take(2); take(2); }      // feature_fn.2/4
-    take(1); take(2); take(2);                                                         // rgb_fn.0
-    take(4);                                                                           // density_fn.0
-    take(2);                                                                           // rgb_fn.2
-    return t;
-}
-static __constant__ MergedTable c_merged = make_merged_table();
-static_assert(make_merged_table().s[kMergedStages - 1].offset + make_merged_table().s[kMergedStages - 1].bytes ==
-                  pk::kLayout.weight_bytes, "merged stage table must cover the whole weight image");
 
 // cos / sin of a = fl32(2^i pi) * x for |a| up to a few thousand: Cody-Waite reduction by 2 pi in two FMAs,
 // then the MUFU approximations on [-pi, pi] (abs error ~1e-6, far below bf16 resolution).
@@ -71,15 +37,6 @@ __device__ __forceinline__ void fast_sincos(float a, float& s, float& c) {
     r = fmaf(-k, tcm::k2PiLo, r);
     s = __sinf(r);
     c = __cosf(r);
-}
-
-// Row `r` of a [128 x 64] bf16 K-major 128B-swizzled tile <- 32 packed registers (64 bf16).
-__device__ __forceinline__ void store_row_sw128(uint8_t* tile, int r, const uint32_t (&v)[32]) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        uint4 q = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-        *(uint4*)(tile + r * 128 + ((c ^ (r & 7)) << 4)) = q;
-    }
 }
 
 template <int L>
@@ -99,11 +56,5 @@ __device__ __forceinline__ void encode_row(const float (&x)[3], uint32_t (&v)[32
     for (int j = 3 * L; j < 32; ++j) v[j] = 0u;
 }
 
-
-// per-CTA cycle counters of the diagnostic builds (dbg[blockIdx.x * 16 + i]):
-//   0 MMA warp total, 1 MMA wait(full = weights), 2 MMA wait(edone = epilogue), 3 MMA wait(pe_full),
-//   4 producer wait(empty), 5 epilogue total, 6 epilogue wait(dfull), 7 unused, 8 tiles
-#define NERF_PROF_BEGIN(var) long long var = 0; if (PROFILE) var = clock64();
-#define NERF_PROF_END(var, slot) if (PROFILE) prof[slot] += clock64() - var;
 
 }  // namespace nerf

@@ -94,8 +94,13 @@ constexpr int kGridCtas = 25 + (17 + 17 + 18) + (17 + 18 + 17) + 12 + 7;        
 
 struct Grads { float* p[20]; };
 
-// diagnostic: per-CTA (elapsed clocks, clocks until the last MMA completed) of the most recent launch (tools/profile_wgrad.py)
+#ifdef NERF_DEBUG_BUILD
+// diagnostic library only: per-CTA (elapsed clocks, clocks until the last MMA completed) of the most recent launch (tools/profile_wgrad.py)
 __device__ long long g_wgrad_cycles[2 * 160];
+#define NERF_WGRAD_CYCLES(i, v) g_wgrad_cycles[i] = (v)
+#else
+#define NERF_WGRAD_CYCLES(i, v) ((void)0)
+#endif
 
 __global__ void __launch_bounds__(wg::kThreads, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __restrict__ dz, const float* __restrict__ o_rays,
@@ -345,7 +350,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
         // ---- epilogue: D_i[m = lane (row of block i), n] -> atomics into dW (skipped by CTAs that had no tile)
         umma::mbar_wait(done, 0);
         umma::tc_fence_after();
-        if (tid == 128) g_wgrad_cycles[2 * blockIdx.x + 1] = clock64() - t_start;
+        if (tid == 128) NERF_WGRAD_CYCLES(2 * blockIdx.x + 1, clock64() - t_start);
         if (first < num_tiles) {
             const int m = (warp & 3) * 32 + lane;
             const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -398,7 +403,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (tid == 0) g_wgrad_cycles[2 * blockIdx.x] = clock64() - t_start;
+    if (tid == 0) NERF_WGRAD_CYCLES(2 * blockIdx.x, clock64() - t_start);
     if (warp == 3) umma::tmem_dealloc(tmem, 512);
 }
 
@@ -406,9 +411,11 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
 
 using namespace nerf;
 
-extern "C" int nerf_debug_wgrad_cycles(long long* host_out320) {
+#ifdef NERF_DEBUG_BUILD
+extern "C" NERF_API int nerf_debug_wgrad_cycles(long long* host_out320) {
     return cudaMemcpyFromSymbol(host_out320, g_wgrad_cycles, sizeof(long long) * 320) == cudaSuccess ? 0 : NERF_E_CUDA;
 }
+#endif
 
 extern "C" int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
                              float* const* grads20_host, void* stream) {
@@ -421,11 +428,11 @@ extern "C" int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, c
         NERF_REQUIRE(grads20_host[i], "nerf_wgrad_tc: grads20_host[%d] is NULL", i);
         G.p[i] = grads20_host[i];
     }
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::kSmemBytes);
+    static thread_local unsigned long long attr_mask = 0;
+    if (attrs_pending(attr_mask)) {
+        cudaError_t e = allow_smem(wgrad_tc_kernel, wg::kSmemBytes);
         if (e != cudaSuccess) { set_error("nerf_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
-        attr_set = true;
+        attrs_done(attr_mask);
     }
     wgrad_tc_kernel<<<wg::kGridCtas, wg::kThreads, wg::kSmemBytes, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)acts, (const __nv_bfloat16*)dz, o, d, ts, N * S, S, G);

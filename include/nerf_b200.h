@@ -24,52 +24,60 @@
 extern "C" {
 #endif
 
-#define NERF_ABI_VERSION 1
+#define NERF_ABI_VERSION 2
+
+/* libnerf_b200.so is built with -fvisibility=hidden: the functions declared here are its whole dynamic symbol table
+ * (tests/test_abi.py compares `nm -D` with this header). */
+#if defined(__GNUC__)
+#define NERF_API __attribute__((visibility("default")))
+#else
+#define NERF_API
+#endif
 
 #define NERF_E_ARG    (-1)   /* null pointer / bad size / unsupported shape */
 #define NERF_E_CUDA   (-2)   /* CUDA runtime error at launch */
 #define NERF_E_DEVICE (-3)   /* device is not sm_100 */
 
-int nerf_abi_version(void);
-const char* nerf_last_error(void);
+NERF_API int nerf_abi_version(void);
+NERF_API const char* nerf_last_error(void);
 
 /* ---- H0: rays.  dataloader.py:36-43 (get_rays), :150-152 (pixel gather).
  * c2w_host: 12 or 16 floats on the HOST, row-major rows of the 4x4 camera-to-world matrix.
  * xs, ys: [n] int64 device arrays of pixel column / row, or both NULL for the full H*W grid in
  * row-major order (then n must be H*W).  o, d: [n,3].  d is NOT normalised (as upstream). */
-int nerf_raygen(const float* c2w_host, int H, int W, float focal, const int64_t* xs, const int64_t* ys,
+NERF_API int nerf_raygen(const float* c2w_host, int H, int W, float focal, const int64_t* xs, const int64_t* ys,
                 int64_t n, float* o, float* d, void* stream);
 
 /* ---- H1: stratified depths and points.  nerf_helpers.py:28-56.
  * u: [N,C] uniforms in [0,1).  t_base: [C] strata origins (the reference's torch.arange(near, far, step),
  * evaluated by the host with torch so that its rounding is inherited).  ts[n,i] = t_base[i] + u*step,
  * samples = d*t + o (separate multiply and add).  samples may be NULL. */
-int nerf_coarse_sample(const float* o, const float* d, const float* u, const float* t_base, float step,
+NERF_API int nerf_coarse_sample(const float* o, const float* d, const float* u, const float* t_base, float step,
                        int64_t N, int C, float* samples, float* ts, void* stream);
 
 /* ---- H2: deltas.  nerf_helpers.py:58-73.  ts, deltas: [N,S]; deltas[:, S-1] = 1e10. */
-int nerf_deltas(const float* ts, int64_t N, int S, float* deltas, void* stream);
+NERF_API int nerf_deltas(const float* ts, int64_t N, int S, float* deltas, void* stream);
 
 /* ---- H3: unnormalised weights.  nerf_helpers.py:75-91.  sigma, deltas, weights: [N,S].
  * The exclusive running sum of -sigma*delta is taken sequentially in fp32 (CPU torch order). */
-int nerf_weights(const float* sigma, const float* deltas, int64_t N, int S, float* weights, void* stream);
+NERF_API int nerf_weights(const float* sigma, const float* deltas, int64_t N, int S, float* weights, void* stream);
 
 /* ---- H4: ray colour.  nerf_helpers.py:93-104.  weights [N,S], rgb [N,S,3] -> ray_rgb [N,3]. */
-int nerf_ray_color(const float* weights, const float* rgb, int64_t N, int S, float* ray_rgb, void* stream);
+NERF_API int nerf_ray_color(const float* weights, const float* rgb, int64_t N, int S, float* ray_rgb, void* stream);
 
 /* ---- H2+H3+H4 in one pass (what NeRFNetwork.forward does at nerf_model.py:109-111 and :128-130).
  * sigma [N,S], rgb [N,S,3], ts [N,S].  Every output may be NULL: deltas [N,S], weights [N,S],
  * ray_rgb [N,3], depth [N] (sum w*t), acc [N] (sum w).  stats2 (nullable, [4], zero-initialised by the caller, ACCUMULATED with atomics):
  * [0] sum sigma^2, [1] count(sigma != 0) - the two density statistics logged at nerf_model.py:105-106 -, [2] sqrt([0]) written
  * by the last block of the launch, [3] internal block counter. */
-int nerf_composite(const float* sigma, const float* rgb, const float* ts, int64_t N, int S,
+NERF_API int nerf_composite(const float* sigma, const float* rgb, const float* ts, int64_t N, int S,
                    float* deltas, float* weights, float* ray_rgb, float* depth, float* acc,
                    float* stats2, void* stream);
 
 /* ---- backward of H2+H3+H4 (training; autograd of nerf_model.py:109-111 / :128-130).  g_ray [N,3] = dL/d ray_rgb.
  * Outputs are the gradients w.r.t. the head PRE-activations (ReLU / sigmoid derivatives of nerf_model.py:352,359
  * folded in): dsigma_pre [N,S], drgb_pre [N,S,3]. */
-int nerf_composite_backward(const float* sigma, const float* rgb, const float* ts, const float* g_ray, int64_t N, int S,
+NERF_API int nerf_composite_backward(const float* sigma, const float* rgb, const float* ts, const float* g_ray, int64_t N, int S,
                             float* dsigma_pre, float* drgb_pre, void* stream);
 
 /* ---- H5: inverse-CDF fine sampling.  nerf_helpers.py:106-156.
@@ -77,23 +85,23 @@ int nerf_composite_backward(const float* sigma, const float* rgb, const float* t
  * (the reference's torch.arange(0, 1, 1/F), evaluated by the host).  cdf = sequential fp32 cumsum / last;
  * an all-zero ray has a NaN cdf and every query falls in the last bin, as upstream.
  * fine_samples [N,F,3] (nullable), fine_ts [N,F], idx [N,F] int64 lower-bound indices (nullable). */
-int nerf_fine_sample(const float* o, const float* d, const float* w, const float* ts, const float* eps,
+NERF_API int nerf_fine_sample(const float* o, const float* d, const float* w, const float* ts, const float* eps,
                      const float* u, const float* q_base, int64_t N, int C, int F, float near_, float far_,
                      float* fine_samples, float* fine_ts, int64_t* idx, void* stream);
 
 /* ---- H6: merge + sort.  nerf_model.py:116-120.  ts_a [N,A] (fine) and ts_b [N,B] (coarse) are
  * concatenated, sorted ascending per ray; samples_sorted [N,A+B,3] = o + t*d (nullable). A+B <= 1024. */
-int nerf_merge_sort(const float* o, const float* d, const float* ts_a, int A, const float* ts_b, int B,
+NERF_API int nerf_merge_sort(const float* o, const float* d, const float* ts_a, int A, const float* ts_b, int B,
                     int64_t N, float* ts_sorted, float* samples_sorted, void* stream);
 /* K3 + K4 in one launch: the sorted depths NeRFNetwork.forward feeds the fine network (nerf_model.py:114-120) straight from
  * the coarse weights / depths: inverse-CDF fine depths (as nerf_fine_sample), concatenated fine-first with the coarse ones
  * and sorted (as nerf_merge_sort), bit-identical to those two calls.  C + F <= 256.  ts_sorted [N, C+F]. */
-int nerf_fine_sample_merge(const float* w, const float* ts, const float* eps, const float* u, const float* q_base,
+NERF_API int nerf_fine_sample_merge(const float* w, const float* ts, const float* eps, const float* u, const float* q_base,
                            int64_t N, int C, int F, float near_, float far_, float* ts_sorted, void* stream);
 
 /* ---- H7: positional encoding.  nerf_model.py:19-33.  x [n,c] -> out [n, 2*L*c];
  * per frequency i: cos(2^i pi x) for the c channels, then sin(2^i pi x). */
-int nerf_positional_encoding(const float* x, int64_t n, int c, int L, float* out, void* stream);
+NERF_API int nerf_positional_encoding(const float* x, int64_t n, int c, int L, float* out, void* stream);
 
 /* ---- H8: one NeRFModel forward.  nerf_model.py:362-389.
  * params20_host: HOST array of 20 device pointers in state_dict order
@@ -102,19 +110,19 @@ int nerf_positional_encoding(const float* x, int64_t n, int c, int L, float* out
  * samples [N,S,3], direc [N,3] -> sigma [N,S], rgb [N,S,3].
  * This is the exact-fp32 CUDA-core form (any position_dim/direction_dim, any N,S); the tensor-core form is
  * nerf_mlp_forward_tc below. */
-int nerf_mlp_forward_fp32(const float* const* params20_host, int position_dim, int direction_dim,
+NERF_API int nerf_mlp_forward_fp32(const float* const* params20_host, int position_dim, int direction_dim,
                           const float* samples, const float* direc, int64_t N, int S,
                           float* sigma, float* rgb, void* stream);
 
 /* ---- K5: pack one network's weights for the tcgen05 kernels (bf16, K-major, 128B-swizzled UMMA tiles,
  * biases fp32).  position_dim must be 10 and direction_dim 4 (the only shape the tensor-core kernel is
  * specialised for).  `packed` holds nerf_packed_bytes() bytes. */
-size_t nerf_packed_bytes(void);
-int nerf_pack_weights(const float* const* params20_host, void* packed, void* stream);
+NERF_API size_t nerf_packed_bytes(void);
+NERF_API int nerf_pack_weights(const float* const* params20_host, void* packed, void* stream);
 
 /* ---- K8: NeRFModel forward on the 5th-gen tensor cores (bf16 operands, fp32 accumulation in TMEM).
  * Samples are given as rays + depths: sample (n,s) sits at o[n] + ts[n,s]*d[n].  sigma [N,S], rgb [N,S,3]. */
-int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, const float* ts,
+NERF_API int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, const float* ts,
                         int64_t N, int S, float* sigma, float* rgb, void* stream);
 /* Training form: also stores the bf16 activations each layer consumed (outputs of mlp.0, mlp.2, mlp.4, mlp.6,
  * feature_fn.0, feature_fn.2, feature_fn.4 at feature 256*k; rgb_fn.0 at 1792).  act_out: ceil(N*S/128)*128 rows x 1920
@@ -124,25 +132,25 @@ int nerf_mlp_forward_tc(const void* packed, const float* o, const float* d, cons
  * kernels write one 32-bit word per (sample, 32-feature group) at word ((row/128)*60 + f/32)*128 + row%128, bit 15-j / 31-j =
  * [pre-activation of feature 32*(f/32) + 2j / 2j+1 is negative]; the diagnostic one-tile kernels (NERF_TC_ONE_TILE=1) write 64-bit
  * words, word ((row/128)*30 + f/64)*128 + row%128, bit i = [act(row, 64*(f/64)+i) > 0].  Treat it as opaque. */
-int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
+NERF_API int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
                               int64_t N, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream);
 /* ---- backward of H8 (dgrad chain) on the tensor cores.  packed_t = nerf_pack_weights_t image (W^T stages, bf16).
  * masks: the forward's ReLU sign words (see above); dsigma_pre [N*S], drgb_pre [N*S,3] from
  * nerf_composite_backward.  dz_out: ceil(N*S/128)*128 rows x 1936 features bf16, tiled chunk-major with 242 chunks per
  * tile: gradient w.r.t. every layer's pre-activation at the same feature offsets as acts (mlp.0 .. feature_fn.4 at 256*k,
  * rgb_fn.0 at 1792) + a heads block [dsigma_pre, drgb_pre x3, 0..] at 1920; weight gradients are dz^T . (layer input). */
-size_t nerf_packed_t_bytes(void);
-int nerf_pack_weights_t(const float* const* params20_host, void* packed_t, void* stream);
-int nerf_mlp_backward_tc(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre,
+NERF_API size_t nerf_packed_t_bytes(void);
+NERF_API int nerf_pack_weights_t(const float* const* params20_host, void* packed_t, void* stream);
+NERF_API int nerf_mlp_backward_tc(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre,
                          int64_t N, int S, void* dz_out, void* stream);
 /* ---- weight / bias gradients of one network on the tensor cores: dW_l += dz_l^T . (input of layer l), db_l += sum dz_l.
  * acts, dz: the tiled chunk-major training tensors written by nerf_mlp_forward_tc_train / nerf_mlp_backward_tc;
  * o, d, ts as in the forward (PE(x) / PE(dir) operands are recomputed).  grads20_host: HOST array of 20 device pointers
  * (state_dict order, fp32, nn.Linear layout), ACCUMULATED into with atomics - zero them first. */
-int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
+NERF_API int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
                   float* const* grads20_host, void* stream);
 /* Same kernel with explicit sample points [N,S,3] (the NeRFModel.forward(samples, direc) call surface). */
-int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
+NERF_API int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
                                int64_t N, int S, float* sigma, float* rgb, void* stream);
 
 /* ---- K8 + K2 fused: NeRFModel forward (nerf_model.py:362-389) with deltas, weights, ray colour, depth and opacity
@@ -155,29 +163,29 @@ int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const f
  * sigma [N,S] / rgb [N,S,3]: nullable together (render does not need them); act_out / mask_out: non-NULL = training form
  * (as nerf_mlp_forward_tc_train; needs sigma / rgb too).  weights [N,S], depth [N], acc [N]: nullable.  ray_rgb [N,3].
  * stats4: nullable; as nerf_composite (zero it first). */
-int nerf_mlp_composite_tc_supported(int S);
-int nerf_mlp_composite_tc(const void* packed, const float* o, const float* d, const float* ts, int64_t N, int S,
+NERF_API int nerf_mlp_composite_tc_supported(int S);
+NERF_API int nerf_mlp_composite_tc(const void* packed, const float* o, const float* d, const float* ts, int64_t N, int S,
                           float* sigma, float* rgb, void* act_out, void* mask_out,
                           float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream);
 
 /* The coarse network's form of nerf_mlp_composite_tc: K1 (generate_coarse_samples, nerf_helpers.py:28-56) runs inside the kernel
  * too.  u [N,S] uniforms, t_base [S] = the reference's torch.arange(near, far, step) on the device, ts_out [N,S] receives the depths
  * t = t_base[i] + u * step (bit-identical to nerf_coarse_sample); everything else as nerf_mlp_composite_tc. */
-int nerf_mlp_composite_tc_strata(const void* packed, const float* o, const float* d, const float* u, const float* t_base, float step,
+NERF_API int nerf_mlp_composite_tc_strata(const void* packed, const float* o, const float* d, const float* u, const float* t_base, float step,
                                  int64_t N, int S, float* ts_out, float* sigma, float* rgb, void* act_out, void* mask_out,
                                  float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream);
 
 /* Both weight images (nerf_pack_weights + nerf_pack_weights_t) of both networks in ONE launch - what a training step needs
  * after the optimiser has changed the parameters.  params40_host: the 40 tensors of NeRFNetwork's state_dict order (coarse
  * network's 20, then the fine network's 20). */
-int nerf_pack_weights_all(const float* const* params40_host, void* packed0, void* packed_t0, void* packed1, void* packed_t1,
+NERF_API int nerf_pack_weights_all(const float* const* params40_host, void* packed0, void* packed_t0, void* packed1, void* packed_t1,
                           void* stream);
 
 /* ---- optimiser step.  nerf_model.py:134-143 (torch.optim.Adam, lr 5e-4, betas (0.9, 0.999), eps 1e-8, no weight decay)
  * over flat fp32 buffers of n elements (all parameters of both networks): params updated in place, exp_avg / exp_avg_sq
  * are the Adam moments, step >= 1 is the 1-based step count used for the bias corrections.  Same arithmetic and order as
  * torch's single-tensor Adam; buffers 16-byte aligned. */
-int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+NERF_API int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, int64_t step, void* stream);
 
 #ifdef __cplusplus

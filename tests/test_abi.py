@@ -27,8 +27,25 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), f"{name} declared in include/nerf_b200.h but not exported"
     import _native
     assert declared == set(_native.exported_symbols())
-    assert lib.nerf_abi_version() == 1
+    assert lib.nerf_abi_version() == 2
     assert lib.nerf_packed_bytes() == 57 * 16384 + 6 * 2048 + 1928 * 4
+
+
+def test_dynamic_symbol_table_is_exactly_the_header(lib):
+    """The product library is built with -fvisibility=hidden: `nm -D` must list the functions of include/nerf_b200.h and
+    nothing else of ours (no nerf_debug_* probes, no internal C++ symbols); the probes live in tools/libnerf_b200_debug.so."""
+    import subprocess
+    import _native
+    header = (ROOT / "include" / "nerf_b200.h").read_text()
+    declared = set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", header))
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_native.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    exported = {s for s in exported if not s.startswith(("_init", "_fini", "__bss_start", "_edata", "_end"))}
+    assert exported == declared, (sorted(exported - declared), sorted(declared - exported))
+    assert not any("debug" in s for s in exported)
+    if _native.DEBUG_LIB_PATH.exists():
+        dbg = subprocess.run(["nm", "-D", "--defined-only", str(_native.DEBUG_LIB_PATH)], capture_output=True, text=True, check=True).stdout
+        assert "nerf_debug_umma" in dbg and "nerf_debug_mlp_tc_profile" in dbg
 
 
 def test_argument_validation_without_gpu(lib):

@@ -1,5 +1,6 @@
 """GPU known-answer probe of the tcgen05 building blocks (umma.cuh): one-CTA GEMMs with A in swizzled shared
-memory (SS) or in TMEM (TS) against torch.matmul on the same bf16 inputs."""
+memory (SS) or in TMEM (TS) against torch.matmul on the same bf16 inputs.  The probe kernels live in the diagnostic
+library (tools/libnerf_b200_debug.so, csrc/debug/umma_probe.cu), not in the product library."""
 import ctypes
 
 import pytest
@@ -12,7 +13,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("K,N,d_col", [(64, 128, 0), (256, 128, 128), (256, 16, 128), (128, 256, 0), (64, 144, 0)])
 def test_umma_probe(mode, K, N, d_col):
     import _native as nat
-    fn = nat.lib().nerf_debug_umma
+    fn = nat.debug_lib().nerf_debug_umma
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                    ctypes.c_void_p]
@@ -31,7 +32,7 @@ def test_umma_probe(mode, K, N, d_col):
 def test_umma_probe_mn_major(K, N, d_col):
     """Both operands MN-major without swizzle (the wgrad form: contraction over samples): D = A^T B with A [K,128], B [K,N]."""
     import _native as nat
-    fn = nat.lib().nerf_debug_umma
+    fn = nat.debug_lib().nerf_debug_umma
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                    ctypes.c_void_p]

@@ -6,7 +6,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path[:0] = [str(ROOT), str(ROOT / "cse-573-minimal-nerf_b200")]
 import torch
 import _native as nat
-fn = nat.lib().nerf_debug_hbm_bw
+fn = nat.debug_lib().nerf_debug_hbm_bw
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 buf = torch.empty(8 << 30, dtype=torch.uint8, device="cuda")

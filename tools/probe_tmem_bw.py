@@ -5,7 +5,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path[:0] = [str(ROOT), str(ROOT / "cse-573-minimal-nerf_b200")]
 import torch
 import _native as nat
-fn = nat.lib().nerf_debug_tmem_bw
+fn = nat.debug_lib().nerf_debug_tmem_bw
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 out = torch.zeros(8, dtype=torch.int64, device="cuda")

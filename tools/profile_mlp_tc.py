@@ -54,7 +54,7 @@ if os.environ.get("NERF_PROF_PLAIN") == "1":
             ms = t0.elapsed_time(t1) / 20
             print(f"fused kernel (weights {'on' if want_w else 'off'}) N={N} S={S}: {ms:.4f} ms, {N*S*920832/ms/1e9:.1f} TFLOP/s")
     sys.exit(0)
-fn = nat.lib().nerf_debug_mlp_tc_profile
+fn = nat.debug_lib().nerf_debug_mlp_tc_profile
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p] * 4
 dbg = torch.zeros(148 * 16 + 128, dtype=torch.int64, device=dev)
@@ -72,7 +72,7 @@ ms = t0.elapsed_time(t1)
 detail = dbg[148 * 16:].double().cpu()
 c = dbg[:148 * 16].view(148, 16).double().cpu()[:G]
 tiles = c[:, 8].clamp(min=1)
-one_tile = os.environ.get("NERF_TC_ONE_TILE") == "1"
+one_tile = False          # (the one-tile schedule was removed in round 2; its counter names are kept for old records)
 names3 = ["mma_total", "mma_wait_full(weights)", "mma_wait_dfree(acc read)", "mma_wait_alo/ahi(epilogue)", "mma_wait_pe",
           "producer_wait_empty", "epiX_total", "epiX_wait_dfull", "pairs", "mma_in_issue_blocks(layer_half)", "epiX_h1: dfull->alo (x7)",
           "epiX_h1: dfull->dfree (x7)", "epiX_h1: dfull->ahi (x7)", "epiX_h0: dfull->packed (x7)"]

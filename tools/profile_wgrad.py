@@ -22,7 +22,7 @@ for _ in range(3):
     torch.cuda.synchronize()
     for name, units, t0, t1 in nat.kernel_events:
         print(f"{name}: {t0.elapsed_time(t1):.3f} ms")
-fn = nat.lib().nerf_debug_wgrad_cycles
+fn = nat.debug_lib().nerf_debug_wgrad_cycles
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p]
 buf = (ctypes.c_longlong * 320)()
