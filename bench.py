@@ -3,16 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--hw 800]
 
-One "step" = one H x W novel-view frame (default 800x800 = 640 000 rays) pushed through NeRFNetwork.forward in
-chunks of 4096 rays: stratified sampling -> coarse MLP -> compositing -> inverse-CDF sampling -> merge sort ->
-fine MLP -> compositing (64 coarse + 128 fine samples per ray), weights from a synthetic checkpoint in the
-reference's format (the shipped lego checkpoint is not available offline).
+One "step" = one H x W novel-view frame (default 800x800 = 640 000 rays) pushed through NeRFNetwork.forward by
+nerf_helpers.render_rays_chunked (the reference's 4096-ray chunks grouped into one set of launches per frame): stratified
+sampling -> coarse MLP -> compositing -> inverse-CDF sampling -> merge sort -> fine MLP -> compositing (64 coarse + 128 fine
+samples per ray), weights from a synthetic checkpoint in the reference's format (the shipped lego checkpoint is not available
+offline).
 
   value     device-resident rays, CUDA-event time per step (L2 flushed between steps), max over ranks
-  e2e       same frame through the public view_reconstruction-style path with HOST buffers: pinned rays H2D,
-            render, uint8 conversion, image D2H (and the per-frame gather at N > 1) inside the timed region
+  e2e       the same frame through the public call, nerf_helpers.view_reconstruction, with HOST buffers: pinned rays H2D,
+            render, uint8 conversion, image D2H inside the timed region (weak scaling at N > 1: one frame per rank)
+  strong    N > 1 only: ONE frame's rays sharded over the N ranks through view_reconstruction, incl. the all-gather of the
+            uint8 slabs and the D2H copy (BASELINE.json configs[4] per frame)
   roofline  fused tcgen05 MLP kernel: algorithmic FLOPs / CUDA-event time of its launches inside the timed region
-  cpu_baseline  the CPU oracle (port of the reference) on this box's host cores, bounded sample (N=1 only)
+  train     4096-ray training steps (configs[2]/[3]) + `roofline_train`: per-kernel time, bytes and fraction of peak
+  cpu_baseline  the CPU oracle (port of the reference) on this box's host cores, bounded sample (N=1 only), with the
+            PSNR of this repo's render of the same chunk against it (`parity`)
 
 `--impl reference` times the reference's CPU path (oracle port; the Python reference cannot travel to the GPU
 box) with all host threads on the same metric.  Multi-GPU (torchrun): weak scaling, one frame of the orbit per
@@ -169,13 +174,16 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args):
-    return {"workload": f"render {args.hw}x{args.hw} lego-360 orbit frame, 64 coarse + 128 fine samples/ray, ray chunk 4096, "
+    return {"workload": f"render {args.hw}x{args.hw} lego-360 orbit frame, 64 coarse + 128 fine samples/ray, ray chunk 4096 "
+                        "(chunks grouped into one set of launches per frame by nerf_helpers.render_rays_chunked), "
                         "synthetic checkpoint in the reference's PL format (dense weight set, seed 5)",
             "H": args.hw, "W": args.hw, "chunk": CHUNK, "coarse": COARSE, "fine": FINE,
             "l2": "256 MB L2 flush between timed steps; per-step uniforms (0.49 GB) exceed the 126 MB L2"}
 
 
-def cpu_baseline(args):
+def cpu_baseline(args, net=None):
+    """The CPU oracle on a bounded sample of the workload (also the one place this file checks the product against it: the
+    chunks the oracle renders are rendered by `net` with the SAME uniforms and the PSNR between the two goes into `parity`)."""
     import synthetic
     from oracle import nerf_oracle as O
     torch.set_num_threads(os.cpu_count())
@@ -185,27 +193,45 @@ def cpu_baseline(args):
     o, d = o.reshape(-1, 3), d.reshape(-1, 3)
     n = min(CHUNK, o.shape[0])
     chunks = 3
-    t_best = []
+    t_best, mse, max_abs = [], [], 0.0
     with torch.no_grad():
         for k in range(chunks):
             lo = (k * 7919 * n) % max(o.shape[0] - n + 1, 1)
             rand = (torch.rand(n, COARSE), torch.rand(n, 1), torch.rand(n, FINE, 1))
             t0 = time.perf_counter()
-            O.network_forward(sd, o[lo:lo + n], d[lo:lo + n], *rand)
+            ref = O.network_forward(sd, o[lo:lo + n], d[lo:lo + n], *rand)
             t_best.append(time.perf_counter() - t0)
+            if net is not None:
+                dev = next(net.parameters()).device
+                got = net.forward(o[lo:lo + n].contiguous().to(dev), d[lo:lo + n].contiguous().to(dev), rand=tuple(r.to(dev) for r in rand))
+                diff = (got["fine_rgb_rays"].cpu() - ref["fine_rgb_rays"]).double()
+                mse.append(float((diff ** 2).mean()))
+                max_abs = max(max_abs, float(diff.abs().max()))
     dt = float(np.mean(t_best[1:]))                     # first chunk is warm-up
-    return {"value": n / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{chunks - 1} timed 4096-ray chunks (+1 warm-up) of the same frame through the CPU oracle, no_grad, "
-                      f"{os.cpu_count()} threads"}
+    out = {"value": n / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+           "sample": f"{chunks - 1} timed 4096-ray chunks (+1 warm-up) of the same frame through the CPU oracle, no_grad, "
+                     f"{os.cpu_count()} threads"}
+    if mse:
+        m = float(np.mean(mse))
+        out["parity"] = {"what": f"fine ray colours of {chunks} x {n} rays, this repo (bf16 tensor-core path) vs the CPU oracle, same uniforms",
+                         "psnr_db": float(10 * np.log10(1.0 / max(m, 1e-20))), "max_abs": max_abs}
+    return out
 
 
 TRAIN_FLOP_PER_SAMPLE = 2 * (460416 + 460416 + 426624)     # fwd + wgrad + needed dgrad
+# algorithmic HBM bytes per sample of the training kernels: bf16 activations 1920 x 2 + sign words 60 x 4 written
+# by the forward; sign words read + dz 1936 x 2 written by dgrad; acts + dz read once by wgrad
+TRAIN_BYTES = {"mlp_tc_kernel(train)": 3840 + 240 + 16, "mlp_tc_bwd_kernel": 240 + 3872 + 16, "wgrad_tc_kernel": 3840 + 3872}
+TRAIN_FLOPS = {"mlp_tc_kernel(train)": 2 * 460416, "mlp_tc_bwd_kernel": 2 * 426624, "wgrad_tc_kernel": 2 * 460416}
 
 
 def bench_train(args, rank, world, dev):
     """BASELINE.json configs[2]/[3]: training steps on 4096-ray batches (per GPU), random-init coarse + fine MLP, Adam;
-    data-parallel across ranks with one all-reduce of the flat gradient buffer per step."""
+    data-parallel across ranks with one summed gradient per step (trainer.FlatGradients).  Batches are drawn from the centre
+    crop of analytic-scene images (what the reference does for its first `cropping_epochs`, dataloader.py:13-34), two orbit
+    poses per rank, so that the network sees the object and the loss moves."""
     import torch.distributed as dist
+    import _native as nat
     import dataloader
     import nerf_model
     import synthetic
@@ -216,13 +242,21 @@ def bench_train(args, rank, world, dev):
     net = net.to(dev)
     opt = net.configure_optimizers()["optimizer"]
     grads = FlatGradients(net.parameters(), opt)
+    n_coarse = sum(p.numel() for p in net.coarse_network.parameters())
+    if world > 1:
+        net.on_coarse_grads_ready = lambda: grads.reduce_async(n_coarse)
     H = W = 800
-    c2w, focal = frame_setup(H, W, 7 * rank + 3)
-    image = torch.from_numpy(synthetic.analytic_scene_rgba(c2w.numpy(), H, W, focal)[..., :3].copy()).to(dev)
+    views = []
+    for j in range(2):
+        c2w, focal = frame_setup(H, W, 7 * rank + 3 + 20 * j)
+        views.append((c2w, torch.from_numpy(synthetic.analytic_scene_rgba(c2w.numpy(), H, W, focal)[..., :3].copy()).to(dev)))
     n = CHUNK
+    counter = [0]
 
     def step():
-        xs, ys = dataloader.sample_random_coordinates(n, H, W, device=dev)
+        c2w, image = views[counter[0] % len(views)]
+        counter[0] += 1
+        xs, ys = dataloader.sample_random_coordinates(n, H, W, cropping=True, device=dev)
         o, d = dataloader.get_rays_at(H, W, focal, c2w, xs, ys)
         rgb = image[ys, xs].float() / 255.0
         grads.zero()
@@ -231,8 +265,10 @@ def bench_train(args, rank, world, dev):
         grads.all_reduce_mean()
         opt.step()
         return loss
+    loss_first = None
     for _ in range(max(args.warmup, 3)):
-        step()
+        loss = step()
+        loss_first = loss.detach() if loss_first is None else loss_first
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -249,15 +285,49 @@ def bench_train(args, rank, world, dev):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    loss_last = float(loss.detach())
+    nz = net.logged.get("fine_density_non_zeros") if hasattr(net, "logged") else None
+    # ---- per-kernel record (a few extra steps with CUDA events around the three tensor-core kernels; not part of the timing above)
+    nat.kernel_events = []
+    for _ in range(4):
+        step()
+    torch.cuda.synchronize()
+    events, nat.kernel_events = nat.kernel_events, None
     pk = peaks()
+    per = {}
+    for name, units, a, b in events:
+        e = per.setdefault(name, {"ms": 0.0, "samples": 0})
+        e["ms"] += a.elapsed_time(b) / 4
+        e["samples"] += units // 4
+    kernels = []
+    for name, e in per.items():
+        gb = e["samples"] * TRAIN_BYTES.get(name, 0) / 1e9
+        tf = e["samples"] * TRAIN_FLOPS.get(name, 0) / 1e12
+        sec = e["ms"] * 1e-3
+        kernels.append({"kernel": name, "ms_per_step": e["ms"], "algorithmic_gb": gb, "hbm_gbs": gb / sec, "hbm_frac": gb / sec / pk["hbm_gbs"],
+                        "tflops": tf / sec, "tensor_frac_of_sustained": tf / sec / pk["tflops_sustained"]})
+    kms = sum(k["ms_per_step"] for k in kernels)
     tfl = n * 256 * TRAIN_FLOP_PER_SAMPLE / (ms * 1e-3) / 1e12
+    dom = max(kernels, key=lambda k: k["ms_per_step"]) if kernels else None
+    roofline_train = None
+    if dom is not None:
+        hbm_bound = dom["hbm_frac"] >= dom["tensor_frac_of_sustained"]
+        roofline_train = {"bound": "hbm" if hbm_bound else "tensor", "kernel": dom["kernel"],
+                          "achieved": dom["hbm_gbs"] if hbm_bound else dom["tflops"], "peak": pk["hbm_gbs"] if hbm_bound else pk["tflops_sustained"],
+                          "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": dom["hbm_frac"] if hbm_bound else dom["tensor_frac_of_sustained"],
+                          "traffic": None, "kernels": kernels, "kernel_ms_per_step": kms, "kernel_share_of_step": kms / ms,
+                          "step_algorithmic_tflops": tfl, "step_frac_of_sustained_peak": tfl / pk["tflops_sustained"],
+                          "step_frac_of_burst_peak": tfl / pk["tflops_burst"]}
     return {"metric": "rays/sec train (device-timed)", "value": n * world / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
-            "steps": steps, "rays_per_step_per_gpu": n, "final_loss": float(loss.detach()),
+            "steps": steps, "rays_per_step_per_gpu": n, "loss_first": float(loss_first), "loss_last": loss_last, "final_loss": loss_last,
+            "fine_density_non_zeros": float(nz) if nz is not None else None,
             "algorithmic_tflops_per_gpu": tfl, "frac_of_sustained_peak": tfl / pk["tflops_sustained"],
-            "backward": "hand-written: composite_backward_kernel, mlp_tc_bwd_kernel (tcgen05 dgrad chain), "
+            "frac_of_burst_peak": tfl / pk["tflops_burst"], "roofline_train": roofline_train,
+            "data": "centre-cropped pixels of two analytic-scene orbit views per rank (synthetic), random-init weights (seed 0)",
+            "backward": "hand-written: composite_backward_kernel, mlp_tc_bwd3_kernel (tcgen05 dgrad chain), "
                         "wgrad_tc_kernel (tcgen05 wgrad + bias sums); Adam = hand-written flat kernel (adam.cu), gradients accumulated straight into the flat buffer",
-            "hbm_bytes_per_step_per_gpu_est": int(n * 256 * (3840 + 240 + 240 + 3872 + 1.14 * 7712)),
-            "collective": "one NCCL all-reduce of the 924 680-float flat gradient buffer per step" if world > 1 else None}
+            "collective": ("NCCL sum of the 924 680-float flat gradient buffer per step (coarse slice overlapped with the fine backward), "
+                           "1/world folded into the Adam kernel") if world > 1 else None}
 
 
 def emit(line):
@@ -273,7 +343,7 @@ def main():
     global _REAL_STDOUT
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)                                # fd 1 -> stderr for the rest of the process
+    os.dup2(2, 1)                                # fd 1 -> stderr for the rest of the process (NCCL_DEBUG output included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -281,6 +351,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hw", type=int, default=800, help="frame height = width")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--reference-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' runs the same eager-PyTorch port of the reference on the GPU (what the "
                          "reference itself does when a GPU is present); the contract arm is the default, 'cpu'")
@@ -295,7 +366,6 @@ def main():
         return
 
     import torch.distributed as dist
-    os.environ.pop("NCCL_DEBUG", None)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -303,6 +373,8 @@ def main():
 
     import _native as nat
     import dataloader
+    import multi_gpu
+    import nerf_helpers
     import nerf_model
     import synthetic
 
@@ -313,20 +385,15 @@ def main():
     nrays = H * W
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out = torch.empty((nrays, 3), device=dev, dtype=torch.float32)
-    host_o = torch.empty((nrays, 3), dtype=torch.float32).pin_memory()
-    host_d = torch.empty((nrays, 3), dtype=torch.float32).pin_memory()
-    host_im = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
-    gathered = torch.empty((world, H, W, 3), dtype=torch.uint8, device=dev) if world > 1 else None
+    host_o = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    host_d = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
 
-    def rays_for(step):
-        c2w, focal = frame_setup(H, W, step * world + rank)
-        o, d = dataloader.get_rays(H, W, focal, c2w, device=dev)
-        return o.reshape(nrays, 3), d.reshape(nrays, 3)
-
-    import nerf_helpers
+    def rays_for(step, per_rank=True):
+        c2w, focal = frame_setup(H, W, step * world + rank if per_rank else step)
+        return dataloader.get_rays(H, W, focal, c2w, device=dev)                # [H,W,3] each
 
     def render(o, d):                         # the chunk loop of view_reconstruction (public API), fine colours into `out`
-        nerf_helpers.render_rays_chunked(net, o, d, CHUNK, out=out)
+        nerf_helpers.render_rays_chunked(net, o.reshape(nrays, 3), d.reshape(nrays, 3), CHUNK, out=out)
 
     def barrier():
         if world > 1:
@@ -364,21 +431,25 @@ def main():
     mlp_samples = sum(u for _, u, _, _ in events)
     pk = peaks()
     achieved = mlp_samples * FLOP_PER_SAMPLE / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-    traffic = None
-    tf = ROOT / "profiles" / "mlp_tc_traffic.json"
-    if tf.exists():
-        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+    traffic, traffic_src = None, None
+    for tf in sorted((ROOT / "profiles").glob("r*_mlp_tc_traffic.json"), reverse=True):      # ncu --set full of the fine network's launch
+        rec = json.loads(tf.read_text())
+        if rec.get("rays_per_launch") == min(nrays, nerf_helpers.RAYS_PER_LAUNCH or CHUNK):       # same launch shape as this run
+            traffic, traffic_src = rec.get("dram_bytes_per_launch"), f"profiles/{tf.name}: {rec.get('what', '')}"
+            break
     roofline = {"bound": "tensor", "kernel": "mlp_tc3_kernel", "achieved": achieved, "peak": pk["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+                "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": f"{pk['source']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); "
                                f"burst {pk['tflops_burst']}",
                 "frac_of_burst": achieved / pk["tflops_burst"], "launches_timed": len(events),
                 "kernel_share_of_step": mlp_ms / (sum(step_ms) or 1.0),
+                "step_frac_of_sustained": nrays * 256 * FLOP_PER_SAMPLE / (ms_per_step * 1e-3) / 1e12 / pk["tflops_sustained"],
+                "step_frac_of_burst": nrays * 256 * FLOP_PER_SAMPLE / (ms_per_step * 1e-3) / 1e12 / pk["tflops_burst"],
                 "flop_per_sample": FLOP_PER_SAMPLE}
 
-    # ------------------------------------------------------------------ end-to-end arm (host buffers)
-    def e2e_step(k):
-        o, d = rays_for(k)                    # stands in for the reference's CPU get_rays: produce host rays first
+    # ------------------------------------------------------------------ end-to-end arm (host buffers, the public call)
+    def e2e_step(k, sharded):
+        o, d = rays_for(k, per_rank=not sharded)      # stands in for the reference's CPU get_rays: produce host rays first
         host_o.copy_(o); host_d.copy_(d)
         torch.cuda.synchronize()
         flush.fill_(k & 0xFF)
@@ -388,24 +459,36 @@ def main():
         t0.record()
         od = host_o.to(dev, non_blocking=True)           # nerf_helpers.py:184: o_rays.to(device), d_rays.to(device)
         dd = host_d.to(dev, non_blocking=True)
-        render(od, dd)
-        im = (out * 255).clamp_(0, 255).to(torch.uint8).reshape(H, W, 3)     # nerf_helpers.py:207-210
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, im)
-        host_im.copy_(im, non_blocking=True)
+        if sharded:                                      # one frame over all ranks: slabs + all-gather inside view_reconstruction
+            im = nerf_helpers.view_reconstruction(net, od, dd, N=CHUNK)
+        else:
+            with multi_gpu.local_only():                 # weak scaling: every rank renders its own frame
+                im = nerf_helpers.view_reconstruction(net, od, dd, N=CHUNK)          # uint8 numpy [H,W,3] on the host
         t1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - w0
         barrier()
+        assert im.shape == (H, W, 3) and im.dtype == np.uint8
         return t0.elapsed_time(t1), wall * 1e3
-    e2e_step(0)
-    e2e = [e2e_step(k) for k in range(args.steps)]
-    e_ms = torch.tensor([float(np.mean([max(a, b) for a, b in e2e]))], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = nrays * world / (float(e_ms.item()) * 1e-3)
 
-    train = bench_train(args, rank, world, dev)
+    def e2e_run(sharded):
+        e2e_step(0, sharded)
+        e2e = [e2e_step(k, sharded) for k in range(args.steps)]
+        t = torch.tensor([float(np.mean([max(a, b) for a, b in e2e]))], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    e_ms = e2e_run(False)
+    e2e_value = nrays * world / (e_ms * 1e-3)
+    strong = None
+    if world > 1:
+        s_ms = e2e_run(True)
+        strong = {"what": f"ONE {H}x{W} frame, rays sharded over {world} GPUs through nerf_helpers.view_reconstruction (host rays in, "
+                          "uint8 all-gather, host image out; BASELINE.json configs[4] per frame)",
+                  "ms_per_frame": s_ms, "rays_per_s": nrays / (s_ms * 1e-3), "speedup_vs_one_rank_e2e": e_ms / s_ms, "n_gpus": world,
+                  "scaling": "strong"}
+
+    train = None if args.no_train else bench_train(args, rank, world, dev)
 
     if rank == 0:
         line = {
@@ -413,11 +496,17 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(host_o.numel() * 4 * 2),
-                    "d2h_bytes_per_step": int(host_im.numel()), "ms_per_step": float(e_ms.item())},
+                    "d2h_bytes_per_step": int(H * W * 3), "ms_per_step": e_ms,
+                    "call": "nerf_helpers.view_reconstruction(model, o.to(device), d.to(device), N=4096) -> host uint8 image"},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks.summary(), "train": train,
         }
+        if train is not None and train.get("roofline_train") is not None:
+            line["roofline_train"] = train["roofline_train"]
+        if strong is not None:
+            line["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
+            line["cpu_baseline"] = cpu_baseline(args, net)
+            line["parity"] = line["cpu_baseline"].get("parity")
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -11,12 +11,15 @@ namespace nerf {
 
 __global__ void __launch_bounds__(256)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-                 float one_minus_beta1, float beta2, float one_minus_beta2, float step_size, float inv_bc2_sqrt, float eps) {
+                 float one_minus_beta1, float beta2, float one_minus_beta2, float step_size, float inv_bc2_sqrt, float eps,
+                 float grad_scale) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n4 = n >> 2;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pp = ((float4*)p)[i], mm = ((float4*)m)[i], vv = ((float4*)v)[i];
-        const float4 gg = ((const float4*)g)[i];
+        float4 gg = ((const float4*)g)[i];
+        // data parallel: the buffer holds the SUM over ranks; grad_scale = 1 / world_size (exactly 1.0f otherwise: x * 1 == x)
+        gg.x *= grad_scale; gg.y *= grad_scale; gg.z *= grad_scale; gg.w *= grad_scale;
         float* P = (float*)&pp; float* M = (float*)&mm; float* V = (float*)&vv; const float* G = (const float*)&gg;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -28,7 +31,7 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
         ((float4*)p)[i] = pp; ((float4*)m)[i] = mm; ((float4*)v)[i] = vv;
     }
     for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float gi = g[i];
+        const float gi = g[i] * grad_scale;
         const float mi = fmaf(gi - m[i], one_minus_beta1, m[i]);
         const float vi = fmaf(one_minus_beta2 * gi, gi, v[i] * beta2);
         const float denom = __fadd_rn(__fmul_rn(sqrtf(vi), inv_bc2_sqrt), eps);
@@ -42,7 +45,7 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 using namespace nerf;
 
 extern "C" int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                              float beta1, float beta2, float eps, int64_t step, void* stream) {
+                              float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream) {
     NERF_REQUIRE(n >= 0 && step >= 1, "nerf_adam_step: bad size / step");
     if (n == 0) return 0;
     NERF_REQUIRE(params && grads && exp_avg && exp_avg_sq, "nerf_adam_step: null pointer");
@@ -56,6 +59,6 @@ extern "C" int nerf_adam_step(float* params, const float* grads, float* exp_avg,
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     adam_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, 1.0f - beta1, beta2,
-                                                                    1.0f - beta2, step_size, inv_bc2_sqrt, eps);
+                                                                    1.0f - beta2, step_size, inv_bc2_sqrt, eps, grad_scale);
     return check_launch("nerf_adam_step");
 }

@@ -6,8 +6,25 @@ import torch
 import torch.distributed as dist
 
 
+import contextlib
+
+_local_only = 0
+
+
+@contextlib.contextmanager
+def local_only():
+    """Inside this context the render helpers behave as a single process (world() == (0, 1)): used where only ONE rank renders
+    (validation frames during data-parallel training), so that no all-gather waits for ranks that never arrive."""
+    global _local_only
+    _local_only += 1
+    try:
+        yield
+    finally:
+        _local_only -= 1
+
+
 def world():
-    if dist.is_available() and dist.is_initialized():
+    if not _local_only and dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
 
@@ -20,17 +37,26 @@ def ray_slab(n_rays, rank, world_size):
 
 
 def gather_slabs(local, n_rays, world_size=None):
-    """All-gather variable-length slabs [n_local, C] (uint8 or float) into [n_rays, C] on every rank."""
+    """All-gather variable-length slabs [n_local, C] (uint8 or float) into [n_rays, C] on every rank: ONE collective into one
+    [world, longest, C] tensor (slabs differ by at most one ray; shorter ones are padded)."""
     rank, ws = world()
     ws = world_size or ws
     if ws == 1:
         return local
     longest = ray_slab(n_rays, 0, ws)[1]
-    padded = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    padded[:local.shape[0]] = local
-    out = [torch.empty_like(padded) for _ in range(ws)]
-    dist.all_gather(out, padded)
-    return torch.cat([out[r][:ray_slab(n_rays, r, ws)[1] - ray_slab(n_rays, r, ws)[0]] for r in range(ws)], dim=0)
+    if local.shape[0] == longest:
+        padded = local.contiguous()
+    else:
+        padded = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded[:local.shape[0]] = local
+    out = torch.empty((ws,) + tuple(padded.shape), dtype=local.dtype, device=local.device)
+    if out.is_cuda:
+        dist.all_gather_into_tensor(out, padded)
+    else:                                        # gloo (the CPU tests of this host logic) has no flat all-gather
+        dist.all_gather(list(out.unbind(0)), padded)
+    if n_rays % ws == 0:
+        return out.reshape((n_rays,) + tuple(local.shape[1:]))
+    return torch.cat([out[r, :ray_slab(n_rays, r, ws)[1] - ray_slab(n_rays, r, ws)[0]] for r in range(ws)], dim=0)
 
 
 def sharded_render(render_rays, all_o, all_d):

@@ -178,71 +178,57 @@ def generate_360_view_synthesis(model, save_dir: Path, epoch, height=800, width=
     return views
 
 
-# Draw chunk i+1's uniforms on a side stream while chunk i is in the tensor pipe.  Measured neutral on B200
-# (tools/probe_prefetch.py: 118.0-118.2 vs 117.9-119.7 ms per 800x800 frame - the persistent MLP CTAs leave no room for a
-# 256-thread block until they exit), so it is OFF by default; the values drawn are identical either way.
-PREFETCH_UNIFORMS = False
+# The reference pushes N rays at a time through the network because eager PyTorch holds ~2.5 MB of activations per ray
+# (nerf_helpers.py:204-206).  The fused kernels keep a sample's activations on the SM and need ~2.2 KB of HBM per ray (uniforms,
+# depths, coarse weights), and their persistent CTAs loop over any number of ray groups, so consecutive chunks are GROUPED: up to
+# RAYS_PER_LAUNCH rays go through one set of launches (3 torch.rand draws + coarse kernel + sampler + fine kernel = 6 launches
+# for a whole 800x800 frame instead of 157 x 6, and one pipeline fill / drain per kernel instead of 157).  N keeps its meaning
+# as the upper bound when it is larger than RAYS_PER_LAUNCH; `RAYS_PER_LAUNCH = None` restores one launch set per N-ray chunk.
+# The uniforms are the same `torch.rand` calls in the same order, just with more rows per call.
+RAYS_PER_LAUNCH = 1 << 20
 
 
 def render_rays_chunked(model, o, d, N=4096, out=None):
-    """The chunk loop of view_reconstruction (nerf_helpers.py:196-206): `model.forward` on N rays at a time, fine colours
-    gathered into one [n,3] tensor.  The three `torch.rand` draws of a chunk (nerf_helpers.py:52,139,154) do not depend on the
-    previous chunk; with PREFETCH_UNIFORMS they are issued - in the same order, from the same generator, hence with the same
-    values - on a side stream one chunk ahead."""
+    """The chunk loop of view_reconstruction (nerf_helpers.py:196-206): `model.forward` over all rays, fine colours gathered
+    into one [n,3] tensor (`out`, written in place by the fine network's kernel)."""
     n = o.shape[0]
     if out is None:
         out = torch.empty((n, 3), device=o.device, dtype=torch.float32)
-    C, Fn = getattr(model, "coarse_samples", None), getattr(model, "fine_samples", None)
-    direct = C is not None and Fn is not None and hasattr(model, "coarse_network") and out.is_contiguous()
-    prefetch = PREFETCH_UNIFORMS and direct and n > N
-    main = torch.cuda.current_stream(o.device)
-    side = _side_stream(o.device) if prefetch else None
-
-    def draw(k):
-        with torch.cuda.stream(side):
-            r = (torch.rand((k, C), device=o.device), torch.rand((k, 1), device=o.device), torch.rand((k, Fn, 1), device=o.device))
-            ev = torch.cuda.Event()
-            ev.record(side)
-        for t in r:
-            t.record_stream(main)           # allocated on the side stream, consumed on the main one
-        return r, ev
-
+    direct = hasattr(model, "coarse_network") and hasattr(model, "fine_network") and out.is_contiguous()
+    step = N if (RAYS_PER_LAUNCH is None or not direct) else max(N, RAYS_PER_LAUNCH)
     with torch.no_grad():
-        if prefetch:
-            side.wait_stream(main)
-            nxt = draw(min(N, n))
-        for i in range(0, n, N):
-            if prefetch:
-                rand, ev = nxt
-                if i + N < n:
-                    nxt = draw(min(N, n - i - N))
-                main.wait_event(ev)
-                model.forward(o[i:i + N], d[i:i + N], rand=rand, fine_out=out[i:i + N])
-            elif direct:
-                model.forward(o[i:i + N], d[i:i + N], fine_out=out[i:i + N])          # the kernel writes into the frame buffer
+        for i in range(0, n, step):
+            if direct:
+                model.forward(o[i:i + step], d[i:i + step], fine_out=out[i:i + step])      # the kernel writes into the frame buffer
             else:
-                out[i:i + N] = model.forward(o[i:i + N], d[i:i + N])['fine_rgb_rays']
+                out[i:i + step] = model.forward(o[i:i + step], d[i:i + step])['fine_rgb_rays']
     return out
 
 
-_side_streams = {}
+_pinned = {}
 
 
-def _side_stream(dev):
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=dev)
-    return _side_streams[key]
+def _to_host_u8(image):
+    """uint8 [H,W,3] device image -> numpy array through a cached PINNED staging buffer (an asynchronous copy + one stream
+    synchronisation instead of a pageable-memory `.cpu()`); the returned array owns its memory."""
+    key = (tuple(image.shape), image.device.index)
+    if key not in _pinned:
+        _pinned[key] = torch.empty(image.shape, dtype=torch.uint8).pin_memory()
+    stage = _pinned[key]
+    stage.copy_(image, non_blocking=True)
+    torch.cuda.current_stream(image.device).synchronize()
+    return stage.numpy().copy()
 
 
 def view_reconstruction(model, all_o_rays, all_d_rays, N=4096):
-    """Render every ray of an [H,W,3] ray grid through `model` in chunks of N; returns uint8 [H,W,3].
+    """Render every ray of an [H,W,3] ray grid through `model`; returns uint8 [H,W,3] (host, numpy).
     Under torch.distributed (one process per GPU) every rank renders a contiguous slab of the rays and the uint8
     slabs are all-gathered, so each rank returns the whole image."""
     import multi_gpu
     o_all, d_all = nat.dev(all_o_rays, "all_o_rays"), nat.dev(all_d_rays, "all_d_rays")
-    # (x * 255).clamp(0, 255).to(uint8) truncates like numpy's astype(uint8) upstream (nerf_helpers.py:207-210)
-    return multi_gpu.sharded_render(lambda o, d: render_rays_chunked(model, o, d, N), o_all, d_all).cpu().numpy()
+    with torch.cuda.device(o_all.device):
+        # (x * 255).clamp(0, 255).to(uint8) truncates like numpy's astype(uint8) upstream (nerf_helpers.py:207-210)
+        return _to_host_u8(multi_gpu.sharded_render(lambda o, d: render_rays_chunked(model, o, d, N), o_all, d_all))
 
 
 def torch_to_numpy(torch_tensor, is_normalized_image=False):

@@ -203,6 +203,7 @@ class NeRFNetwork(LightningModule):
         self.timer = timer()
         self.last = {}                      # depth / acc / weights of the most recent forward
         self.keep_samples = False           # True: inference passes also materialise per-sample sigma / rgb in self.last
+        self.on_coarse_grads_ready = None   # trainer hook: called by the backward once the coarse network's gradients are queued
 
     def forward(self, o_rays, d_rays, rand=None, fine_out=None):
         """rand = (u_c [N,C], eps [N,1], u_f [N,F,1]) replaces the three torch.rand draws when given.
@@ -275,10 +276,9 @@ class NeRFNetwork(LightningModule):
         gamma = (end_lr / start_lr) ** (1 / num_epochs)
         import optim
         # one hand-written kernel over flat parameter / gradient / moment buffers (csrc/adam.cu) instead of torch's
-        # multi-tensor Adam.  It updates the parameters in place without bumping their version counters, which is what
-        # the packed bf16 weight images are keyed on: re-pack all four of them (one launch) after every step
-        optimizer = optim.FlatAdam(self.parameters(), lr=start_lr)
-        optimizer.register_step_post_hook(lambda *args, **kwargs: self.repack_all())
+        # multi-tensor Adam.  After every update the optimiser bumps the parameters' version counters (what the packed bf16
+        # weight images are keyed on) and calls back: all four images are re-packed by one launch
+        optimizer = optim.FlatAdam(self.parameters(), lr=start_lr, on_params_changed=self.repack_all)
         lr_decay = torch.optim.lr_scheduler.ExponentialLR(optimizer=optimizer, gamma=gamma)
         return {'optimizer': optimizer, 'lr_scheduler': lr_decay}
 

@@ -5,6 +5,15 @@ updates all of them with a single `nerf_adam_step` launch (csrc/adam.cu) - the s
 torch.optim.Adam's single-tensor path.  It is a `torch.optim.Optimizer`, so `ExponentialLR`, `state_dict()` /
 `load_state_dict()` and the PL-format checkpoints (`optimizer_states`) keep working, with torch.optim.Adam's state layout
 (`step`, `exp_avg`, `exp_avg_sq` per parameter; param_groups with lr / betas / eps / weight_decay / amsgrad).
+
+The kernel writes the parameters behind autograd's back.  So that nothing downstream keeps using stale derived data (the
+packed bf16 weight images of nerf_model.NeRFModel are cached on (data_ptr, _version)), `step()` itself bumps every parameter's
+version counter and then calls `on_params_changed` (NeRFNetwork.configure_optimizers passes its one-launch repack): an optimiser
+built directly with `FlatAdam(net.parameters())` therefore still invalidates the caches.  `step()` also checks that the parameters
+are still views of the flat buffer (a later `model.to()` / `.float()` would silently detach them from what the kernel updates).
+
+Data parallel: `grad_scale` (default 1.0) multiplies every gradient as the kernel reads it; trainer.Trainer sets it to
+1 / world_size, so the all-reduced SUM is never rescaled by a separate elementwise launch.
 """
 import torch
 
@@ -12,7 +21,7 @@ import _native as nat
 
 
 class FlatAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, on_params_changed=None):
         params = [p for p in params if p.requires_grad]
         if not params or not all(p.is_cuda and p.dtype == torch.float32 for p in params):
             raise RuntimeError("FlatAdam: expected fp32 CUDA parameters (this path has no CPU implementation)")
@@ -28,6 +37,8 @@ class FlatAdam(torch.optim.Optimizer):
         self.flat_m = torch.zeros(self._n, device=dev, dtype=torch.float32)
         self.flat_v = torch.zeros(self._n, device=dev, dtype=torch.float32)
         self._step = 0
+        self.grad_scale = 1.0
+        self.on_params_changed = on_params_changed
         off = 0
         for p in params:
             k = p.numel()
@@ -59,9 +70,28 @@ class FlatAdam(torch.optim.Optimizer):
             off += p.numel()
         return True
 
+    def _params_are_flat(self):
+        off = 0
+        base = self.flat_params.data_ptr()
+        for p in self._params:
+            if p.data_ptr() != base + 4 * off:
+                return False
+            off += p.numel()
+        return True
+
+    def params_changed(self):
+        """Call after writing the parameters through the flat buffer (the step kernel, a broadcast into `flat_params`, ...):
+        bumps the version counters autograd-side caches are keyed on, then runs the `on_params_changed` callback."""
+        torch.autograd.graph.increment_version(self._params)
+        if self.on_params_changed is not None:
+            self.on_params_changed()
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        if not self._params_are_flat():
+            raise RuntimeError("FlatAdam: a parameter no longer points into the optimiser's flat buffer (was the model moved or "
+                               "cast after configure_optimizers()?); rebuild the optimiser after model.to() / .float()")
         if not self._grads_are_flat():            # someone re-pointed .grad (e.g. trainer.FlatGradients): gather once
             off = 0
             for p in self._params:
@@ -75,7 +105,8 @@ class FlatAdam(torch.optim.Optimizer):
         self._step += 1
         nat.check(nat.lib().nerf_adam_step(nat.ptr(self.flat_params), nat.ptr(self.flat_grads), nat.ptr(self.flat_m),
                                            nat.ptr(self.flat_v), self._n, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
-                                           float(g["eps"]), self._step, nat.stream()), "nerf_adam_step")
+                                           float(g["eps"]), self._step, float(self.grad_scale), nat.stream()), "nerf_adam_step")
+        self.params_changed()
         return loss
 
     def state_dict(self):

@@ -54,7 +54,8 @@ def train_full_nerf(root_dir, base_dir, logger_name, steps, pos_enc, direc_enc, 
                     num_rays, coarse_samples, fine_samples, near, far, cropping_epochs, ckpt, args):
     """Coarse + fine NeRF on a Blender-synthetic scene; returns the trainer (global_step, last_checkpoint, ...)."""
     _join_process_group()
-    metrics = JsonLogger(name=logger_name, project='NeRF', save_dir=root_dir)
+    rank0 = not dist.is_initialized() or dist.get_rank() == 0
+    metrics = JsonLogger(name=logger_name, project='NeRF', save_dir=root_dir, enabled=rank0)   # one writer per run
     metrics.log_hyperparams(args)
     network = nerf_model.NeRFNetwork(position_dim=pos_enc, direction_dim=direc_enc, coarse_samples=coarse_samples,
                                      fine_samples=fine_samples, near=near, far=far)

@@ -177,6 +177,8 @@ class RenderFunction(torch.autograd.Function):
     def backward(ctx, g_c, g_f):
         net, o, d, a = ctx.net, ctx.o, ctx.d, ctx.aux
         gc = mlp_backward(net.coarse_network, o, d, a["c_ts"], a["c_sigma"], a["c_rgb"], a["c_acts"], g_c.contiguous(), True)
+        if all(g is None for g in gc) and getattr(net, "on_coarse_grads_ready", None) is not None:
+            net.on_coarse_grads_ready()      # data parallel: the coarse slice of the all-reduce overlaps the fine backward
         gf = mlp_backward(net.fine_network, o, d, a["ts"], a["f_sigma"], a["f_rgb"], a["f_acts"], g_f.contiguous(), True)
         ctx.aux = None
         return (None,) * 6 + tuple(gc) + tuple(gf)

@@ -184,9 +184,10 @@ NERF_API int nerf_pack_weights_all(const float* const* params40_host, void* pack
 /* ---- optimiser step.  nerf_model.py:134-143 (torch.optim.Adam, lr 5e-4, betas (0.9, 0.999), eps 1e-8, no weight decay)
  * over flat fp32 buffers of n elements (all parameters of both networks): params updated in place, exp_avg / exp_avg_sq
  * are the Adam moments, step >= 1 is the 1-based step count used for the bias corrections.  Same arithmetic and order as
- * torch's single-tensor Adam; buffers 16-byte aligned. */
+ * torch's single-tensor Adam; buffers 16-byte aligned.  grad_scale multiplies every gradient as it is read: 1.0f, or
+ * 1 / world_size when `grads` holds the all-reduced SUM of the data-parallel ranks (the mean is never materialised). */
 NERF_API int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                   float beta1, float beta2, float eps, int64_t step, void* stream);
+                            float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

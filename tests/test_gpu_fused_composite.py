@@ -190,7 +190,7 @@ def test_fine_depths_sorted_matches_sampler_plus_merge(N, C, F):
 
 def test_full_frame_is_independent_of_chunking_and_sharding():
     """BASELINE configs[1] size (800 x 800 = 640 000 rays, 64 + 128 samples): with the uniforms fixed per ray, the image must not
-    depend on how the rays are cut into chunks (4096 as the reference, an odd 4095, 12 345) or into per-GPU slabs - every ray is
+    depend on how the rays are cut into chunks (4096 as the reference, an odd 4095, 12 345, all 640 000 at once) or into per-GPU slabs - every ray is
     composited by exactly one CTA from its own samples, whatever tile range that CTA was given.  Also: opacity <= 1, expected
     depth inside [near, far] where the ray hit anything, sorted merged depths."""
     import dataloader
@@ -227,7 +227,7 @@ def test_full_frame_is_independent_of_chunking_and_sharding():
     assert bool(hit.any())
     mean_depth = depth[hit] / acc[hit]
     assert float(mean_depth.min()) >= 2.0 - 1e-3 and float(mean_depth.max()) <= 6.0 + 1e-3
-    for chunk in (4095, 12345):
+    for chunk in (4095, 12345, n):                           # n: the whole frame through one set of launches
         got, _, _ = render(chunk)
         assert bits_equal(got, ref), chunk
     for ws in (3, 8):                                        # per-GPU slabs of multi_gpu.ray_slab, each rendered on its own
@@ -238,21 +238,33 @@ def test_full_frame_is_independent_of_chunking_and_sharding():
     torch.cuda.synchronize()
 
 
-def test_uniform_prefetch_keeps_the_random_stream():
-    """render_rays_chunked draws chunk i+1's uniforms on a side stream: same generator, same order, so a seeded render is bit
-    for bit the render without the prefetch."""
+def test_grouped_launches_render_the_same_scene():
+    """render_rays_chunked groups the reference's N-ray chunks into launches of up to RAYS_PER_LAUNCH rays (a whole frame goes
+    through ONE set of launches).  Seeded renders are reproducible in either mode; the two modes hand different rows of the same
+    uniform stream to a ray, so the frames agree like two jittered renders of one scene (not bit for bit), and the grouped mode
+    launches 157x fewer kernels."""
     import dataloader
+    import _native as nat
     import nerf_helpers as h
+    import numpy as np
     net = make_net(5, "dense")
     H = W = 72
     o, d = dataloader.get_rays(H, W, 0.5 * W / 0.36, h.pose_spherical(-60.0, -30.0, 4.0), device=DEV)
-    frames = []
+    frames, launches = {}, {}
     try:
-        for prefetch in (False, True, True):
-            h.PREFETCH_UNIFORMS = prefetch
-            torch.manual_seed(123)
-            frames.append(h.view_reconstruction(net, o, d, N=1000))          # 5184 rays: 6 chunks, ragged last one
+        for mode in (None, 1 << 20):
+            h.RAYS_PER_LAUNCH = mode
+            for rep in range(2):
+                torch.manual_seed(123)
+                n0 = nat.launches
+                frames[(mode, rep)] = h.view_reconstruction(net, o, d, N=1000)          # 5184 rays: 6 chunks, ragged last one
+                launches[mode] = nat.launches - n0
     finally:
-        h.PREFETCH_UNIFORMS = False
-    assert frames[0].dtype.name == "uint8" and frames[0].shape == (H, W, 3)
-    assert (frames[0] == frames[1]).all() and (frames[1] == frames[2]).all()
+        h.RAYS_PER_LAUNCH = 1 << 20
+    for mode in (None, 1 << 20):
+        assert frames[(mode, 0)].dtype.name == "uint8" and frames[(mode, 0)].shape == (H, W, 3)
+        assert (frames[(mode, 0)] == frames[(mode, 1)]).all()
+    assert launches[None] == 6 * launches[1 << 20] and launches[1 << 20] <= 4
+    a, b = frames[(None, 0)].astype(np.float64), frames[(1 << 20, 0)].astype(np.float64)
+    psnr = 10 * np.log10(255.0 ** 2 / max(((a - b) ** 2).mean(), 1e-12))
+    assert psnr > 30, psnr
