@@ -144,6 +144,30 @@ def dev(t, name, dtype=torch.float32):
     return t.contiguous()
 
 
+def device_guard(fn):
+    """Run `fn` with the CUDA device of its first CUDA-tensor argument (or of `self`'s parameters) current: the wrappers launch
+    on `torch.cuda.current_stream()`, and a kernel for tensors on cuda:1 must not be queued while cuda:0 is the current device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dv = None
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda:
+                    dv = a.device
+                    break
+            elif isinstance(a, torch.nn.Module):
+                p = next(a.parameters(), None)
+                if p is not None and p.is_cuda:
+                    dv = p.device
+        if dv is None or dv.index is None or dv.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dv):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 

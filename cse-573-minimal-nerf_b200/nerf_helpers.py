@@ -48,6 +48,7 @@ def fix_batchify(batch):
         batch[key] = batch[key].squeeze(0)
 
 
+@nat.device_guard
 def generate_coarse_samples(o_rays, d_rays, num_samples, near=2.0, far=6.0, rand=None):
     """Stratified samples: returns (samples [N,num_samples,3], ts [N,num_samples,1]).
     `rand` ([N,num_samples] uniforms) replaces the internal torch.rand draw when given."""
@@ -62,6 +63,7 @@ def generate_coarse_samples(o_rays, d_rays, num_samples, near=2.0, far=6.0, rand
     return samples, ts
 
 
+@nat.device_guard
 def generate_deltas(ts):
     """delta_i = t_{i+1} - t_i with a 1e10 tail.  ts: [N,S,1] (any numeric dtype, promoted to fp32)."""
     t = nat.dev(ts, "ts")
@@ -71,6 +73,7 @@ def generate_deltas(ts):
     return out
 
 
+@nat.device_guard
 def calculate_unnormalized_weights(density, deltas):
     """w = T (1 - exp(-density * delta)); density, deltas: [N,S,1]."""
     sg, dl = nat.dev(density, "density"), nat.dev(deltas, "deltas")
@@ -80,6 +83,7 @@ def calculate_unnormalized_weights(density, deltas):
     return out
 
 
+@nat.device_guard
 def estimate_ray_color(weights, rgb):
     """sum_i w_i rgb_i.  weights [N,S,1], rgb [N,S,3] -> [N,3]."""
     w, c = nat.dev(weights, "weights"), nat.dev(rgb, "rgb")
@@ -89,6 +93,7 @@ def estimate_ray_color(weights, rgb):
     return out
 
 
+@nat.device_guard
 def composite(density, rgb, ts, want_weights=True):
     """deltas + weights + ray colour + depth + opacity in one launch (what NeRFNetwork.forward needs).
     Returns dict(weights [N,S,1], rgb [N,3], depth [N], acc [N], stats [2] = (sum sigma^2, count sigma != 0),
@@ -106,6 +111,7 @@ def composite(density, rgb, ts, want_weights=True):
     return {"weights": w, "rgb": col, "depth": depth, "acc": acc, "stats": stats[:2], "norm": stats[2]}
 
 
+@nat.device_guard
 def inverse_transform_sampling(o_rays, d_rays, weights, ts, num_samples, near=2.0, far=6.0, rand=None,
                                return_idx=False):
     """Inverse-CDF fine samples: returns (fine_samples [N,num_samples,3], fine_ts [N,num_samples,1]).
@@ -128,6 +134,7 @@ def inverse_transform_sampling(o_rays, d_rays, weights, ts, num_samples, near=2.
     return (pts, fts, idx) if return_idx else (pts, fts)
 
 
+@nat.device_guard
 def fine_depths_sorted(weights, ts, num_samples, near=2.0, far=6.0, rand=None):
     """inverse_transform_sampling + merge_samples in one launch, depths only (what NeRFNetwork.forward needs between the two
     networks, nerf_model.py:114-120): returns the sorted [N, C+num_samples, 1] depths, bit-identical to the two calls.
@@ -146,6 +153,7 @@ def fine_depths_sorted(weights, ts, num_samples, near=2.0, far=6.0, rand=None):
     return out
 
 
+@nat.device_guard
 def merge_samples(o_rays, d_rays, fine_ts, coarse_ts, want_points=True):
     """The concat + sort + gather of NeRFNetwork.forward (nerf_model.py:116-120) as one kernel.
     Returns (samples [N,A+B,3] or None, ts [N,A+B,1])."""

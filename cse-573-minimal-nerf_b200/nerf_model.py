@@ -25,6 +25,7 @@ from lightning_shim import LightningModule
 ACT_FN = nn.ReLU()
 
 
+@nat.device_guard
 def positional_encoding(x, dim=10):
     """[..., C] -> [..., 2*dim*C]: per frequency i, cos(2^i pi x) for all channels then sin(2^i pi x)."""
     t = nat.dev(x, "x")
@@ -78,6 +79,7 @@ class NeRFModel(nn.Module):
     def uses_tensor_cores(self):
         return self.precision == "bf16" and self.position_dim == 10 and self.direction_dim == 4
 
+    @nat.device_guard
     def packed_weights(self):
         """bf16 swizzled weight image for the tcgen05 kernel; re-packed whenever a parameter changed."""
         params = self.ordered_params()
@@ -90,6 +92,7 @@ class NeRFModel(nn.Module):
             self._packed_key = key
         return self._packed
 
+    @nat.device_guard
     def packed_weights_t(self):
         """W^T stage image for the tcgen05 dgrad kernel (training); re-packed whenever a parameter changed."""
         params = self.ordered_params()
@@ -103,6 +106,7 @@ class NeRFModel(nn.Module):
         return self._packed_t
 
     # ---- forward
+    @nat.device_guard
     def forward(self, samples, direc):
         """samples [N,S,3], direc [N,3] -> density [N,S,1], rgb [N,S,3]."""
         x, dr = nat.dev(samples, "samples"), nat.dev(direc, "direc")
@@ -118,6 +122,7 @@ class NeRFModel(nn.Module):
                                                       N, S, nat.ptr(sigma), nat.ptr(rgb), nat.stream()), "nerf_mlp_forward_fp32")
         return sigma, rgb
 
+    @nat.device_guard
     def forward_rays(self, o_rays, d_rays, ts):
         """Same network evaluated at o + t*d for ts [N,S,1] without materialising the points."""
         N, S = ts.shape[0], ts.shape[1]
@@ -137,6 +142,7 @@ class NeRFModel(nn.Module):
         """True when render_rays can run (tensor-core shape, sample count the fused kernel supports)."""
         return self.uses_tensor_cores() and bool(nat.lib().nerf_mlp_composite_tc_supported(int(S)))
 
+    @nat.device_guard
     def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False, stats=None, out=None, strata=None):
         """Network + alpha compositing in ONE kernel (nerf_mlp_composite_tc): the per-sample sigma / rgb stay on the SM
         unless `keep_samples` (or `save`, the training form, which also stores activations + ReLU sign words).
@@ -205,6 +211,7 @@ class NeRFNetwork(LightningModule):
         self.keep_samples = False           # True: inference passes also materialise per-sample sigma / rgb in self.last
         self.on_coarse_grads_ready = None   # trainer hook: called by the backward once the coarse network's gradients are queued
 
+    @nat.device_guard
     def forward(self, o_rays, d_rays, rand=None, fine_out=None):
         """rand = (u_c [N,C], eps [N,1], u_f [N,F,1]) replaces the three torch.rand draws when given.
         fine_out (inference only): contiguous [N,3] fp32 tensor that receives 'fine_rgb_rays' directly (a slice of a frame
@@ -222,7 +229,19 @@ class NeRFNetwork(LightningModule):
         else:
             c_rgb, f_rgb, aux = training.forward_pass(self, o, d, rand, save=False, keep_samples=self.keep_samples, fine_out=fine_out)
             self._publish(aux)
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                # forward-only kernels: usable as before, but a backward through the result fails with the reason
+                c_rgb, f_rgb = training.NotDifferentiable.apply(self.TRAINABLE_ONLY, params[0], c_rgb, f_rgb)
         return {'fine_rgb_rays': f_rgb, 'coarse_rgb_rays': c_rgb}
+
+    TRAINABLE_ONLY = ("NeRFNetwork: the differentiable path exists for precision='bf16' with position_dim=10, direction_dim=4 (the fused "
+                      "tcgen05 kernels) only; this network runs the forward-only exact-fp32 kernel - it can render, not train")
+
+    def check_trainable(self):
+        """Raises, at construction time of a training run, what a later loss.backward() would raise."""
+        if not (self.coarse_network.uses_tensor_cores() and self.fine_network.uses_tensor_cores()):
+            raise RuntimeError(self.TRAINABLE_ONLY + f" (got position_dim={self.position_dim}, direction_dim={self.direction_dim}, "
+                               f"precision={self.coarse_network.precision!r})")
 
     def _publish(self, aux):
         """The four density statistics the reference logs inside forward (nerf_model.py:105-106,124-125) + extras."""
@@ -235,6 +254,7 @@ class NeRFNetwork(LightningModule):
                      "coarse_weights": c["weights"], "coarse_sigma": aux["c_sigma"], "fine_sigma": aux["f_sigma"],
                      "coarse_rgb": aux["c_rgb"], "fine_rgb": aux["f_rgb"]}
 
+    @nat.device_guard
     def repack_all(self):
         """All four bf16 weight images (forward + W^T, both networks) in one launch; called after every optimiser step, whose
         in-place update does not bump the parameters' version counters (the keys the cached images are checked against)."""

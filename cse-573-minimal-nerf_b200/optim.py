@@ -103,10 +103,11 @@ class FlatAdam(torch.optim.Optimizer):
                 off += k
         g = self.param_groups[0]
         self._step += 1
-        nat.check(nat.lib().nerf_adam_step(nat.ptr(self.flat_params), nat.ptr(self.flat_grads), nat.ptr(self.flat_m),
-                                           nat.ptr(self.flat_v), self._n, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
-                                           float(g["eps"]), self._step, float(self.grad_scale), nat.stream()), "nerf_adam_step")
-        self.params_changed()
+        with torch.cuda.device(self.flat_params.device):
+            nat.check(nat.lib().nerf_adam_step(nat.ptr(self.flat_params), nat.ptr(self.flat_grads), nat.ptr(self.flat_m),
+                                               nat.ptr(self.flat_v), self._n, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                               float(g["eps"]), self._step, float(self.grad_scale), nat.stream()), "nerf_adam_step")
+            self.params_changed()
         return loss
 
     def state_dict(self):

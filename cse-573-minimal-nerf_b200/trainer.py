@@ -145,6 +145,8 @@ class Trainer:
         return path
 
     def fit(self, model, datamodule=None, train_dataloaders=None, val_dataloaders=None):
+        if hasattr(model, "check_trainable"):
+            model.check_trainable()                        # e.g. train_nerf.py -p / -d other than 10 / 4: fail before any work
         model = model.to(self.device)
         model.trainer, model.logger = self, self.logger
         if datamodule is not None:

@@ -162,6 +162,21 @@ def forward_pass(net, o, d, rand, save, keep_samples=False, fine_out=None):
     return c["rgb"], f["rgb"], aux
 
 
+class NotDifferentiable(torch.autograd.Function):
+    """Marks the outputs of a forward that has no hand-written backward (precision="fp32" or encoding sizes other than 10 / 4:
+    the exact-fp32 CUDA-core kernel is forward-only).  The forward works as before; a `.backward()` through it fails HERE, with
+    a message that names the cause, instead of deep inside torch with "element 0 of tensors does not require grad"."""
+
+    @staticmethod
+    def forward(ctx, why, anchor, *outputs):
+        ctx.why = why
+        return tuple(t.view_as(t) for t in outputs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise RuntimeError(ctx.why)
+
+
 class RenderFunction(torch.autograd.Function):
     """(o, d, u_c, eps, u_f, *40 parameters) -> (coarse_rgb_rays [N,3], fine_rgb_rays [N,3])."""
 

@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 sys.path.insert(0, str(HERE / "stubs"))
 sys.path.insert(0, "/root/reference")
-sys.path.insert(0, str(ROOT / "cse-573-minimal-nerf_b200"))
+sys.path.append(str(ROOT / "cse-573-minimal-nerf_b200"))      # `synthetic` only: the reference's same-named modules must win
 os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
 import numpy as np
@@ -262,6 +262,92 @@ def gen_render():
     with RandStream(600):
         im = ref_helpers.view_reconstruction(net, o, d, N=4096)
     save("render100", image=im, c2w=c2w, focal=np.float64(focal))
+
+
+TRAJ_STEPS, TRAJ_RAYS, TRAJ_VIEWS = 200, 512, 8
+
+
+def trajectory_batch(step, images=None):
+    """Batch `step` of the training-trajectory fixture, a pure function of the step (tests/test_gpu_trajectory.py rebuilds it on
+    the device): TRAJ_RAYS centre-cropped pixels (dataloader.py:13-34 with cropping) of orbit view step % TRAJ_VIEWS of the analytic
+    scene, colours from that view's image."""
+    H = W = 800
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    v = step % TRAJ_VIEWS
+    c2w = synthetic.orbit_pose(-180.0 + 45.0 * v, -30.0, 4.0)
+    xs = (synthetic.uniforms(9000 + 2 * step, (TRAJ_RAYS,)) * (W // 2)).astype(np.int64) + W // 4
+    ys = (synthetic.uniforms(9001 + 2 * step, (TRAJ_RAYS,)) * (H // 2)).astype(np.int64) + H // 4
+    return v, c2w, focal, xs, ys
+
+
+def gen_trajectory():
+    """~200 optimiser steps of the UNMODIFIED reference (NeRFNetwork.training_step + the Adam of configure_optimizers,
+    nerf_model.py:134-169) from the synthetic random-init weights on recorded batches / uniforms: the loss trajectory, the
+    "briefly-trained" weight set it ends on, a 1024-ray step on that set with all 40 gradients (8c(vi)) and
+    a 100x100 frame rendered with it next to the analytic ground truth (delta-PSNR fixture)."""
+    import time
+    H = W = 800
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    images = []
+    for v in range(TRAJ_VIEWS):
+        c2w = synthetic.orbit_pose(-180.0 + 45.0 * v, -30.0, 4.0)
+        images.append(synthetic.analytic_scene_rgba(c2w.numpy(), H, W, focal)[..., :3].astype(np.float32) / 255.0)
+    net = load_model(synthetic.make_state_dict(0, "init"))
+    opt = net.configure_optimizers()["optimizer"]
+    assert type(opt).__name__ == "Adam" and opt.param_groups[0]["lr"] == 5e-4
+    losses, stats = [], []
+    t0 = time.time()
+    for step in range(TRAJ_STEPS):
+        v, c2w, focal, xs, ys = trajectory_batch(step)
+        o, d = ref_data.get_rays(H, W, focal, c2w)
+        o, d = o[ys, xs, :].contiguous(), d[ys, xs, :].contiguous()
+        rgb = T(images[v][ys, xs, :])
+        with RandStream(20000 + 3 * step):
+            loss = net.training_step({"origin": o[None].clone(), "direc": d[None].clone(), "rgb": rgb[None].clone()}, step)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append([float(net.logged["train_loss"]), float(net.logged["train_coarse_loss"]), float(net.logged["train_fine_loss"])])
+        stats.append([float(net.logged[k]) for k in ("coarse_density_norms", "coarse_density_non_zeros", "fine_density_norms", "fine_density_non_zeros")])
+        if step % 10 == 0:
+            print(f"step {step}: loss {losses[-1][0]:.5f} fine nz {stats[-1][3]:.0f} ({time.time() - t0:.0f} s)", flush=True)
+    arrs = {"losses": np.array(losses), "stats": np.array(stats), "steps": np.int64(TRAJ_STEPS), "rays": np.int64(TRAJ_RAYS)}
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    for k, v in sd.items():
+        arrs[f"sd__{k}"] = v
+    # ---- a 1024-ray training step on the trained set: loss, forward, every gradient (full tensors for the small ones,
+    # 16 x 32 corner blocks + norms for the 256-wide ones)
+    N = 1024
+    o, d, xs, ys, c2w, focal = orbit_rays(70.0, N, 71)
+    xs, ys = xs // 2 + 200, ys // 2 + 200
+    o_all, d_all = ref_data.get_rays(H, W, focal, c2w)
+    o, d = o_all[ys, xs, :].contiguous(), d_all[ys, xs, :].contiguous()
+    img = synthetic.analytic_scene_rgba(c2w.numpy(), H, W, focal)[..., :3].astype(np.float32) / 255.0
+    target = T(img[ys.numpy(), xs.numpy(), :])
+    net.zero_grad()
+    with RandStream(30000):
+        loss = net.training_step({"origin": o[None].clone(), "direc": d[None].clone(), "rgb": target[None].clone()}, 0)
+    loss.backward()
+    with RandStream(30000), torch.no_grad():
+        pred = net.forward(o, d)
+    arrs.update(g_o=o, g_d=d, g_target=target, g_loss=loss.detach(), g_fine=pred["fine_rgb_rays"], g_coarse=pred["coarse_rgb_rays"])
+    names, norms = [], []
+    for k, p in net.named_parameters():
+        names.append(k)
+        norms.append(float(p.grad.norm()))
+        arrs[f"grad__{k}"] = p.grad.clone() if p.grad.numel() <= 1024 else p.grad[:16, :32].clone()
+    arrs["grad_names"] = np.array(names)
+    arrs["grad_norms"] = np.array(norms)
+    # ---- 100 x 100 frame with the trained set + the analytic ground truth of the same camera
+    Hs = Ws = 100
+    focal_s = 0.5 * Ws / np.tan(0.5 * 0.6911112070083618)
+    c2w = ref_helpers.pose_spherical(30.0, -30.0, 4.0)
+    o, d = ref_data.get_rays(Hs, Ws, focal_s, c2w)
+    with RandStream(31000):
+        im = ref_helpers.view_reconstruction(net, o, d, N=4096)
+    arrs.update(frame=im, frame_gt=synthetic.analytic_scene_rgba(c2w.numpy(), Hs, Ws, focal_s)[..., :3], frame_c2w=c2w,
+                frame_focal=np.float64(focal_s))
+    save("trajectory", **arrs)
 
 
 if __name__ == "__main__":

@@ -105,3 +105,40 @@ def test_score_metrics_match_oracle_and_entry_point(scene, tmp_path):
     synthetic.make_checkpoint(ckpt, synthetic.make_state_dict(5, "dense"))
     psnr, ssim = score.calculate_scores(str(ckpt), scene, 8192)
     assert np.isfinite(psnr) and 0.0 < psnr < 60.0 and -1.0 <= ssim <= 1.0
+
+
+def test_validation_step_and_logged_reconstruction(scene, tmp_path):
+    """The every-n-epochs validation of train_nerf.py:26-29 / nerf_model.py:171-205 with n = 1: validation_step runs on the val
+    image, logs val_loss / val_fine_loss / val_coarse_loss, renders the full 800x800 frame through view_reconstruction and hands it
+    to the logger (recon_*.png), then training continues and the checkpoint is written."""
+    import json
+    import dataloader
+    import nerf_model
+    from trainer import JsonLogger, Trainer
+    torch.manual_seed(5)
+    logger = JsonLogger(name="val", project="NeRF", save_dir=tmp_path)
+    net = nerf_model.NeRFNetwork()
+    net.load_state_dict(synthetic.make_state_dict(4, "dense"))
+    scene_dm = dataloader.SyntheticDataModule(scene, 256, cropping_epochs=1)
+    run = Trainer(gpus=1, default_root_dir=tmp_path, max_steps=6, logger=logger, check_val_every_n_epoch=1, track_grad_norm=2,
+                  log_every_n_steps=1)
+    run.fit(net, datamodule=scene_dm)
+    assert run.global_step == 6 and run.current_epoch == 2                            # 3 train images per epoch
+    pngs = sorted((tmp_path / "NeRF" / "val").glob("recon_*.png"))
+    assert len(pngs) >= 1
+    from PIL import Image
+    im = np.asarray(Image.open(pngs[0]))
+    assert im.shape == (800, 800, 3) and im.dtype == np.uint8 and im.max() > 0
+    for key in ("val_loss", "val_fine_loss", "val_coarse_loss"):
+        assert key in net.logged and np.isfinite(float(net.logged[key])), key
+    lines = [json.loads(l) for l in open(tmp_path / "NeRF" / "val" / "metrics.jsonl")]
+    assert any("val_loss" in l for l in lines) and any("grad_2.0_norm_total" in l for l in lines)
+    assert net.training                                                                # validate() puts the model back in train mode
+
+
+def test_non_default_encodings_are_refused_up_front(scene, tmp_path):
+    """train_nerf.py -p / -d (train_nerf.py:68-69 upstream) other than 10 / 4: the B200 training kernels are specialised, so the run
+    stops at construction with the reason instead of dying in loss.backward()."""
+    import train_nerf
+    with pytest.raises(RuntimeError, match="differentiable path exists"):
+        train_nerf.main(["-n", "odd", "--gpu", "-s", "2", "-rd", str(tmp_path), "-r", "64", "-p", "6", "-d", "2", "full", "-b", str(scene)])

@@ -65,7 +65,7 @@ def test_forward_bf16_dense(golden):
         diff = (out[key].cpu() - T(g[f"{key}_dense"])).abs()
         psnr = 10 * np.log10(1.0 / max(float((diff ** 2).mean()), 1e-20))
         print(f"{key}: max {diff.max():.3e} mean {diff.mean():.3e} PSNR-vs-reference {psnr:.1f} dB")
-        assert diff.mean() < 1e-3 and diff.max() < 8e-3 and psnr > 50.0
+        assert diff.mean() < 5e-4 and diff.max() < 5e-3 and psnr > 60.0          # the stated bf16 contract
     assert out["fine_rgb_rays"].shape == (64, 3)
     assert net.last["depth"].shape == (64,) and (net.last["acc"] <= 1 + 1e-5).all()
 
@@ -88,7 +88,7 @@ def test_render_100x100(golden):
     g = golden["render100"]
     o, d = dataloader.get_rays(100, 100, float(g["focal"]), T(g["c2w"]))
     real_rand = torch.rand
-    for precision, min_psnr in (("fp32", 45.0), ("bf16", 40.0)):
+    for precision, min_psnr in (("fp32", 80.0), ("bf16", 60.0)):
         net = make_net(5, "dense", precision)
         state = {"k": 0}
 
@@ -97,10 +97,12 @@ def test_render_100x100(golden):
             state["k"] += 1
             return out
         torch.rand = fake_rand
+        h.RAYS_PER_LAUNCH = None           # the reference's own chunking: its frame consumed one (u_c, eps, u_f) triple per 4096 rays
         try:
             im = h.view_reconstruction(net, o, d, N=4096)
         finally:
             torch.rand = real_rand
+            h.RAYS_PER_LAUNCH = 1 << 20
         assert im.shape == (100, 100, 3) and im.dtype == np.uint8
         psnr = O.psnr_uint8(im, g["image"])
         diff = np.abs(im.astype(np.int32) - g["image"].astype(np.int32))

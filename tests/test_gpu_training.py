@@ -63,16 +63,53 @@ def test_training_step_gradients_match_reference(golden, kind, seed):
         assert got is not None and got.shape == params[n].shape, n
         rel = abs(float(got.norm()) - ref_norm) / max(ref_norm, 1e-12)
         worst = max(worst, rel)
-        assert rel < 0.10, f"{n}: |grad| {float(got.norm()):.4e} vs reference {ref_norm:.4e}"
+        assert rel < 0.03, f"{n}: |grad| {float(got.norm()):.4e} vs reference {ref_norm:.4e}"
         key = f"grad_{kind}__{n}"
         if key in g.files:                      # full tensors for biases and the two small heads
             ref = T(g[key])
             cos = F.cosine_similarity(got.cpu().flatten(), ref.flatten(), dim=0).item()
-            assert cos > 0.995, f"{n}: cosine {cos}"
+            assert cos > 0.999, f"{n}: cosine {cos}"
         else:
             ref = T(g[f"gradhead_{kind}__{n}"])
             torch.testing.assert_close(got.cpu()[:4, :8], ref, rtol=0.1, atol=0.15 * float(ref.abs().max()) + 1e-9)   # bf16 chain: element-wise within 15 % of the block scale
     print(f"loss {loss.item():.6f} (reference {ref_loss:.6f}); worst gradient-norm deviation {worst:.3%}")
+
+
+def test_gradient_run_to_run_spread_is_atomics_noise(golden):
+    """wgrad adds its per-CTA partial sums with fp32 atomics, so gradients are not bit-reproducible: bound the spread.  Five
+    backward passes over the same batch: every parameter's gradient stays within 1e-5 (relative 2-norm) of the first run's."""
+    g = golden["network"]
+    net = make_net(4, "dense")
+    o, d, target = T(g["o"], DEV), T(g["d"], DEV), T(g["target"], DEV)
+    runs = []
+    for _ in range(5):
+        net.zero_grad(set_to_none=True)
+        pred = net.forward(o, d, rand=rand_triple(540, 64, device=DEV))
+        (F.mse_loss(pred["coarse_rgb_rays"], target) + F.mse_loss(pred["fine_rgb_rays"], target)).backward()
+        runs.append([p.grad.double().clone() for p in net.parameters()])
+    worst = 0.0
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            worst = max(worst, float((a - b).norm() / a.norm().clamp(min=1e-30)))
+    print(f"worst relative gradient difference between identical runs: {worst:.2e}")
+    assert worst < 1e-5
+
+
+def test_forward_only_networks_fail_backward_with_the_reason():
+    """precision='fp32' / other encoding sizes run the forward-only exact kernel: forward works with gradients enabled, the
+    backward raises a RuntimeError that says why; a training run refuses them up front (train_nerf.py -p / -d)."""
+    import nerf_model
+    import trainer
+    for kw in (dict(precision="fp32"), dict(position_dim=6, direction_dim=2)):
+        net = nerf_model.NeRFNetwork(**kw).to(DEV)
+        o = torch.zeros(8, 3, device=DEV)
+        d = F.normalize(torch.ones(8, 3, device=DEV), dim=1)
+        out = net.forward(o, d)
+        assert out["fine_rgb_rays"].shape == (8, 3) and torch.isfinite(out["fine_rgb_rays"]).all()
+        with pytest.raises(RuntimeError, match="differentiable path exists"):
+            out["fine_rgb_rays"].sum().backward()
+        with pytest.raises(RuntimeError, match="differentiable path exists"):
+            trainer.Trainer(max_steps=1, save_checkpoints=False).fit(net, train_dataloaders=[])
 
 
 def test_no_gradient_from_fine_loss_into_coarse_network(golden):

@@ -170,3 +170,36 @@ def test_score_oracle_known_answers():
     noisy = np.clip(a.astype(np.int16) + rng.integers(-3, 4, size=a.shape), 0, 255).astype(np.uint8)
     other = rng.integers(0, 256, size=a.shape, dtype=np.uint8)
     assert S.structural_similarity(a, noisy) > 0.98 > 0.2 > S.structural_similarity(a, other)
+
+
+def test_oracle_training_path_matches_reference_trajectory(golden):
+    """Pins the oracle's loss + autograd path (oracle.training_loss / loss_and_grads) against the UNMODIFIED reference's
+    training run (tests/golden/trajectory.npz): the first step's loss on the recorded batch, and the 1024-ray step on the
+    briefly-trained weight set - loss, both ray-colour outputs and every gradient the fixture holds."""
+    import numpy as np
+    import synthetic
+    from oracle import nerf_oracle as O
+    from util import T, rand_triple
+    g = golden["trajectory"]
+    rays = int(g["rays"])
+    H = W = 800
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    c2w = synthetic.orbit_pose(-180.0, -30.0, 4.0)
+    xs = T((synthetic.uniforms(9000, (rays,)) * (W // 2)).astype(np.int64) + W // 4)
+    ys = T((synthetic.uniforms(9001, (rays,)) * (H // 2)).astype(np.int64) + H // 4)
+    o, d = O.get_rays(H, W, focal, c2w, xs, ys)
+    img = synthetic.analytic_scene_rgba(c2w.numpy(), H, W, focal)[..., :3].astype(np.float32) / 255.0
+    target = T(img[ys.numpy(), xs.numpy(), :])
+    with torch.no_grad():
+        loss0, _ = O.training_loss(synthetic.make_state_dict(0, "init"), o.contiguous(), d, target, *rand_triple(20000, rays))
+    assert abs(float(loss0) - g["losses"][0, 0]) < 1e-6
+    sd = {k[4:]: T(g[k]) for k in g.files if k.startswith("sd__")}
+    loss, grads, out = O.loss_and_grads(sd, T(g["g_o"]), T(g["g_d"]), T(g["g_target"]), *rand_triple(30000, 1024))
+    assert abs(float(loss) - float(g["g_loss"])) < 1e-6
+    torch.testing.assert_close(out["fine_rgb_rays"], T(g["g_fine"]), atol=1e-6, rtol=0)
+    torch.testing.assert_close(out["coarse_rgb_rays"], T(g["g_coarse"]), atol=1e-6, rtol=0)
+    for n, ref_norm in zip([str(x) for x in g["grad_names"]], g["grad_norms"]):
+        got = grads[n]
+        assert abs(float(got.norm()) - ref_norm) <= 1e-4 * ref_norm + 1e-12, n
+        blk = got if got.numel() <= 1024 else got[:16, :32]
+        torch.testing.assert_close(blk, T(g[f"grad__{n}"]), atol=1e-5 * float(T(g[f"grad__{n}"]).abs().max()) + 1e-12, rtol=1e-3)
