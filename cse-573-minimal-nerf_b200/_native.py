@@ -43,9 +43,8 @@ _PROTOTYPES = {
     "nerf_mlp_forward_tc_train": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     "nerf_packed_t_bytes": (ctypes.c_size_t, []),
     "nerf_pack_weights_t": (_int, [_vp, _vp, _vp]),
-    "nerf_mlp_backward_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _int, _vp]),
-    "nerf_backward_flags_bytes": (ctypes.c_size_t, [_i64, _int]),
-    "nerf_wgrad_tc": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
+    "nerf_mlp_backward_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    "nerf_wgrad_tc": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "nerf_mlp_forward_tc_points": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "nerf_mlp_composite_tc_supported": (_int, [_int]),
     "nerf_mlp_composite_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -173,5 +172,5 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def stream(s=None):
-    return ctypes.c_void_p((s if s is not None else torch.cuda.current_stream()).cuda_stream)
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

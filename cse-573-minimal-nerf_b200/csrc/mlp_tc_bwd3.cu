@@ -11,14 +11,6 @@
 // 1 = pre-activation negative; they are applied to the PACKED bf16 pairs (shift + PRMT sign replication + AND-NOT: three
 // instructions per pair).
 // mlp.0's dgrad (d PE) is not needed: the inputs carry no gradient.
-//
-// FLAGS form (the training step's default): the kernel runs CONCURRENTLY with wgrad_tc_kernel, which is launched on a second
-// stream on the SMs this launch leaves free, and hands every block of dz over through L2 as soon as it is stored instead of
-// through a kernel boundary (and HBM): `ready` holds 8 counters per tile pair - [0] the dr block of rgb_fn.0 + the heads
-// block (4 producer warps), [1 + k] chain step k (dz6, dz5 .. dz0; one count per pair).  The 16 epilogue warps arrive on a
-// shared-memory barrier once their stores of a chain step are issued; producer warp 20 - idle once the next pair's dr tile is
-// built - waits for that barrier and publishes the step with red.release.gpu (release is cumulative over the barrier: the
-// pattern of a split-K semaphore), so the epilogue warps never execute a gpu-scope fence themselves.
 #include <type_traits>
 #include "mlp_tc3_common.cuh"
 
@@ -61,20 +53,11 @@ constexpr uint32_t kOffTmemHolder = kOffBars + t3::kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemHolder + 16 + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 constexpr int kStagesT = pk::kStagesT;                            // 52 requests of 16 KB per tile pair
-constexpr uint32_t kBarStepDone = t3::kBarOutFull;                // FLAGS form: 2 barriers (even / odd chain steps), 16 arrivals each
-constexpr int kChainSteps = 7;
 }  // namespace b3
 
-// dz stores: written once and read by wgrad.  Stand-alone form: streaming (evict-first, the reader is a later kernel and the
-// 4 GB do not fit the L2 anyway).  FLAGS form: plain stores - the reader is already running and should find the lines in L2.
-template <bool KEEP, class T> __device__ __forceinline__ void store_dz(T* p, T v) {
-    if (KEEP) *p = v; else store_once(p, v);
-}
-
-template <bool FLAGS>
 __global__ void __launch_bounds__(t3::kThreads, 1)
 mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restrict__ masks32, const float* __restrict__ dsigma_pre,
-                   const float* __restrict__ drgb_pre, int64_t total, __nv_bfloat16* __restrict__ dz_out, uint32_t* __restrict__ ready) {
+                   const float* __restrict__ drgb_pre, int64_t total, __nv_bfloat16* __restrict__ dz_out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = umma::smem_u32(smem);
@@ -97,7 +80,6 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
             umma::mbar_init(&b[t3::kBarPexFull + i], t3::kPEWarps);     // dr tile written
             umma::mbar_init(&b[t3::kBarPexEmpty + i], 1);               // dr tile no longer read
             umma::mbar_init(&b[t3::kBarTurn + i], 1);
-            umma::mbar_init(&b[b3::kBarStepDone + i], t3::kEpiWarps);
         }
         umma::fence_mbar_init();
     }
@@ -151,16 +133,6 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
         const int r = (warp - 20) * 32 + lane;
         const float* W9 = sConst;
         uint32_t it = 0;
-        // FLAGS: warp 20 relays the chain steps of pair `p` (epilogue warps -> shared-memory barrier -> global counter)
-        auto relay_steps = [&](int64_t p, uint32_t pair_index) {
-            for (int k = 0; k < b3::kChainSteps; ++k) {
-                const uint32_t sg = pair_index * b3::kChainSteps + (uint32_t)k;
-                umma::mbar_wait_u32(bars + 8u * (b3::kBarStepDone + (sg & 1u)), (sg >> 1) & 1u);
-                if (lane == 0) umma::red_release_gpu_add(ready + p * 8 + 1 + k, 1u);
-                __syncwarp();
-            }
-        };
-        int64_t prev_pair = -1;
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
@@ -190,26 +162,19 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                     const uint4 q4 = make_uint4(v[0], v[1], v[2], v[3]);
                     const int kb = c >> 3, cc = c & 7;            // K block, chunk inside its 128-byte row
                     *(uint4*)(tile_smem + kb * 16384 + r * 128 + ((cc ^ (r & 7)) << 4)) = q4;
-                    if (store) store_dz<FLAGS>((uint4*)(dz_out + pk::tiled_offset(row, 1792 + c * 8, pk::kDzChunks)), q4);
+                    if (store) *(uint4*)(dz_out + pk::tiled_offset(row, 1792 + c * 8, pk::kDzChunks)) = q4;
                 }
                 if (store) {   // heads block (features 1920..1935): [dsigma_pre, drgb_pre x3, 0 ...] in bf16 for the head weight gradients
                     const float dsg = valid ? dsigma_pre[row] : 0.f;
                     uint4* dst = (uint4*)(dz_out + pk::tiled_offset(row, 1920, pk::kDzChunks));
-                    store_dz<FLAGS>(dst, make_uint4(umma::pack_bf16(dsg, g0), umma::pack_bf16(g1, g2), 0u, 0u));
-                    store_dz<FLAGS>(dst + 128, make_uint4(0u, 0u, 0u, 0u));
+                    dst[0] = make_uint4(umma::pack_bf16(dsg, g0), umma::pack_bf16(g1, g2), 0u, 0u);
+                    dst[128] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 umma::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive_u32(bars + 8u * (t3::kBarPexFull + t));
             }
-            if (FLAGS) {
-                // this warp's rows of the pair's dr blocks + heads blocks are stored (the __syncwarp above orders the lanes)
-                if (lane == 0) umma::red_release_gpu_add(ready + pair * 8, 1u);
-                if (warp == 20 && prev_pair >= 0) relay_steps(prev_pair, it - 1u);
-                prev_pair = pair;
-            }
         }
-        if (FLAGS && warp == 20 && prev_pair >= 0) relay_steps(prev_pair, it - 1u);
     } else {
         // ------------------------------------------------------------------ epilogue: all 16 warps on every task
         reg_inc<t3::kRegsEpi>();
@@ -224,12 +189,11 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
             umma::tc_fence_after();
             ++nd[t];
         };
-        auto store_dz4 = [&](__nv_bfloat16* dz_at, const uint32_t* p) {
+        auto store_dz = [&](__nv_bfloat16* dz_at, const uint32_t* p) {
             uint4* dst = (uint4*)dz_at;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) store_dz<FLAGS>(dst + i * 128, make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]));
+            for (int i = 0; i < 4; ++i) store_once(dst + i * 128, make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]));
         };
-        uint32_t steps_done = 0;
 
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int64_t row0 = pair * 2 * t3::kTileM + r;
@@ -304,8 +268,8 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
 #if NERF_INTERLEAVE_STORES_BWD
                                 if (st && (i & 3) == 3) {       // chunks i / 4 and i / 4 + 2 are complete: let them go now
                                     uint4* dst = (uint4*)(dzp + t * kTileDzStride + h * kHalfDzStride);
-                                    store_dz<FLAGS>(dst + (i >> 2) * 128, make_uint4(p[i - 3], p[i - 2], p[i - 1], p[i]));
-                                    store_dz<FLAGS>(dst + ((i >> 2) + 2) * 128, make_uint4(p[i + 5], p[i + 6], p[i + 7], p[i + 8]));
+                                    store_once(dst + (i >> 2) * 128, make_uint4(p[i - 3], p[i - 2], p[i - 1], p[i]));
+                                    store_once(dst + ((i >> 2) + 2) * 128, make_uint4(p[i + 5], p[i + 6], p[i + 7], p[i + 8]));
                                 }
 #endif
                             }
@@ -315,16 +279,11 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                             umma::tmem_wait_st();
                             warp_arrive(bars + 8u * (t3::kBarAHi + t), lane);
                         }
-                        if (st && (FIRST || !NERF_INTERLEAVE_STORES_BWD)) store_dz4(dzp + t * kTileDzStride + h * kHalfDzStride, p);     // rows past `total` carry zeros
+                        if (st && (FIRST || !NERF_INTERLEAVE_STORES_BWD)) store_dz(dzp + t * kTileDzStride + h * kHalfDzStride, p);     // rows past `total` carry zeros
                     }
                 }
                 dzp -= 2 * kHalfDzStride;
                 mkp -= 2 * kHalfMaskStride;
-                if (FLAGS) {            // this warp's share of the step's dz is on its way: tell the relaying warp
-                    __syncwarp();
-                    if (lane == 0) umma::mbar_arrive_u32(bars + 8u * (b3::kBarStepDone + (steps_done & 1u)));
-                    ++steps_done;
-                }
             };
             chain_step(std::true_type{}, 6);
 #pragma unroll 1
@@ -337,25 +296,18 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
 }
 
 int launch_mlp_tc_bwd3(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre, int64_t total,
-                       void* dz_out, uint32_t* ready, int max_ctas, void* stream) {
+                       void* dz_out, void* stream) {
     static thread_local unsigned long long attr_mask = 0;
     if (attrs_pending(attr_mask)) {
-        cudaError_t e = allow_smem(mlp_tc_bwd3_kernel<false>, b3::kSmemBytes);
-        if (e == cudaSuccess) e = allow_smem(mlp_tc_bwd3_kernel<true>, b3::kSmemBytes);
+        cudaError_t e = allow_smem(mlp_tc_bwd3_kernel, b3::kSmemBytes);
         if (e != cudaSuccess) { set_error("nerf_mlp_backward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
         attrs_done(attr_mask);
     }
     const int64_t tiles = (total + t3::kTileM - 1) / t3::kTileM;
     const int64_t pairs = (tiles + 1) / 2;
-    int cap = num_sms();
-    if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
-    const int grid = (int)(pairs < cap ? pairs : cap);
-    if (ready)
-        mlp_tc_bwd3_kernel<true><<<grid, t3::kThreads, b3::kSmemBytes, (cudaStream_t)stream>>>(
-            (const uint8_t*)packed_t, (const uint32_t*)masks, dsigma_pre, drgb_pre, total, (__nv_bfloat16*)dz_out, ready);
-    else
-        mlp_tc_bwd3_kernel<false><<<grid, t3::kThreads, b3::kSmemBytes, (cudaStream_t)stream>>>(
-            (const uint8_t*)packed_t, (const uint32_t*)masks, dsigma_pre, drgb_pre, total, (__nv_bfloat16*)dz_out, nullptr);
+    const int grid = (int)(pairs < num_sms() ? pairs : num_sms());
+    mlp_tc_bwd3_kernel<<<grid, t3::kThreads, b3::kSmemBytes, (cudaStream_t)stream>>>(
+        (const uint8_t*)packed_t, (const uint32_t*)masks, dsigma_pre, drgb_pre, total, (__nv_bfloat16*)dz_out);
     return check_launch("nerf_mlp_backward_tc");
 }
 
@@ -364,18 +316,11 @@ int launch_mlp_tc_bwd3(const void* packed_t, const void* masks, const float* dsi
 using namespace nerf;
 
 extern "C" int nerf_mlp_backward_tc(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre,
-                                    int64_t N, int S, void* dz_out, uint32_t* ready, int max_ctas, void* stream) {
+                                    int64_t N, int S, void* dz_out, void* stream) {
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_backward_tc: bad size");
     if (N == 0) return 0;
     NERF_REQUIRE(packed_t && masks && dsigma_pre && drgb_pre && dz_out, "nerf_mlp_backward_tc: null pointer");
     NERF_REQUIRE(((uintptr_t)packed_t & 127) == 0 && ((uintptr_t)masks & 7) == 0 && ((uintptr_t)dz_out & 15) == 0,
                  "nerf_mlp_backward_tc: misaligned buffer");
-    NERF_REQUIRE(!ready || ((uintptr_t)ready & 3) == 0, "nerf_mlp_backward_tc: misaligned ready flags");
-    return launch_mlp_tc_bwd3(packed_t, masks, dsigma_pre, drgb_pre, N * S, dz_out, ready, max_ctas, stream);
-}
-
-extern "C" size_t nerf_backward_flags_bytes(int64_t N, int S) {
-    if (N <= 0 || S <= 0) return 0;
-    const int64_t tiles = (N * S + t3::kTileM - 1) / t3::kTileM;
-    return (size_t)((tiles + 1) / 2) * 8 * sizeof(uint32_t);
+    return launch_mlp_tc_bwd3(packed_t, masks, dsigma_pre, drgb_pre, N * S, dz_out, stream);
 }

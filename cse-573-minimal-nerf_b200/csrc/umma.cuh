@@ -67,18 +67,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// generic-proxy accesses (here: an acquire load that observed another SM's stores to global memory) ordered before this
-// thread's later async-proxy accesses (cp.async.bulk reads of that memory)
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// cross-kernel / cross-SM progress flags in global memory (dgrad -> wgrad hand-over, mlp_tc_bwd3.cu / wgrad_tc.cu)
-__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // -------------------------------------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {   // one full warp

@@ -20,19 +20,11 @@
 // the bias gradients while they sit in shared memory and run the final TMEM -> atomics epilogue, warps 8-11 recompute the
 // PE(x) / PE(dir) tile for the products whose input is a positional encoding.  The kernel is HBM-bound by design (128 KB of
 // operands per 2048 clk of MMA); its roofline is bytes / HBM bandwidth.
-//
-// Concurrent form (`ready` != NULL; the training step's default): the kernel is launched on a second stream next to the dgrad
-// kernel (mlp_tc_bwd3.cu, FLAGS form), on the SMs that launch leaves free, and follows it tile pair by tile pair: before a
-// producer warp requests a dz block it waits (ld.acquire.gpu) for the counter dgrad publishes once that block is stored,
-// so dz reaches this kernel through L2 instead of through a kernel boundary and HBM, and the two kernels' tensor work
-// overlaps.  Both kernels walk the tiles in increasing order, so the distance between them stays a few tiles.  The job -> CTA
-// shares are a launch parameter (`job_ctas`): 148 CTAs by measured HBM-bound cost when the kernel runs alone, fewer next to dgrad.
 #include "mlp_tc_common.cuh"
 
 namespace nerf {
 
 namespace wg {
-constexpr int kNumJobs = 9;
 constexpr int kThreads = 384;
 constexpr int kSlots = 2;
 constexpr uint32_t kABytes = 32768;        // [128 samples x 128 n_out]
@@ -71,7 +63,7 @@ struct Job {
     uint8_t pe_valid;     // valid PE columns (60 / 24)
     uint8_t out_kind;
     uint8_t heads_bias;   // 1: db of the two heads = column sums of the B tile (the dz heads block)
-    uint8_t ctas;         // CTAs that split this job's tiles when the kernel has the GPU to itself (default shares)
+    uint8_t ctas;         // CTAs that split this job's tiles
     uint8_t dens;         // 1: the B tile is feat: its two 128-feature halves, used as A operands against the dz heads block
                           //    (4 KB more per tile), also give dW(density_fn.0) - feat is not read a second time by a job of its own
 };
@@ -94,29 +86,13 @@ __constant__ Job c_jobs[9] = {
     {1, {{SRC_ACTS, 1792, 9, 0, 128, 0, 0}, NB, NB, NB}, 1, SRC_DZ, 1920, PE_NONE, 0, OUT_RGB, 1, 7, 0},                                 // rgb_fn.2: r^T . heads (+ head biases)
 };
 #undef NB
-// default shares (148 CTAs, the kernel alone on the GPU): they follow the measured per-tile cost of each job (tools/profile_wgrad.py:
-// the PE(x) job recomputes 60 sin/cos per row and is issue-bound, the 256-wide jobs are HBM-bound), not its bytes
-constexpr uint8_t c_jobs_host_ctas[9] = {25, 17, 17, 18, 17, 18, 17, 12, 7};
+constexpr int kNumJobs = 9;
+constexpr int kGridCtas = 25 + (17 + 17 + 18) + (17 + 18 + 17) + 12 + 7;          // 148: CTA shares follow the measured per-tile cost of each job
+                                                                 // (tools/profile_wgrad.py: the PE(x) job recomputes 60 sin/cos per row and is
+                                                                 // issue-bound, the 256-wide jobs are HBM-bound), not its bytes
 }  // namespace wg
 
 struct Grads { float* p[20]; };
-struct JobShares { uint8_t n[wg::kNumJobs]; };        // CTAs per job of this launch (sum = grid)
-
-// dgrad's progress counter for a dz block: 8 per tile pair - [0] dr block (features 1792..) + heads block (1920..), complete at
-// 4 (producer warps); [1 + k] chain step k, i.e. the dz of layer 6 - k (features 256 (6 - k) ..), complete at 1
-__device__ __forceinline__ void wait_dz_ready(const uint32_t* ready, int64_t tile, int feat) {
-    const uint32_t idx = feat >= 1792 ? 0u : 7u - (uint32_t)(feat >> 8);
-    const uint32_t need = feat >= 1792 ? 4u : 1u;
-    const uint32_t* f = ready + (tile >> 1) * 8 + idx;
-    if (umma::ld_acquire_gpu(f) < need) {
-        const long long t0 = clock64();
-        while (umma::ld_acquire_gpu(f) < need) {
-            __nanosleep(200);
-            if (clock64() - t0 > 8000000000ll) __trap();          // ~4 s: dgrad is not running - a protocol bug, do not hang the GPU
-        }
-    }
-    umma::fence_proxy_async_all();                                // the bulk copy that follows reads through the async proxy
-}
 
 #ifdef NERF_DEBUG_BUILD
 // diagnostic library only: per-CTA (elapsed clocks, clocks until the last MMA completed) of the most recent launch (tools/profile_wgrad.py)
@@ -128,8 +104,7 @@ __device__ long long g_wgrad_cycles[2 * 160];
 
 __global__ void __launch_bounds__(wg::kThreads, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __restrict__ dz, const float* __restrict__ o_rays,
-                const float* __restrict__ d_rays, const float* __restrict__ ts, int64_t total, int S, Grads G,
-                const uint32_t* __restrict__ ready, const JobShares shares) {
+                const float* __restrict__ d_rays, const float* __restrict__ ts, int64_t total, int S, Grads G) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + wg::kOffBars);
@@ -148,10 +123,10 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
 
     // which job, and which share of its tiles, this CTA owns
     int job_idx = 0, first = blockIdx.x;
-    while (job_idx < wg::kNumJobs && first >= shares.n[job_idx]) { first -= shares.n[job_idx]; ++job_idx; }
+    while (job_idx < wg::kNumJobs && first >= wg::c_jobs[job_idx].ctas) { first -= wg::c_jobs[job_idx].ctas; ++job_idx; }
     if (job_idx >= wg::kNumJobs) return;                 // spare CTAs
     const wg::Job job = wg::c_jobs[job_idx];
-    const int stride = shares.n[job_idx], nA = job.nA;
+    const int stride = job.ctas, nA = job.nA;
     const int b_cols = job.b_cols16 * 16;
     const bool has_pe = job.pe != wg::PE_NONE;
     const int region_cols = b_cols + (has_pe ? 64 : 0);  // TMEM columns per A block
@@ -187,7 +162,6 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
                 umma::mbar_wait(&emptyA[slot], ph ^ 1);
                 if (leader) {
                     const wg::Block bk = job.blk[i];
-                    if (ready && bk.src == wg::SRC_DZ) wait_dz_ready(ready, tile, bk.feat);
                     const int chunks = (bk.src == wg::SRC_DZ) ? pk::kDzChunks : pk::kActChunks;
                     const __nv_bfloat16* src = (bk.src == wg::SRC_DZ ? dz : acts) + (tile * chunks + (bk.feat >> 3)) * 1024;
                     umma::mbar_arrive_expect_tx(&fullA[slot], wg::kABytes);
@@ -205,7 +179,6 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
                 const uint32_t slot = it & 1, ph = (it >> 1) & 1;
                 umma::mbar_wait(&emptyB[slot], ph ^ 1);
                 if (leader) {
-                    if (ready && (job.b_src == wg::SRC_DZ || job.dens)) wait_dz_ready(ready, tile, 1920);      // the dz heads block
                     umma::mbar_arrive_expect_tx(&fullB[slot], b_bytes + (job.dens ? wg::kHeadsBytes : 0u));
                     umma::bulk_g2s(smem + wg::kOffB + slot * wg::kBBytes, b_base + tile * (int64_t)bsrc_chunks * 1024, b_bytes, &fullB[slot]);
                     if (job.dens)          // the dz heads block [128 x 16] of the same tile
@@ -445,7 +418,7 @@ extern "C" NERF_API int nerf_debug_wgrad_cycles(long long* host_out320) {
 #endif
 
 extern "C" int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
-                             float* const* grads20_host, const uint32_t* ready, const int* job_ctas9_host, void* stream) {
+                             float* const* grads20_host, void* stream) {
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_wgrad_tc: bad size");
     if (N == 0) return 0;
     NERF_REQUIRE(acts && dz && o && d && ts && grads20_host, "nerf_wgrad_tc: null pointer");
@@ -455,21 +428,13 @@ extern "C" int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, c
         NERF_REQUIRE(grads20_host[i], "nerf_wgrad_tc: grads20_host[%d] is NULL", i);
         G.p[i] = grads20_host[i];
     }
-    JobShares shares;
-    int grid = 0;
-    for (int j = 0; j < wg::kNumJobs; ++j) {
-        const int n = job_ctas9_host ? job_ctas9_host[j] : (int)wg::c_jobs_host_ctas[j];
-        NERF_REQUIRE(n >= 1 && n <= 255, "nerf_wgrad_tc: job_ctas9_host[%d] = %d (every job needs 1..255 CTAs)", j, n);
-        shares.n[j] = (uint8_t)n;
-        grid += n;
-    }
     static thread_local unsigned long long attr_mask = 0;
     if (attrs_pending(attr_mask)) {
         cudaError_t e = allow_smem(wgrad_tc_kernel, wg::kSmemBytes);
         if (e != cudaSuccess) { set_error("nerf_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
         attrs_done(attr_mask);
     }
-    wgrad_tc_kernel<<<grid, wg::kThreads, wg::kSmemBytes, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)acts, (const __nv_bfloat16*)dz, o, d, ts, N * S, S, G, ready, shares);
+    wgrad_tc_kernel<<<wg::kGridCtas, wg::kThreads, wg::kSmemBytes, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)acts, (const __nv_bfloat16*)dz, o, d, ts, N * S, S, G);
     return check_launch("nerf_wgrad_tc");
 }

@@ -59,74 +59,34 @@ def composite_backward(sigma, rgb, ts, g_ray):
     return dsig, drgb
 
 
-# Concurrent backward: the dgrad kernel runs on CONCURRENT_DGRAD_CTAS SMs and the wgrad kernel, launched on a side stream with the
-# remaining SMs split over its 9 jobs (CONCURRENT_WGRAD_JOB_CTAS), follows it tile pair by tile pair through progress counters in
-# global memory (csrc/mlp_tc_bwd3.cu FLAGS form, csrc/wgrad_tc.cu): dz reaches wgrad through L2 and the two kernels' tensor
-# work overlaps.  `None` = the two-kernels-in-sequence form (each kernel on all 148 SMs, dz through HBM).
-CONCURRENT_DGRAD_CTAS = 88
-CONCURRENT_WGRAD_JOB_CTAS = (10, 7, 7, 7, 7, 7, 7, 5, 3)          # sum 60
-_side_streams = {}
-
-
-def side_stream(dev):
-    key = torch.device(dev).index
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=dev)
-    return _side_streams[key]
-
-
-def _grad_targets(model, device, accumulate_into_grad):
-    """The 20 tensors wgrad accumulates into: the existing .grad buffers (views of the optimiser's flat gradient buffer; autograd
-    is then handed nothing to accumulate - 40 AccumulateGrad adds and a memset per step less) or a fresh zeroed flat buffer."""
-    params = model.ordered_params()
-    direct = accumulate_into_grad and all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == F32 for p in params)
-    if direct:
-        return [p.grad for p in params], True
-    flat = torch.zeros(sum(p.numel() for p in params), device=device, dtype=F32)
-    grads, off = [], 0
-    for p in params:
-        grads.append(flat[off:off + p.numel()].view_as(p))
-        off += p.numel()
-    return grads, False
-
-
-def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray, accumulate_into_grad=False, concurrent=None, side=None):
+def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray, accumulate_into_grad=False):
     """Gradients of one network's 20 parameters (state_dict order) given dL/d(ray colour) [N,3]: all hand-written kernels -
-    compositing backward, tcgen05 dgrad chain (mlp_tc_bwd3.cu), tcgen05 wgrad + bias sums (wgrad_tc.cu).
-    concurrent = (dgrad_ctas, wgrad_job_ctas) runs wgrad on the stream `side` next to dgrad (see CONCURRENT_DGRAD_CTAS); the caller
-    joins `side` back into the current stream."""
+    compositing backward, tcgen05 dgrad chain (mlp_tc_bwd.cu), tcgen05 wgrad + bias sums (wgrad_tc.cu)."""
     import ctypes
     acts, masks = acts
     N, S = ts.shape[0], ts.shape[1]
     M = N * S
     dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
     dz_t = torch.empty((padded_rows(M) * DZ,), device=ts.device, dtype=BF)
-    grads, direct = _grad_targets(model, ts.device, accumulate_into_grad)
-    arr = (ctypes.c_void_p * 20)(*[g.data_ptr() for g in grads])
-    lib = nat.lib()
-    if concurrent is None:
-        with nat.timed_kernel("mlp_tc_bwd_kernel", M):
-            nat.check(lib.nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb),
-                                               N, S, nat.ptr(dz_t), None, 0, nat.stream()), "nerf_mlp_backward_tc")
-        with nat.timed_kernel("wgrad_tc_kernel", M):
-            nat.check(lib.nerf_wgrad_tc(nat.ptr(acts), nat.ptr(dz_t), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, arr, None, None,
-                                        nat.stream()), "nerf_wgrad_tc")
+    with nat.timed_kernel("mlp_tc_bwd_kernel", M):
+        nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb),
+                                                 N, S, nat.ptr(dz_t), nat.stream()), "nerf_mlp_backward_tc")
+    params = model.ordered_params()
+    direct = accumulate_into_grad and all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == F32 for p in params)
+    if direct:
+        # wgrad ACCUMULATES with atomics: add straight into the existing .grad buffers (views of the optimiser's flat
+        # gradient buffer) and hand autograd nothing to accumulate - 40 AccumulateGrad adds and a memset per step less
+        grads = [p.grad for p in params]
     else:
-        dgrad_ctas, job_ctas = concurrent
-        main = torch.cuda.current_stream(ts.device)
-        flags = torch.zeros((lib.nerf_backward_flags_bytes(N, S) // 4,), device=ts.device, dtype=torch.int32)
-        packed_t = model.packed_weights_t()
-        side.wait_stream(main)                         # saved tensors, dsig / drgb's producers, zeroed flags and gradients
-        with nat.timed_kernel("backward(dgrad || wgrad)", M):
-            nat.check(lib.nerf_mlp_backward_tc(nat.ptr(packed_t), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb), N, S, nat.ptr(dz_t),
-                                               nat.ptr(flags), int(dgrad_ctas), nat.stream(main)), "nerf_mlp_backward_tc")
-            shares = (ctypes.c_int * 9)(*[int(c) for c in job_ctas])
-            nat.check(lib.nerf_wgrad_tc(nat.ptr(acts), nat.ptr(dz_t), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, arr, nat.ptr(flags),
-                                        shares, nat.stream(side)), "nerf_wgrad_tc")
-            if nat.kernel_events is not None:
-                main.wait_stream(side)                 # per-kernel timing pass only: the closing event must see wgrad's end
-        # (every tensor the side stream reads was allocated on `main` and is released by the caller after it has joined `side`
-        # back into `main`: the caching allocator hands the memory to later `main` work only, which is ordered behind the join)
+        flat = torch.zeros(sum(p.numel() for p in params), device=ts.device, dtype=F32)
+        grads, off = [], 0
+        for p in params:
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+    arr = (ctypes.c_void_p * 20)(*[g.data_ptr() for g in grads])
+    with nat.timed_kernel("wgrad_tc_kernel", M):
+        nat.check(nat.lib().nerf_wgrad_tc(nat.ptr(acts), nat.ptr(dz_t), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, arr, nat.stream()),
+                  "nerf_wgrad_tc")
     return [None] * 20 if direct else grads
 
 
@@ -231,16 +191,9 @@ class RenderFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_c, g_f):
         net, o, d, a = ctx.net, ctx.o, ctx.d, ctx.aux
-        conc = (CONCURRENT_DGRAD_CTAS, CONCURRENT_WGRAD_JOB_CTAS) if CONCURRENT_DGRAD_CTAS else None
-        main = torch.cuda.current_stream(o.device)
-        side = side_stream(o.device) if conc else None
-        gc = mlp_backward(net.coarse_network, o, d, a["c_ts"], a["c_sigma"], a["c_rgb"], a["c_acts"], g_c.contiguous(), True, conc, side)
+        gc = mlp_backward(net.coarse_network, o, d, a["c_ts"], a["c_sigma"], a["c_rgb"], a["c_acts"], g_c.contiguous(), True)
         if all(g is None for g in gc) and getattr(net, "on_coarse_grads_ready", None) is not None:
-            # data parallel: the coarse slice of the gradient sum overlaps the fine backward (queued behind the coarse wgrad)
-            with torch.cuda.stream(side if conc else main):
-                net.on_coarse_grads_ready()
-        gf = mlp_backward(net.fine_network, o, d, a["ts"], a["f_sigma"], a["f_rgb"], a["f_acts"], g_f.contiguous(), True, conc, side)
-        if conc:
-            main.wait_stream(side)           # both wgrads (and the coarse reduction's launch) are behind everything that follows
+            net.on_coarse_grads_ready()      # data parallel: the coarse slice of the all-reduce overlaps the fine backward
+        gf = mlp_backward(net.fine_network, o, d, a["ts"], a["f_sigma"], a["f_rgb"], a["f_acts"], g_f.contiguous(), True)
         ctx.aux = None
         return (None,) * 6 + tuple(gc) + tuple(gf)

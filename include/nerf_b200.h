@@ -142,25 +142,13 @@ NERF_API int nerf_mlp_forward_tc_train(const void* packed, const float* o, const
 NERF_API size_t nerf_packed_t_bytes(void);
 NERF_API int nerf_pack_weights_t(const float* const* params20_host, void* packed_t, void* stream);
 NERF_API int nerf_mlp_backward_tc(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre,
-                                  int64_t N, int S, void* dz_out, uint32_t* ready, int max_ctas, void* stream);
-/* ready / max_ctas (concurrent backward, what training.py launches): `ready` = nerf_backward_flags_bytes(N, S) bytes of ZEROED device
- * memory, 8 progress counters per 256-sample tile pair that this kernel increments (release, gpu scope) as soon as a block of dz
- * has been stored - [0] the rgb_fn.0 block + heads block (complete at 4), [1 + k] chain step k = the dz of layer 6 - k (complete
- * at 1).  nerf_wgrad_tc, launched on ANOTHER stream with the same `ready` and a CTA count that leaves max_ctas SMs to this
- * kernel (max_ctas + sum(job_ctas9) <= SM count), consumes every block through L2 while this kernel is still running.
- * ready = NULL, max_ctas = 0: the stand-alone form (all SMs, dz handed over by the kernel boundary). */
-NERF_API size_t nerf_backward_flags_bytes(int64_t N, int S);
+                         int64_t N, int S, void* dz_out, void* stream);
 /* ---- weight / bias gradients of one network on the tensor cores: dW_l += dz_l^T . (input of layer l), db_l += sum dz_l.
  * acts, dz: the tiled chunk-major training tensors written by nerf_mlp_forward_tc_train / nerf_mlp_backward_tc;
  * o, d, ts as in the forward (PE(x) / PE(dir) operands are recomputed).  grads20_host: HOST array of 20 device pointers
  * (state_dict order, fp32, nn.Linear layout), ACCUMULATED into with atomics - zero them first. */
 NERF_API int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
-                           float* const* grads20_host, const uint32_t* ready, const int* job_ctas9_host, void* stream);
-/* ready: NULL, or the counters nerf_mlp_backward_tc publishes (see there): every dz block is then requested only once dgrad has
- * stored it, so this kernel may start before the dgrad kernel of the same network has finished (or started).
- * job_ctas9_host: NULL (148 CTAs, shares by measured cost when the kernel has the GPU to itself) or a HOST array of 9 CTA counts,
- * one per job (mlp.0 + feature_fn.0's PE(x) part | mlp.2 | mlp.4 | mlp.6 | feature_fn.0 | feature_fn.2 | feature_fn.4 |
- * rgb_fn.0 + density_fn.0 | rgb_fn.2); grid = their sum. */
+                  float* const* grads20_host, void* stream);
 /* Same kernel with explicit sample points [N,S,3] (the NeRFModel.forward(samples, direc) call surface). */
 NERF_API int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
                                int64_t N, int S, float* sigma, float* rgb, void* stream);

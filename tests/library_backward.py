@@ -24,7 +24,7 @@ def mlp_backward_library_wgrad(model, o, d, ts, sigma, rgb, acts, g_ray):
     dz_t = torch.empty((padded_rows(M) * DZ,), device=ts.device, dtype=BF)
     with nat.timed_kernel("mlp_tc_bwd_kernel", M):
         nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb),
-                                                 N, S, nat.ptr(dz_t), None, 0, nat.stream()), "nerf_mlp_backward_tc")
+                                                 N, S, nat.ptr(dz_t), nat.stream()), "nerf_mlp_backward_tc")
     acts, dz = untile(acts, M, ACT), untile(dz_t, M, DZ)        # interim: the library wgrad GEMMs want row-major operands
     feat, r, dr = acts[:, 1536:1792], acts[:, 1792:1920], dz[:, 1792:1920]
     pts = (d[:, None, :] * ts + o[:, None, :]).reshape(M, 3)
