@@ -246,29 +246,24 @@ def bench_train(args, rank, world, dev):
     if world > 1:
         net.on_coarse_grads_ready = lambda: grads.reduce_async(n_coarse)
     H = W = 800
-    views = []
+    import training
+    images, poses = [], []
     for j in range(2):
         c2w, focal = frame_setup(H, W, 7 * rank + 3 + 20 * j)
-        views.append((c2w, torch.from_numpy(synthetic.analytic_scene_rgba(c2w.numpy(), H, W, focal)[..., :3].copy()).to(dev)))
+        poses.append(c2w.to(torch.float32))
+        images.append(torch.from_numpy(synthetic.analytic_scene_rgba(c2w.numpy(), H, W, focal)[..., :3].copy()))
+    images, poses = torch.stack(images).to(dev).contiguous(), torch.stack(poses).to(dev).contiguous()
     n = CHUNK
+    # the product's training step: Trainer.fit's body captured once as a CUDA graph (training.GraphedTrainStep) and replayed
+    stepper = training.GraphedTrainStep(net, opt, grads, images, poses, focal, n, cropping=True, warmup=max(args.warmup, 3))
     counter = [0]
 
     def step():
-        c2w, image = views[counter[0] % len(views)]
         counter[0] += 1
-        xs, ys = dataloader.sample_random_coordinates(n, H, W, cropping=True, device=dev)
-        o, d = dataloader.get_rays_at(H, W, focal, c2w, xs, ys)
-        rgb = image[ys, xs].float() / 255.0
-        grads.zero()
-        loss = net.training_step({"origin": o[None], "direc": d[None], "rgb": rgb[None]}, 0)
-        loss.backward()
-        grads.all_reduce_mean()
-        opt.step()
-        return loss
-    loss_first = None
-    for _ in range(max(args.warmup, 3)):
-        loss = step()
-        loss_first = loss.detach() if loss_first is None else loss_first
+        return stepper.eager_step(counter[0] % 2) if args.eager_train else stepper.step(counter[0] % 2)
+    loss_first = stepper.first_loss            # loss of the very first optimiser step (first warm-up step before the capture)
+    for _ in range(3):
+        step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -289,8 +284,8 @@ def bench_train(args, rank, world, dev):
     nz = net.logged.get("fine_density_non_zeros") if hasattr(net, "logged") else None
     # ---- per-kernel record (a few extra steps with CUDA events around the three tensor-core kernels; not part of the timing above)
     nat.kernel_events = []
-    for _ in range(4):
-        step()
+    for k in range(4):
+        stepper.eager_step(k % 2)
     torch.cuda.synchronize()
     events, nat.kernel_events = nat.kernel_events, None
     pk = peaks()
@@ -324,6 +319,7 @@ def bench_train(args, rank, world, dev):
             "algorithmic_tflops_per_gpu": tfl, "frac_of_sustained_peak": tfl / pk["tflops_sustained"],
             "frac_of_burst_peak": tfl / pk["tflops_burst"], "roofline_train": roofline_train,
             "data": "centre-cropped pixels of two analytic-scene orbit views per rank (synthetic), random-init weights (seed 0)",
+            "step": "eager (launch by launch)" if args.eager_train else "training.GraphedTrainStep: the whole step replayed as one CUDA graph",
             "backward": "hand-written: composite_backward_kernel, mlp_tc_bwd3_kernel (tcgen05 dgrad chain), "
                         "wgrad_tc_kernel (tcgen05 wgrad + bias sums); Adam = hand-written flat kernel (adam.cu), gradients accumulated straight into the flat buffer",
             "collective": ("NCCL sum of the 924 680-float flat gradient buffer per step (coarse slice overlapped with the fine backward), "
@@ -352,6 +348,7 @@ def main():
     ap.add_argument("--hw", type=int, default=800, help="frame height = width")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--eager-train", action="store_true", help="time the training step launch by launch instead of as the replayed CUDA graph")
     ap.add_argument("--reference-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' runs the same eager-PyTorch port of the reference on the GPU (what the "
                          "reference itself does when a GPU is present); the contract arm is the default, 'cpu'")

@@ -25,6 +25,7 @@ _PROTOTYPES = {
     "nerf_abi_version": (ctypes.c_int, []),
     "nerf_last_error": (ctypes.c_char_p, []),
     "nerf_raygen": (_int, [_vp, _int, _int, _f32, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "nerf_batch_rays": (_int, [_vp, _vp, _vp, _int, _int, _int, _f32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "nerf_coarse_sample": (_int, [_vp, _vp, _vp, _vp, _f32, _i64, _int, _vp, _vp, _vp]),
     "nerf_deltas": (_int, [_vp, _i64, _int, _vp, _vp]),
     "nerf_weights": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
@@ -49,6 +50,7 @@ _PROTOTYPES = {
     "nerf_mlp_composite_tc_supported": (_int, [_int]),
     "nerf_mlp_composite_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerf_mlp_composite_tc_strata": (_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nerf_adam_step_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "nerf_adam_step": (_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i64, _f32, _vp]),
 }
 

@@ -40,9 +40,49 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     }
 }
 
+// Graph-safe form: nothing about the step comes from the host, so a CUDA graph can replay it.  state[0..4] = lr, beta1, beta2,
+// eps, grad_scale (written by the host when they change), state[5..6] = step_size, 1 / sqrt(bias_correction2) (written here);
+// *step is the number of steps taken so far and is incremented here.
+__global__ void adam_prepare_kernel(float* __restrict__ state, long long* __restrict__ step) {
+    const long long t = *step + 1;
+    *step = t;
+    const double bc1 = 1.0 - pow((double)state[1], (double)t), bc2 = 1.0 - pow((double)state[2], (double)t);
+    state[5] = (float)((double)state[0] / bc1);
+    state[6] = (float)(1.0 / sqrt(bc2));
+}
+
+__global__ void __launch_bounds__(256)
+adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                     const float* __restrict__ state) {
+    const float one_minus_beta1 = 1.0f - state[1], beta2 = state[2], one_minus_beta2 = 1.0f - state[2], eps = state[3], grad_scale = state[4],
+                step_size = state[5], inv_bc2_sqrt = state[6];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {       // n is a multiple of 4 (flat buffers are padded)
+        const float gi = g[i] * grad_scale;
+        const float mi = fmaf(gi - m[i], one_minus_beta1, m[i]);
+        const float vi = fmaf(one_minus_beta2 * gi, gi, v[i] * beta2);
+        const float denom = __fadd_rn(__fmul_rn(sqrtf(vi), inv_bc2_sqrt), eps);
+        m[i] = mi; v[i] = vi;
+        p[i] = fmaf(-step_size, __fdiv_rn(mi, denom), p[i]);
+    }
+}
+
 }  // namespace nerf
 
 using namespace nerf;
+
+extern "C" int nerf_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* state8_dev,
+                                  int64_t* step_dev, void* stream) {
+    NERF_REQUIRE(n >= 0, "nerf_adam_step_dev: bad size");
+    if (n == 0) return 0;
+    NERF_REQUIRE(params && grads && exp_avg && exp_avg_sq && state8_dev && step_dev, "nerf_adam_step_dev: null pointer");
+    adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state8_dev, (long long*)step_dev);
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    adam_step_dev_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, state8_dev);
+    return check_launch("nerf_adam_step_dev");
+}
 
 extern "C" int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                               float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream) {

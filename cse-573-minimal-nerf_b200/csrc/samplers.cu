@@ -72,6 +72,39 @@ raygen_kernel(Pose pose, int H, int W, float half_w, float half_h, float focal,
     }
 }
 
+// N1, the training batch producer in graph-safe form (dataloader.py:143-152 for a pixel list): which image the batch comes from
+// is read from DEVICE memory (a CUDA graph replays this launch with a new index each step), the pose from a device table, and
+// the target colours are gathered from the device-resident uint8 images: rgb = fl32(u8 / 255) evaluated in double precision
+// like numpy's `imread(...) / 255` upstream (dataloader.py:148).  One thread per ray.
+__global__ void __launch_bounds__(256)
+batch_rays_kernel(const float* __restrict__ poses, const int64_t* __restrict__ img_idx, const uint8_t* __restrict__ images, int n_img,
+                  int H, int W, float half_w, float half_h, float focal, const int64_t* __restrict__ xs, const int64_t* __restrict__ ys,
+                  int64_t n, float* __restrict__ o, float* __restrict__ d, float* __restrict__ rgb) {
+    int64_t im = *img_idx;
+    im = im < 0 ? 0 : (im >= n_img ? n_img - 1 : im);
+    Pose pose;
+    const float* c2w = poses + im * 16;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) pose.r[r][c] = __ldg(c2w + r * 4 + c);
+        pose.t[r] = __ldg(c2w + r * 4 + 3);
+    }
+    const uint8_t* img = images + im * (int64_t)H * W * 3;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float dir[3];
+        raygen_one(pose, W, half_w, half_h, focal, xs, ys, i, dir);
+        const int64_t x = xs[i], y = ys[i];
+        const bool inside = x >= 0 && x < W && y >= 0 && y < H;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            d[i * 3 + k] = dir[k];
+            o[i * 3 + k] = pose.t[k];
+            rgb[i * 3 + k] = inside ? (float)((double)img[(y * W + x) * 3 + k] / 255.0) : 0.f;
+        }
+    }
+}
+
 // --------------------------------------------------------------------------------- K1 coarse sampling
 __global__ void __launch_bounds__(256)
 coarse_sample_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ u,
@@ -675,6 +708,16 @@ extern "C" int nerf_raygen(const float* c2w_host, int H, int W, float focal, con
         raygen_kernel<false><<<grid_for(n - n_vec, 256), 256, 0, (cudaStream_t)stream>>>(p, H, W, (float)(W * .5), (float)(H * .5), focal,
                                                                                       xs, ys, n_vec, n, o, d);
     return check_launch("nerf_raygen");
+}
+
+extern "C" int nerf_batch_rays(const float* poses_dev, const int64_t* img_idx_dev, const uint8_t* images_u8, int n_img, int H, int W,
+                               float focal, const int64_t* xs, const int64_t* ys, int64_t n, float* o, float* d, float* rgb, void* stream) {
+    NERF_REQUIRE(poses_dev && img_idx_dev && images_u8 && xs && ys && o && d && rgb, "nerf_batch_rays: null pointer");
+    NERF_REQUIRE(n_img > 0 && H > 0 && W > 0 && n >= 0, "nerf_batch_rays: bad size n_img=%d H=%d W=%d n=%lld", n_img, H, W, (long long)n);
+    if (n == 0) return 0;
+    batch_rays_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(poses_dev, img_idx_dev, images_u8, n_img, H, W, (float)(W * .5),
+                                                                          (float)(H * .5), focal, xs, ys, n, o, d, rgb);
+    return check_launch("nerf_batch_rays");
 }
 
 extern "C" int nerf_coarse_sample(const float* o, const float* d, const float* u, const float* t_base, float step,

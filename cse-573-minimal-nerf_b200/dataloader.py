@@ -66,6 +66,22 @@ def get_rays_at(H, W, focal, c2w, xs, ys):
     return o, d
 
 
+def batch_rays(poses, img_idx, images, focal, xs, ys):
+    """Rays AND target colours of a pixel list of image `img_idx` (a 0-d int64 DEVICE tensor): poses [n_img,4,4] fp32 and images
+    [n_img,H,W,3] uint8 are device-resident tables (SyntheticDataset.stacked()).  Nothing about the choice of image passes through
+    the host, so the call can sit inside a CUDA graph (training.GraphedTrainStep).  Returns (o [n,3], d [n,3], rgb [n,3])."""
+    xs, ys = nat.dev(xs, "xs", torch.int64), nat.dev(ys, "ys", torch.int64)
+    n_img, H, W, _ = images.shape
+    n = xs.shape[0]
+    o = torch.empty((n, 3), device=xs.device, dtype=torch.float32)
+    d = torch.empty((n, 3), device=xs.device, dtype=torch.float32)
+    rgb = torch.empty((n, 3), device=xs.device, dtype=torch.float32)
+    with torch.cuda.device(xs.device):
+        nat.check(nat.lib().nerf_batch_rays(nat.ptr(poses), nat.ptr(img_idx), nat.ptr(images), n_img, H, W, float(np.float32(focal)),
+                                            nat.ptr(xs), nat.ptr(ys), n, nat.ptr(o), nat.ptr(d), nat.ptr(rgb), nat.stream()), "nerf_batch_rays")
+    return o, d, rgb
+
+
 def read_image(path, pilmode="RGB"):
     from PIL import Image
     return np.asarray(Image.open(path).convert(pilmode))
@@ -104,6 +120,14 @@ class SyntheticDataset(Dataset):
         if idx not in self._images:
             self._images[idx] = torch.from_numpy(read_image(self.frames[idx]['file_path'], "RGB").copy()).to(self.device)
         return self._images[idx]
+
+    def stacked(self):
+        """(images [n,H,W,3] uint8, poses [n,4,4] fp32) of the whole split on the device: the tables `batch_rays` indexes."""
+        if getattr(self, "_stacked", None) is None:
+            images = torch.stack([self.image_u8(i) for i in range(len(self))]).contiguous()
+            poses = torch.stack([torch.tensor(f['transform_matrix'], dtype=torch.float32) for f in self.frames]).to(self.device).contiguous()
+            self._stacked = (images, poses)
+        return self._stacked
 
     def __getitem__(self, idx):
         frame = self.frames[idx]

@@ -39,6 +39,11 @@ class FlatAdam(torch.optim.Optimizer):
         self._step = 0
         self.grad_scale = 1.0
         self.on_params_changed = on_params_changed
+        # graph-safe form (training.GraphedTrainStep): every step-dependent scalar lives in device memory
+        self.graph_safe = False
+        self.dev_state = torch.zeros(8, device=dev, dtype=torch.float32)      # lr, beta1, beta2, eps, grad_scale | 2 scratch
+        self.dev_step = torch.zeros((), device=dev, dtype=torch.int64)
+        self._dev_key = None
         off = 0
         for p in params:
             k = p.numel()
@@ -86,6 +91,19 @@ class FlatAdam(torch.optim.Optimizer):
         if self.on_params_changed is not None:
             self.on_params_changed()
 
+    def sync_device_state(self):
+        """Graph-safe form: push lr / betas / eps / grad_scale and the step count to the device when the host's view changed (the
+        per-epoch LR decay, a loaded checkpoint).  Host -> device copies: call it OUTSIDE graph capture."""
+        g = self.param_groups[0]
+        key = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(self.grad_scale))
+        if key != self._dev_key:
+            self.dev_state[:5].copy_(torch.tensor(key, dtype=torch.float32))
+            self._dev_key = key
+        return self
+
+    def set_device_step(self):
+        self.dev_step.fill_(self._step)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
@@ -103,6 +121,13 @@ class FlatAdam(torch.optim.Optimizer):
                 off += k
         g = self.param_groups[0]
         self._step += 1
+        if self.graph_safe:
+            with torch.cuda.device(self.flat_params.device):
+                nat.check(nat.lib().nerf_adam_step_dev(nat.ptr(self.flat_params), nat.ptr(self.flat_grads), nat.ptr(self.flat_m),
+                                                       nat.ptr(self.flat_v), self._n, nat.ptr(self.dev_state), nat.ptr(self.dev_step),
+                                                       nat.stream()), "nerf_adam_step_dev")
+                self.params_changed()
+            return loss
         with torch.cuda.device(self.flat_params.device):
             nat.check(nat.lib().nerf_adam_step(nat.ptr(self.flat_params), nat.ptr(self.flat_grads), nat.ptr(self.flat_m),
                                                nat.ptr(self.flat_v), self._n, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),

@@ -105,7 +105,7 @@ class FlatGradients:
 class Trainer:
     def __init__(self, gpus=0, default_root_dir=".", max_steps=100000, resume_from_checkpoint=None, logger=None,
                  check_val_every_n_epoch=10, track_grad_norm=-1, reload_dataloaders_every_n_epochs=0, callbacks=None,
-                 log_every_n_steps=50, save_checkpoints=True, max_epochs=None, seed=None):
+                 log_every_n_steps=50, save_checkpoints=True, max_epochs=None, seed=None, cuda_graph=True):
         if not torch.cuda.is_available():
             raise RuntimeError("Trainer: this NeRF path has no CPU implementation; a CUDA device is required")
         self.root, self.max_steps, self.resume = Path(default_root_dir), max_steps, resume_from_checkpoint
@@ -117,6 +117,8 @@ class Trainer:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.seed = seed
+        self.cuda_graph = cuda_graph            # capture the training step as a CUDA graph where the data allows it (training.GraphedTrainStep)
+        self._steppers = {}
         self._metrics = {}
         self.last_checkpoint = None
 
@@ -175,21 +177,22 @@ class Trainer:
             if loader is None or (self.reload_every and self.current_epoch % self.reload_every == 0):
                 loader = datamodule.train_dataloader() if datamodule is not None else train_dataloaders
             model.train()
-            for idx, batch in enumerate(loader):
-                if self.global_step >= self.max_steps:
-                    break
-                batch = {k: v.to(self.device) for k, v in batch.items()}
-                grads.zero()
-                loss = model.training_step(batch, idx)
-                loss.backward()
-                grads.all_reduce_mean()
-                if self.track_grad_norm and self.track_grad_norm > 0:
-                    self.record("grad_2.0_norm_total", grads.norm())
-                optimizer.step()
-                self.global_step += 1
-                if self.logger is not None and self.rank == 0 and self.global_step % self.log_every == 0:
-                    self.logger.log_metrics(dict(self.metrics(), lr=optimizer.param_groups[0]["lr"], epoch=self.current_epoch),
-                                            self.global_step)
+            stepper = self._graphed_stepper(model, optimizer, grads, loader)
+            if stepper is not None:
+                self._run_epoch_graphed(stepper, loader, optimizer)
+            else:
+                for idx, batch in enumerate(loader):
+                    if self.global_step >= self.max_steps:
+                        break
+                    batch = {k: v.to(self.device) for k, v in batch.items()}
+                    grads.zero()
+                    loss = model.training_step(batch, idx)
+                    loss.backward()
+                    grads.all_reduce_mean()
+                    if self.track_grad_norm and self.track_grad_norm > 0:
+                        self.record("grad_2.0_norm_total", grads.norm())
+                    optimizer.step()
+                    self._step_done(optimizer)
             if scheduler is not None:
                 scheduler.step()
             if self.val_every and (self.current_epoch + 1) % self.val_every == 0:
@@ -199,6 +202,50 @@ class Trainer:
             self.current_epoch += 1
         model.on_coarse_grads_ready = None
         return model
+
+    def _step_done(self, optimizer):
+        self.global_step += 1
+        if self.logger is not None and self.rank == 0 and self.global_step % self.log_every == 0:
+            self.logger.log_metrics(dict(self.metrics(), lr=optimizer.param_groups[0]["lr"], epoch=self.current_epoch), self.global_step)
+
+    def _graphed_stepper(self, model, optimizer, grads, loader):
+        """A training.GraphedTrainStep for this loader's dataset, or None when the step has to run eagerly: the loader is not the
+        device-resident Blender-synthetic one, the optimiser is not optim.FlatAdam, or too few steps are left to pay for the capture."""
+        ds = getattr(loader, "dataset", None)
+        if (not self.cuda_graph or ds is None or not hasattr(ds, "stacked") or not hasattr(optimizer, "graph_safe")
+                or not hasattr(model, "coarse_network") or self.max_steps - self.global_step < 8 or len(ds) < 1):
+            return None
+        key = (id(ds), bool(ds.cropping))
+        if key not in self._steppers:
+            import training
+            images, poses = ds.stacked()
+            order = self._epoch_order(loader)
+            self._pending_order = order
+            self._steppers[key] = training.GraphedTrainStep(model, optimizer, grads, images, poses, ds.focal, ds.num_rays, cropping=ds.cropping,
+                                                            track_grad_norm=bool(self.track_grad_norm and self.track_grad_norm > 0),
+                                                            warmup_images=order[:3])
+            for _ in range(3):                             # the warm-up steps before the capture were real optimiser steps
+                self._step_done(optimizer)
+            self._pending_order = order[3:]
+        return self._steppers[key]
+
+    @staticmethod
+    def _epoch_order(loader):
+        n = len(loader.dataset)
+        return torch.randperm(n).tolist() if getattr(loader, "shuffle", False) else list(range(n))
+
+    def _run_epoch_graphed(self, stepper, loader, optimizer):
+        order = getattr(self, "_pending_order", None)
+        self._pending_order = None
+        if order is None:
+            order = self._epoch_order(loader)
+        for image_index in order:
+            if self.global_step >= self.max_steps:
+                break
+            stepper.step(image_index)
+            if stepper.grad_norm is not None:
+                self.record("grad_2.0_norm_total", stepper.grad_norm)
+            self._step_done(optimizer)
 
     def synchronize_replicas(self, model, optimizer):
         """Data parallel: rank 0's parameters, Adam moments and step count become everybody's; then every rank seeds its own

@@ -99,7 +99,10 @@ _stats_pool = {}            # (device, stream) -> [zeroed fp32 block, next free 
 
 def _zeroed_stats8(dv):
     """8 zeroed floats (the density statistics of both networks) cut from a pooled block.  Views handed out earlier keep their
-    block alive, so the logged statistics of earlier forwards stay valid."""
+    block alive, so the logged statistics of earlier forwards stay valid.  Under CUDA-graph capture the floats get their own
+    memset node instead (a replayed graph would keep accumulating into a slice that is zeroed only once)."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.zeros((8,), device=dv, dtype=F32)
     key = (dv, torch.cuda.current_stream(dv).cuda_stream)      # the memset is ordered on the stream that will use the floats
     ent = _stats_pool.get(key)
     if ent is None or ent[1] + 8 > ent[0].numel():
@@ -197,3 +200,75 @@ class RenderFunction(torch.autograd.Function):
         gf = mlp_backward(net.fine_network, o, d, a["ts"], a["f_sigma"], a["f_rgb"], a["f_acts"], g_f.contiguous(), True)
         ctx.aux = None
         return (None,) * 6 + tuple(gc) + tuple(gf)
+
+
+class GraphedTrainStep:
+    """One optimiser step of NeRFNetwork - batch draw, forward, the two MSE losses, backward, gradient sum over the data-parallel
+    ranks, Adam, re-pack of the bf16 weight images - captured ONCE as a CUDA graph and replayed: ~35 kernel launches, the autograd
+    engine and every eager op of `training_step` cost one `cudaGraphLaunch` per step (the kernels of a 4096-ray step take ~3.2 ms,
+    the eager step 3.5 ms).  What changes from step to step lives in device memory: the image index (`img_idx`, filled by `step()`),
+    torch's Philox offsets (torch.cuda.graph's capture-aware generator), the optimiser's step count and learning rate
+    (optim.FlatAdam graph-safe form).
+
+    images [n,H,W,3] uint8 / poses [n,4,4]: the device-resident training split (dataloader.SyntheticDataset.stacked()); `cropping`
+    as dataloader.sample_random_coordinates.  The captured body is exactly Trainer.fit's eager body:
+        grads.zero(); loss = model.training_step(batch, 0); loss.backward(); grads.all_reduce_mean(); optimizer.step()
+    """
+
+    def __init__(self, model, optimizer, grads, images, poses, focal, num_rays, cropping=False, track_grad_norm=False, warmup=3,
+                 warmup_images=None):
+        import dataloader
+        self.model, self.optimizer, self.grads = model, optimizer, grads
+        dev = images.device
+        self.img_idx = torch.zeros((), device=dev, dtype=torch.int64)
+        n_img, H, W, _ = images.shape
+        self.n_img = n_img
+        self.grad_norm = None
+
+        def body():
+            xs, ys = dataloader.sample_random_coordinates(num_rays, H, W, cropping=cropping, device=dev)
+            o, d, rgb = dataloader.batch_rays(poses, self.img_idx, images, focal, xs, ys)
+            grads.zero()
+            loss = model.training_step({"origin": o[None], "direc": d[None], "rgb": rgb[None], "xs": xs[None], "ys": ys[None]}, 0)
+            loss.backward()
+            grads.all_reduce_mean()
+            if track_grad_norm:
+                self.grad_norm = grads.norm()
+            optimizer.step()
+            return loss.detach()
+
+        self._body = body
+        optimizer.graph_safe = True
+        optimizer.sync_device_state()
+        optimizer.set_device_step()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up on a side stream, as torch.cuda.graph asks for
+            for k in range(warmup):
+                if warmup_images:
+                    self.img_idx.fill_(int(warmup_images[k % len(warmup_images)]))
+                self.loss = body()
+                if k == 0:
+                    self.first_loss = self.loss.clone()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.warmup_steps = warmup                         # real optimiser steps: the caller counts them
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = body()
+        optimizer._step -= 1                               # the captured call only recorded a step: nothing ran
+        self._logged = dict(getattr(model, "logged", {}))
+
+    def eager_step(self, image_index):
+        """The same step run eagerly (launch by launch) - for per-kernel timing and for comparison with the replayed graph."""
+        self.optimizer.sync_device_state()
+        self.img_idx.fill_(int(image_index))
+        return self._body()
+
+    def step(self, image_index):
+        """Replay with the batch drawn from image `image_index`; returns the (device, 0-d) loss of this step."""
+        self.optimizer.sync_device_state()                 # the LR scheduler may have changed lr since the last step
+        self.img_idx.fill_(int(image_index))
+        self.graph.replay()
+        self.optimizer._step += 1
+        return self.loss

@@ -48,6 +48,13 @@ NERF_API const char* nerf_last_error(void);
 NERF_API int nerf_raygen(const float* c2w_host, int H, int W, float focal, const int64_t* xs, const int64_t* ys,
                 int64_t n, float* o, float* d, void* stream);
 
+/* ---- N1: one training batch (dataloader.py:143-152: rays of a pixel list + their colours) with the image chosen ON THE DEVICE, so
+ * that a CUDA graph of the training step can be replayed with a different image per step.  poses_dev [n_img,16]: row-major 4x4
+ * camera-to-world matrices; img_idx_dev: one int64 (clamped to [0, n_img)); images_u8 [n_img,H,W,3].  xs, ys [n] int64 as
+ * nerf_raygen.  o, d, rgb: [n,3]; rgb = fl32(u8 / 255), the division in double precision as numpy does upstream. */
+NERF_API int nerf_batch_rays(const float* poses_dev, const int64_t* img_idx_dev, const uint8_t* images_u8, int n_img, int H, int W,
+                             float focal, const int64_t* xs, const int64_t* ys, int64_t n, float* o, float* d, float* rgb, void* stream);
+
 /* ---- H1: stratified depths and points.  nerf_helpers.py:28-56.
  * u: [N,C] uniforms in [0,1).  t_base: [C] strata origins (the reference's torch.arange(near, far, step),
  * evaluated by the host with torch so that its rounding is inherited).  ts[n,i] = t_base[i] + u*step,
@@ -188,6 +195,13 @@ NERF_API int nerf_pack_weights_all(const float* const* params40_host, void* pack
  * 1 / world_size when `grads` holds the all-reduced SUM of the data-parallel ranks (the mean is never materialised). */
 NERF_API int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                             float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
+
+/* The same update with every step-dependent scalar in DEVICE memory, for a training step captured in a CUDA graph:
+ * state8_dev[0..4] = lr, beta1, beta2, eps, grad_scale (the host rewrites them when they change, e.g. the per-epoch LR decay),
+ * state8_dev[5..6] are scratch (step size and bias correction of the current step, evaluated on the device in double precision),
+ * *step_dev = steps taken so far, incremented by the call.  n must be a multiple of 4 (the flat buffers are padded). */
+NERF_API int nerf_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* state8_dev,
+                                int64_t* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -183,6 +183,59 @@ def test_dgrad_kernel_matches_library_chain():
             assert cos > 0.999 and rel < tol, f"{name} ({tag}): cosine {cos:.5f} rel {rel:.4f}"
 
 
+def test_graphed_train_step():
+    """training.GraphedTrainStep: Trainer.fit's step body captured as one CUDA graph.  Replays train (the loss falls like the
+    eager step's), the optimiser's host and device step counts stay together, a learning-rate change by the scheduler reaches the
+    captured Adam kernel through device memory, and the packed bf16 weight images follow the parameters (a render with the
+    trained network equals a render with a fresh network loaded from its state_dict, bit for bit)."""
+    import nerf_model
+    import training
+    from trainer import FlatGradients
+    H = W = 800
+    focal = O.focal_from_fov(W, 0.6911112070083618)
+    poses = torch.stack([synthetic.orbit_pose(a, -30.0, 4.0) for a in (40.0, 130.0)]).to(DEV).contiguous()
+    images = torch.stack([torch.from_numpy(synthetic.analytic_scene_rgba(p.cpu().numpy(), H, W, focal)[..., :3].copy()) for p in poses]).to(DEV).contiguous()
+    results = {}
+    for mode in ("graph", "eager"):
+        torch.manual_seed(7)
+        net = make_net(0, "init")
+        opt = net.configure_optimizers()["optimizer"]
+        grads = FlatGradients(net.parameters(), opt)
+        stepper = training.GraphedTrainStep(net, opt, grads, images, poses, focal, 1024, cropping=True)
+        losses = [float(stepper.first_loss)]
+        for k in range(40):
+            loss = stepper.step(k % 2) if mode == "graph" else stepper.eager_step(k % 2)
+            losses.append(float(loss))
+        torch.cuda.synchronize()
+        assert opt._step == 43 and int(opt.dev_step) == 43, (opt._step, int(opt.dev_step))
+        results[mode] = (losses, net, opt, stepper)
+    lg, le = results["graph"][0], results["eager"][0]
+    print("graph:", " ".join(f"{l:.4f}" for l in lg[::8]), "| eager:", " ".join(f"{l:.4f}" for l in le[::8]))
+    assert np.isfinite(lg).all() and np.mean(lg[-5:]) < 0.6 * lg[0] and np.mean(le[-5:]) < 0.6 * le[0]
+    assert abs(np.mean(lg[-10:]) - np.mean(le[-10:])) < 0.35 * np.mean(le[-10:])
+    # the scheduler's learning rate reaches the captured kernel: lr = 0 freezes the parameters
+    _, net, opt, stepper = results["graph"]
+    before = opt.flat_params.clone()
+    opt.param_groups[0]["lr"] = 0.0
+    stepper.step(0)
+    assert torch.equal(opt.flat_params, before)
+    opt.param_groups[0]["lr"] = 5e-4
+    stepper.step(1)
+    assert not torch.equal(opt.flat_params, before)
+    # packed weight images in step with the parameters
+    fresh = nerf_model.NeRFNetwork()
+    fresh.load_state_dict({k: v.detach().clone() for k, v in net.state_dict().items()})
+    fresh = fresh.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    o = torch.randn(300, 3, device=DEV, generator=g) * 0.2 + torch.tensor([0.0, 0.0, 4.0], device=DEV)
+    d = F.normalize(-o + 0.3 * torch.randn(300, 3, device=DEV, generator=g), dim=1)
+    rand = rand_triple(77, 300, device=DEV)
+    with torch.no_grad():
+        a = net.forward(o, d, rand=rand)["fine_rgb_rays"]
+        b = fresh.forward(o, d, rand=rand)["fine_rgb_rays"]
+    assert torch.equal(a, b)
+
+
 def test_flat_adam_matches_torch_adam():
     """optim.FlatAdam (one hand-written kernel over flat buffers, csrc/adam.cu) against torch.optim.Adam on the same
     gradients for 25 steps with a decaying learning rate, then a state_dict round trip into a fresh optimiser (the
