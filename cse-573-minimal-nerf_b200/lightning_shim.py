@@ -18,6 +18,10 @@ except Exception:
             self.logger = None
 
         def log(self, name, value, **kwargs):
+            # detached: a logged loss must not keep the step's autograd graph (and the parameters' grad accumulators, which
+            # remember the stream they were created on) alive into the next step - a CUDA-graph capture of that step would inherit
+            # accumulators bound to the warm-up stream
+            value = value.detach() if isinstance(value, torch.Tensor) else value
             self.logged[name] = value
             if self.trainer is not None and hasattr(self.trainer, "record"):
                 self.trainer.record(name, value)

@@ -119,6 +119,8 @@ def test_validation_step_and_logged_reconstruction(scene, tmp_path):
     logger = JsonLogger(name="val", project="NeRF", save_dir=tmp_path)
     net = nerf_model.NeRFNetwork()
     net.load_state_dict(synthetic.make_state_dict(4, "dense"))
+    net.max_idx = 0        # upstream draws the logged view from randint(0, max_idx) with max_idx starting at 1 (nerf_model.py:171-180): with
+                           # ONE validation image that logs a frame only every other time; 0 makes the draw land on the image we have
     scene_dm = dataloader.SyntheticDataModule(scene, 256, cropping_epochs=1)
     run = Trainer(gpus=1, default_root_dir=tmp_path, max_steps=6, logger=logger, check_val_every_n_epoch=1, track_grad_norm=2,
                   log_every_n_steps=1)
