@@ -301,6 +301,8 @@ def bench_train(args, rank, world, dev):
         sec = e["ms"] * 1e-3
         kernels.append({"kernel": name, "ms_per_step": e["ms"], "algorithmic_gb": gb, "hbm_gbs": gb / sec, "hbm_frac": gb / sec / pk["hbm_gbs"],
                         "tflops": tf / sec, "tensor_frac_of_sustained": tf / sec / pk["tflops_sustained"]})
+    torch.cuda.synchronize()
+    stepper.close()                               # destroys the CUDA graph (and the NCCL work captured in it) before the process group goes
     kms = sum(k["ms_per_step"] for k in kernels)
     tfl = n * 256 * TRAIN_FLOP_PER_SAMPLE / (ms * 1e-3) / 1e12
     dom = max(kernels, key=lambda k: k["ms_per_step"]) if kernels else None
@@ -506,7 +508,14 @@ def main():
             line["parity"] = line["cpu_baseline"].get("parity")
         emit(line)
     if world > 1:
+        # the line is out; nothing below may keep the job alive (a stuck communicator teardown would stall the driver's run)
+        watchdog = threading.Timer(60.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 if __name__ == "__main__":

@@ -122,6 +122,8 @@ class FlatAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         self._step += 1
         if self.graph_safe:
+            if not torch.cuda.is_current_stream_capturing():
+                self.sync_device_state()            # an eager step after graphed ones: the scheduler may have moved lr
             with torch.cuda.device(self.flat_params.device):
                 nat.check(nat.lib().nerf_adam_step_dev(nat.ptr(self.flat_params), nat.ptr(self.flat_grads), nat.ptr(self.flat_m),
                                                        nat.ptr(self.flat_v), self._n, nat.ptr(self.dev_state), nat.ptr(self.dev_step),

@@ -201,6 +201,12 @@ class Trainer:
                 self.save_checkpoint(model, optimizer, scheduler)
             self.current_epoch += 1
         model.on_coarse_grads_ready = None
+        # the captured training steps hold NCCL work (data parallel) and a few GB of graph-private memory: release them with the
+        # run, before anybody tears the process group down
+        torch.cuda.synchronize(self.device)
+        for stepper in self._steppers.values():
+            stepper.close()
+        self._steppers.clear()
         return model
 
     def _step_done(self, optimizer):

@@ -259,6 +259,15 @@ class GraphedTrainStep:
         optimizer._step -= 1                               # the captured call only recorded a step: nothing ran
         self._logged = dict(getattr(model, "logged", {}))
 
+    def close(self):
+        """Destroy the captured graph (and release its private memory pool).  REQUIRED before torch.distributed's process group is
+        destroyed when the step contains NCCL work: tearing a communicator down while a live CUDA graph still references its
+        kernels hangs (measured: tools/scratch/nccl_graph_teardown.py).  The object holds a reference cycle (the captured body
+        closes over it), so dropping the last reference is not enough."""
+        if self.graph is not None:
+            self.graph.reset()
+        self.graph, self._body, self.loss = None, None, None
+
     def eager_step(self, image_index):
         """The same step run eagerly (launch by launch) - for per-kernel timing and for comparison with the replayed graph."""
         self.optimizer.sync_device_state()

@@ -66,7 +66,7 @@ def main():
 
         def spy(*a, **k):
             xs, ys = real(*a, **k)
-            draws.append(xs[:8].cpu())
+            draws.append(xs[:8].clone())          # device-side copy: the call may sit inside a CUDA-graph capture (no host sync there)
             return xs, ys
         dataloader.sample_random_coordinates = spy
         first = {}
@@ -80,7 +80,7 @@ def main():
         run = train_nerf.main(["-n", "dp", "--gpu", "-s", str(steps), "-rd", str(out / "exp"), "-r", str(RAYS), "full", "-b", sys.argv[4], "-cr", "1"])
         torch.cuda.synchronize()
         torch.save({"final": run.optimizer.flat_params.cpu(), "before": first["before"], "after": first["after"],
-                    "draws": torch.stack(draws), "step": run.optimizer._step, "m": run.optimizer.flat_m.cpu()}, out / f"entry_rank{rank}.pt")
+                    "draws": torch.stack(draws).cpu(), "step": run.optimizer._step, "m": run.optimizer.flat_m.cpu()}, out / f"entry_rank{rank}.pt")
         if dist.is_initialized():
             dist.destroy_process_group()
         return

@@ -1,0 +1,29 @@
+import os, sys, time, torch, torch.distributed as dist
+mode = sys.argv[1]
+rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+x = torch.ones(1 << 20, device=dev)
+dist.all_reduce(x)
+s = torch.cuda.Stream()
+s.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(s):
+    for _ in range(3):
+        w = dist.all_reduce(x, async_op=True); w.wait()
+torch.cuda.current_stream().wait_stream(s)
+torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    w = dist.all_reduce(x, async_op=True); w.wait()
+    y = x * 2
+for _ in range(5):
+    g.replay()
+torch.cuda.synchronize()
+print(rank, mode, "replayed, x[0] =", float(x[0]), flush=True)
+t0 = time.time()
+if mode == "del":
+    del g, w
+    torch.cuda.synchronize()
+dist.barrier()
+dist.destroy_process_group()
+print(rank, mode, f"destroyed in {time.time() - t0:.2f} s", flush=True)
