@@ -60,7 +60,15 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
+
+    def mark(self, wait_s=3.0):
+        """Start of the timed region: wait (bounded) until nvidia-smi has delivered its first sample - with 8 ranks each starting
+        one it can take longer than a short timed region - and count only the samples taken from here on."""
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < wait_s:
+            time.sleep(0.02)
+        self.first = max(len(self.rows) - 1, 0)
 
     def __enter__(self):
         try:
@@ -87,7 +95,7 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
                 for n, v in zip(names, r[2:6]):
@@ -408,6 +416,8 @@ def main():
     nat.kernel_events = []
     step_ms = []
     with ClockSampler(local_rank) as clocks:
+        render(o, d)                          # one more untimed frame: the GPU is under load while the sampler comes up
+        clocks.mark()
         for k in range(args.steps):
             o, d = rays_for(k)
             flush.fill_(k & 0xFF)
