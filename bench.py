@@ -418,6 +418,9 @@ def main():
     with ClockSampler(local_rank) as clocks:
         render(o, d)                          # one more untimed frame: the GPU is under load while the sampler comes up
         clocks.mark()
+        barrier()
+        nat.launches = 0
+        nat.kernel_events = []
         for k in range(args.steps):
             o, d = rays_for(k)
             flush.fill_(k & 0xFF)
