@@ -472,16 +472,50 @@ merge_sort256_kernel(const float* __restrict__ o, const float* __restrict__ d, c
 // ---------------------------------------------------------------------------- K3 + K4 in one launch
 // What NeRFNetwork.forward does between the two networks (nerf_model.py:114-120): inverse-CDF fine depths, concatenated
 // with the coarse depths (fine first) and sorted - without the round trip of the fine depths through HBM.  One warp per
-// ray; the same cdf / search / jitter arithmetic as fine_sample_kernel and the same register-resident bitonic network as
-// merge_sort256_kernel (C + F <= 256), so the sorted depths are bit-identical to the two-launch path.
+// ray; the same cdf / search / jitter arithmetic as fine_sample_kernel.
+//
+// The sort uses what is known about the two halves instead of a 256-wide network over everything: the C coarse depths
+// arrive SORTED (stratified: t_i lies in stratum i), so only the F <= 128 fine depths go through a bitonic network (128
+// wide: 28 compare stages over 4 registers instead of 36 over 8), and the two sorted runs are merged by RANK - a fine
+// depth's slot is its index plus the number of coarse depths below it, a coarse depth's slot its index plus the number of
+// fine depths not above it (binary searches in shared memory; ties go fine-first, so the slots are a permutation).  A sorted
+// array is unique, so the result is bit-identical to sorting all C + F values (tests/test_gpu_fused_composite.py, incl. rays
+// whose cdf is NaN).  Rays whose coarse depths are NOT sorted (a caller's own depths), a NaN depth, or F > 128 take the
+// general path: the 256-wide network of merge_sort256_kernel over the concatenation.
+__device__ __forceinline__ void bitonic_stage(float (&v)[8], int nreg, int k, int dist, int lane) {
+    if (dist >= 32) {
+        const int dj = dist >> 5;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nreg && (j & dj) == 0) {
+                const bool up = (((32 * j + lane) & k) == 0);
+                cmpx(v[j], v[j | dj], up);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nreg) {
+                const int el = 32 * j + lane;
+                const float other = __shfl_xor_sync(kFull, v[j], dist);
+                const bool up = ((el & k) == 0);
+                const bool lower = ((lane & dist) == 0);
+                v[j] = (up == lower) ? fminf(v[j], other) : fmaxf(v[j], other);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 fine_sample_merge_kernel(const float* __restrict__ w, const float* __restrict__ ts, const float* __restrict__ eps,
                          const float* __restrict__ u, const float* __restrict__ q_base, int64_t N, int C, int F,
                          float near_, float far_, float* __restrict__ ts_sorted) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float* cdf = smem + (size_t)wib * (2 * C + 2);
+    float* cdf = smem + (size_t)wib * (2 * C + 2 + 128 + 256);
     float* bounds = cdf + C;
+    float* fsorted = bounds + C + 2;           // rank merge: the sorted fine depths ...
+    float* merged = fsorted + 128;             // ... and the merged row, written back coalesced
     const int64_t warps = (int64_t)gridDim.x * kWarpsPerBlock;
     const float Ff = (float)F;
     const int S = C + F;
@@ -504,6 +538,7 @@ fine_sample_merge_kernel(const float* __restrict__ w, const float* __restrict__ 
         __syncwarp();
         const float e = __fdiv_rn(eps[n], Ff);                                      // nerf_helpers.py:139
         float v[8];
+        bool plain = true;                                                           // no NaN among this lane's values
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
             const int j = 32 * jj + lane;                                             // element index in cat([fine, coarse])
@@ -517,42 +552,65 @@ fine_sample_merge_kernel(const float* __restrict__ w, const float* __restrict__ 
                 }
                 const float b0 = bounds[lo], b1 = bounds[lo + 1];
                 t = __fadd_rn(b0, __fmul_rn(__fsub_rn(b1, b0), u[n * F + j]));       // nerf_helpers.py:154
-            } else if (j < S) {
-                t = bounds[j - F + 1];                                                // nerf_model.py:117 (fine first, then coarse)
+                plain = plain && (t == t);
             }
             v[jj] = t;
+        }
+        bool run_sorted = F <= 128 && C <= 128;
+        for (int i = lane; i + 1 < C; i += kWarp) run_sorted = run_sorted && (bounds[i + 2] >= bounds[i + 1]);   // false on NaN too
+        if (__all_sync(kFull, run_sorted && plain)) {
+            // ---- 128-wide network over the fine depths (registers 0..3; entries >= F are +inf), then the rank merge
+#pragma unroll
+            for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+                for (int dist = k >> 1; dist >= 1; dist >>= 1) bitonic_stage(v, 4, k, dist, lane);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) fsorted[32 * jj + lane] = v[jj];
+            __syncwarp();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int el = 32 * jj + lane;
+                if (el < F) {
+                    const float t = v[jj];
+                    int lo = 0, hi = C;                                               // coarse depths below t
+                    while (lo < hi) {
+                        const int mid = lo + ((hi - lo) >> 1);
+                        if (bounds[mid + 1] < t) lo = mid + 1; else hi = mid;
+                    }
+                    merged[el + lo] = t;
+                }
+            }
+            for (int i = lane; i < C; i += kWarp) {
+                const float tc = bounds[i + 1];
+                int lo = 0, hi = F;                                                   // fine depths not above tc
+                while (lo < hi) {
+                    const int mid = lo + ((hi - lo) >> 1);
+                    if (fsorted[mid] <= tc) lo = mid + 1; else hi = mid;
+                }
+                merged[i + lo] = tc;
+            }
+            __syncwarp();
+            for (int el = lane; el < S; el += kWarp) ts_sorted[n * S + el] = merged[el];
+            __syncwarp();
+            continue;
+        }
+        // ---- general path: the coarse depths join the fine ones (nerf_model.py:117: fine first, then coarse), 256-wide network
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = 32 * jj + lane;
+            if (j >= F && j < S) v[jj] = bounds[j - F + 1];
         }
 #pragma unroll
         for (int k = 2; k <= 256; k <<= 1) {
 #pragma unroll
-            for (int dist = k >> 1; dist >= 1; dist >>= 1) {
-                if (dist >= 32) {
-                    const int dj = dist >> 5;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if ((j & dj) == 0) {
-                            const bool up = (((32 * j + lane) & k) == 0);
-                            cmpx(v[j], v[j | dj], up);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int el = 32 * j + lane;
-                        const float other = __shfl_xor_sync(kFull, v[j], dist);
-                        const bool up = ((el & k) == 0);
-                        const bool lower = ((lane & dist) == 0);
-                        v[j] = (up == lower) ? fminf(v[j], other) : fmaxf(v[j], other);
-                    }
-                }
-            }
+            for (int dist = k >> 1; dist >= 1; dist >>= 1) bitonic_stage(v, 8, k, dist, lane);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int el = 32 * j + lane;
             if (el < S) ts_sorted[n * S + el] = v[j];
         }
-        __syncwarp();
     }
 }
 
@@ -807,7 +865,7 @@ extern "C" int nerf_fine_sample_merge(const float* w, const float* ts, const flo
     NERF_REQUIRE(N >= 0 && C > 0 && F > 0 && C + F <= 256, "nerf_fine_sample_merge: bad size N=%lld C=%d F=%d (C + F <= 256)", (long long)N, C, F);
     if (N == 0) return 0;
     NERF_REQUIRE(w && ts && eps && u && q_base && ts_sorted, "nerf_fine_sample_merge: null pointer");
-    const size_t smem = (size_t)kWarpsPerBlock * (2 * C + 2) * sizeof(float);
+    const size_t smem = (size_t)kWarpsPerBlock * (2 * C + 2 + 128 + 256) * sizeof(float);
     fine_sample_merge_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, smem, (cudaStream_t)stream>>>(
         w, ts, eps, u, q_base, N, C, F, near_, far_, ts_sorted);
     return check_launch("nerf_fine_sample_merge");

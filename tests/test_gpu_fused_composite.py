@@ -181,11 +181,22 @@ def test_fine_depths_sorted_matches_sampler_plus_merge(N, C, F):
     if N > 3:
         w[3, : C // 2] = 0.0                                      # flat cdf prefix (ties in the search)
     rand = (torch.rand(N, 1, device=DEV, generator=g), torch.rand(N, F, 1, device=DEV, generator=g))
+    rand[1][::5, ::3] = 0.0                                       # jitter 0: the fine depth EQUALS a coarse depth (ties in the rank merge)
     _, f_ts = h.inverse_transform_sampling(o, d, w, c_ts, F, rand=rand)
     _, ref = h.merge_samples(o, d, f_ts, c_ts, want_points=False)
     got = h.fine_depths_sorted(w, c_ts, F, rand=rand)
     torch.cuda.synchronize()
     assert got.shape == (N, C + F, 1) and bits_equal(got, ref)
+    assert bool((got[:, 1:] >= got[:, :-1]).all())
+    # a caller's own, UNSORTED coarse depths (every second ray reversed): those rays take the general 256-wide network
+    if C > 1:
+        c_mix = c_ts.clone()
+        c_mix[1::2] = c_mix[1::2].flip(1)
+        _, f_ts = h.inverse_transform_sampling(o, d, w, c_mix, F, rand=rand)
+        _, ref = h.merge_samples(o, d, f_ts, c_mix, want_points=False)
+        got = h.fine_depths_sorted(w, c_mix, F, rand=rand)
+        torch.cuda.synchronize()
+        assert bits_equal(got, ref)
 
 
 def test_full_frame_is_independent_of_chunking_and_sharding():
