@@ -506,7 +506,7 @@ __device__ __forceinline__ void bitonic_stage(float (&v)[8], int nreg, int k, in
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)          // 32 registers: 64 resident warps per SM (the kernel is a latency chain per ray)
 fine_sample_merge_kernel(const float* __restrict__ w, const float* __restrict__ ts, const float* __restrict__ eps,
                          const float* __restrict__ u, const float* __restrict__ q_base, int64_t N, int C, int F,
                          float near_, float far_, float* __restrict__ ts_sorted) {
