@@ -45,6 +45,7 @@ _PROTOTYPES = {
     "nerf_packed_t_bytes": (ctypes.c_size_t, []),
     "nerf_pack_weights_t": (_int, [_vp, _vp, _vp]),
     "nerf_mlp_backward_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    "nerf_mlp_backward_tc_fused": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "nerf_wgrad_tc": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "nerf_mlp_forward_tc_points": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "nerf_mlp_composite_tc_supported": (_int, [_int]),

@@ -11,8 +11,16 @@
 // 1 = pre-activation negative; they are applied to the PACKED bf16 pairs (shift + PRMT sign replication + AND-NOT: three
 // instructions per pair).
 // mlp.0's dgrad (d PE) is not needed: the inputs carry no gradient.
+//
+// FUSED form (what training.py launches): the compositing backward (autograd of nerf_helpers.py:58-104) runs INSIDE this kernel.
+// The four producer warps take the rays that overlap the tile pair (one ray per warp at a time, composite_backward_ray of
+// composite_scan.cuh: the same routine as the stand-alone composite_backward_kernel, so dz is bit-identical), leave
+// (dsigma_pre, drgb_pre) of the pair's 256 samples in shared memory (double-buffered by pair), and build the dr tile / heads
+// block from there; the epilogue takes dsigma_pre from the same buffer.  Inputs are then the forward's saved sigma / rgb /
+// depths and dL/d(ray colour) instead of two [N*S] gradient arrays: one launch and 32 B per sample of HBM traffic less.
 #include <type_traits>
 #include "mlp_tc3_common.cuh"
+#include "composite_scan.cuh"
 
 namespace nerf {
 
@@ -48,21 +56,32 @@ namespace b3 {
 constexpr uint32_t kOffDr = 0;                                    // dr tiles of X and Y: 2 x 2 K-blocks x [128 x 64] bf16
 constexpr uint32_t kOffRing = t3::kOffRing;                       // 65536
 constexpr uint32_t kOffConst = kOffRing + t3::kSlots * t3::kSlotBytes;      // fp32 W9 [3][128], w7 [256]
-constexpr uint32_t kOffBars = kOffConst + pk::kConstFloatsT * 4;
+constexpr uint32_t kOffHeadGrad = kOffConst + pk::kConstFloatsT * 4;          // FUSED: 2 pairs x 256 samples x float4 (dsigma_pre, drgb_pre)
+constexpr uint32_t kOffBars = kOffHeadGrad + 2 * 256 * 16;
 constexpr uint32_t kOffTmemHolder = kOffBars + t3::kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemHolder + 16 + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 constexpr int kStagesT = pk::kStagesT;                            // 52 requests of 16 KB per tile pair
 }  // namespace b3
 
+// FUSED: (dsigma_pre, drgb_pre) are not read; (sigma, rgb, ts, g_ray, S) are.
+struct HeadGradSource {
+    const float* dsigma_pre; const float* drgb_pre;                      // !FUSED
+    const float* sigma; const float* rgb; const float* ts; const float* g_ray; int S;      // FUSED
+};
+
+template <bool FUSED>
 __global__ void __launch_bounds__(t3::kThreads, 1)
-mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restrict__ masks32, const float* __restrict__ dsigma_pre,
-                   const float* __restrict__ drgb_pre, int64_t total, __nv_bfloat16* __restrict__ dz_out) {
+mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restrict__ masks32, const HeadGradSource src, int64_t total,
+                   __nv_bfloat16* __restrict__ dz_out) {
+    const float* __restrict__ dsigma_pre = src.dsigma_pre;
+    const float* __restrict__ drgb_pre = src.drgb_pre;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = umma::smem_u32(smem);
     const uint32_t bars = sbase + b3::kOffBars;
     float* sConst = (float*)(smem + b3::kOffConst);        // [0,384) W9[c][k], [384,640) w7[k]
+    float4* sHead = (float4*)(smem + b3::kOffHeadGrad);    // FUSED: [pair parity][256] (dsigma_pre, drgb_pre x 3)
     uint32_t* tmem_holder = (uint32_t*)(smem + b3::kOffTmemHolder);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -134,14 +153,32 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
         const float* W9 = sConst;
         uint32_t it = 0;
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++it) {
+            float4* head = sHead + (it & 1u) * 256;               // (the buffer's last reader was pair it - 2's first chain step)
+            if (FUSED) {
+                // compositing backward of every ray that overlaps this pair's 256 samples, one ray per warp at a time
+                const int64_t row_lo = pair * 2 * t3::kTileM, row_hi = (row_lo + 2 * t3::kTileM < total) ? row_lo + 2 * t3::kTileM : total;
+                const int64_t n_hi = (row_hi - 1) / src.S;
+                for (int64_t n = row_lo / src.S + (warp - 20); n <= n_hi; n += t3::kPEWarps) {
+                    const int64_t first = n * src.S - row_lo;     // pair-local row of the ray's sample 0 (may be negative)
+                    composite_backward_ray(src.sigma, src.rgb, src.ts, src.g_ray, n, src.S, lane, [&](int i, float ds, float d0, float d1, float d2) {
+                        const int64_t local = first + i;
+                        if (local >= 0 && local < 2 * t3::kTileM) head[local] = make_float4(ds, d0, d1, d2);
+                    });
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // the four producer warps: every sample of the pair is in place
+            }
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
                 const int64_t tile = pair * 2 + t;
                 const int64_t row = tile * t3::kTileM + r;
                 const bool valid = row < total;
                 const bool store = tile < num_tiles;              // dz_out holds whole tiles only
-                float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-                if (valid) { g0 = drgb_pre[row * 3]; g1 = drgb_pre[row * 3 + 1]; g2 = drgb_pre[row * 3 + 2]; }
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f, dsg_row = 0.f;
+                if (FUSED) {
+                    if (valid) { const float4 hg = head[t * t3::kTileM + r]; dsg_row = hg.x; g0 = hg.y; g1 = hg.z; g2 = hg.w; }
+                } else if (valid) {
+                    g0 = drgb_pre[row * 3]; g1 = drgb_pre[row * 3 + 1]; g2 = drgb_pre[row * 3 + 2]; dsg_row = dsigma_pre[row];
+                }
                 umma::mbar_wait_u32(bars + 8u * (t3::kBarPexEmpty + t), (it & 1u) ^ 1u);
                 uint8_t* tile_smem = smem + b3::kOffDr + t * 32768;
 #pragma unroll 1
@@ -165,7 +202,7 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                     if (store) *(uint4*)(dz_out + pk::tiled_offset(row, 1792 + c * 8, pk::kDzChunks)) = q4;
                 }
                 if (store) {   // heads block (features 1920..1935): [dsigma_pre, drgb_pre x3, 0 ...] in bf16 for the head weight gradients
-                    const float dsg = valid ? dsigma_pre[row] : 0.f;
+                    const float dsg = dsg_row;
                     uint4* dst = (uint4*)(dz_out + pk::tiled_offset(row, 1920, pk::kDzChunks));
                     dst[0] = make_uint4(umma::pack_bf16(dsg, g0), umma::pack_bf16(g1, g2), 0u, 0u);
                     dst[128] = make_uint4(0u, 0u, 0u, 0u);
@@ -195,12 +232,22 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
             for (int i = 0; i < 4; ++i) store_once(dst + i * 128, make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]));
         };
 
-        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        uint32_t eit = 0;
+        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++eit) {
             const int64_t row0 = pair * 2 * t3::kTileM + r;
             const bool st1 = (pair * 2 + 1 < num_tiles);
-            float dsg[2];
-            dsg[0] = (row0 < total) ? dsigma_pre[row0] : 0.f;
-            dsg[1] = (row0 + 128 < total) ? dsigma_pre[row0 + 128] : 0.f;
+            float dsg[2] = {0.f, 0.f};
+            if (FUSED) {
+                // the producers' shared-memory results of this pair: acquire them through the barrier they arrived on (long complete)
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    umma::mbar_wait_u32(bars + 8u * (t3::kBarPexFull + t), eit & 1u);
+                    if (row0 + t * 128 < total) dsg[t] = sHead[(eit & 1u) * 256 + t * 128 + r].x;
+                }
+            } else {
+                dsg[0] = (row0 < total) ? dsigma_pre[row0] : 0.f;
+                dsg[1] = (row0 + 128 < total) ? dsigma_pre[row0 + 128] : 0.f;
+            }
             // this thread's place in the tiled chunk-major tensors as ONE running pointer pair (the epilogue is instruction-issue
             // bound): its 32-feature group of layer 6 in tile X; tile Y and a layer's second half sit at constant offsets, every
             // chain step moves the pointers back by 256 features
@@ -295,19 +342,24 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
     if (warp == 2) umma::tmem_dealloc(tmem, 512);
 }
 
-int launch_mlp_tc_bwd3(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre, int64_t total,
-                       void* dz_out, void* stream) {
+int launch_mlp_tc_bwd3(const void* packed_t, const void* masks, const HeadGradSource& src, bool fused, int64_t total, void* dz_out,
+                       void* stream) {
     static thread_local unsigned long long attr_mask = 0;
     if (attrs_pending(attr_mask)) {
-        cudaError_t e = allow_smem(mlp_tc_bwd3_kernel, b3::kSmemBytes);
+        cudaError_t e = allow_smem(mlp_tc_bwd3_kernel<false>, b3::kSmemBytes);
+        if (e == cudaSuccess) e = allow_smem(mlp_tc_bwd3_kernel<true>, b3::kSmemBytes);
         if (e != cudaSuccess) { set_error("nerf_mlp_backward_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
         attrs_done(attr_mask);
     }
     const int64_t tiles = (total + t3::kTileM - 1) / t3::kTileM;
     const int64_t pairs = (tiles + 1) / 2;
     const int grid = (int)(pairs < num_sms() ? pairs : num_sms());
-    mlp_tc_bwd3_kernel<<<grid, t3::kThreads, b3::kSmemBytes, (cudaStream_t)stream>>>(
-        (const uint8_t*)packed_t, (const uint32_t*)masks, dsigma_pre, drgb_pre, total, (__nv_bfloat16*)dz_out);
+    if (fused)
+        mlp_tc_bwd3_kernel<true><<<grid, t3::kThreads, b3::kSmemBytes, (cudaStream_t)stream>>>(
+            (const uint8_t*)packed_t, (const uint32_t*)masks, src, total, (__nv_bfloat16*)dz_out);
+    else
+        mlp_tc_bwd3_kernel<false><<<grid, t3::kThreads, b3::kSmemBytes, (cudaStream_t)stream>>>(
+            (const uint8_t*)packed_t, (const uint32_t*)masks, src, total, (__nv_bfloat16*)dz_out);
     return check_launch("nerf_mlp_backward_tc");
 }
 
@@ -322,5 +374,17 @@ extern "C" int nerf_mlp_backward_tc(const void* packed_t, const void* masks, con
     NERF_REQUIRE(packed_t && masks && dsigma_pre && drgb_pre && dz_out, "nerf_mlp_backward_tc: null pointer");
     NERF_REQUIRE(((uintptr_t)packed_t & 127) == 0 && ((uintptr_t)masks & 7) == 0 && ((uintptr_t)dz_out & 15) == 0,
                  "nerf_mlp_backward_tc: misaligned buffer");
-    return launch_mlp_tc_bwd3(packed_t, masks, dsigma_pre, drgb_pre, N * S, dz_out, stream);
+    const HeadGradSource src{dsigma_pre, drgb_pre, nullptr, nullptr, nullptr, nullptr, S};
+    return launch_mlp_tc_bwd3(packed_t, masks, src, false, N * S, dz_out, stream);
+}
+
+extern "C" int nerf_mlp_backward_tc_fused(const void* packed_t, const void* masks, const float* sigma, const float* rgb, const float* ts,
+                                          const float* g_ray, int64_t N, int S, void* dz_out, void* stream) {
+    NERF_REQUIRE(N >= 0 && S > 0 && S <= 1024, "nerf_mlp_backward_tc_fused: bad size (S <= 1024)");
+    if (N == 0) return 0;
+    NERF_REQUIRE(packed_t && masks && sigma && rgb && ts && g_ray && dz_out, "nerf_mlp_backward_tc_fused: null pointer");
+    NERF_REQUIRE(((uintptr_t)packed_t & 127) == 0 && ((uintptr_t)masks & 7) == 0 && ((uintptr_t)dz_out & 15) == 0,
+                 "nerf_mlp_backward_tc_fused: misaligned buffer");
+    const HeadGradSource src{nullptr, nullptr, sigma, rgb, ts, g_ray, S};
+    return launch_mlp_tc_bwd3(packed_t, masks, src, true, N * S, dz_out, stream);
 }

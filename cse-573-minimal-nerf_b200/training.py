@@ -59,18 +59,29 @@ def composite_backward(sigma, rgb, ts, g_ray):
     return dsig, drgb
 
 
+FUSE_COMPOSITE_BACKWARD = True     # the compositing backward inside the dgrad kernel's producer warps (nerf_mlp_backward_tc_fused)
+
+
 def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray, accumulate_into_grad=False):
     """Gradients of one network's 20 parameters (state_dict order) given dL/d(ray colour) [N,3]: all hand-written kernels -
-    compositing backward, tcgen05 dgrad chain (mlp_tc_bwd.cu), tcgen05 wgrad + bias sums (wgrad_tc.cu)."""
+    tcgen05 dgrad chain with the compositing backward in its producer warps (mlp_tc_bwd3.cu), tcgen05 wgrad + bias sums
+    (wgrad_tc.cu).  FUSE_COMPOSITE_BACKWARD = False keeps the compositing backward as its own launch (bit-identical dz)."""
     import ctypes
     acts, masks = acts
     N, S = ts.shape[0], ts.shape[1]
     M = N * S
-    dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
     dz_t = torch.empty((padded_rows(M) * DZ,), device=ts.device, dtype=BF)
-    with nat.timed_kernel("mlp_tc_bwd_kernel", M):
-        nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb),
-                                                 N, S, nat.ptr(dz_t), nat.stream()), "nerf_mlp_backward_tc")
+    if FUSE_COMPOSITE_BACKWARD and S <= 1024:
+        g = nat.dev(g_ray, "g_ray")
+        with nat.timed_kernel("mlp_tc_bwd_kernel", M):
+            nat.check(nat.lib().nerf_mlp_backward_tc_fused(nat.ptr(model.packed_weights_t()), nat.ptr(masks), nat.ptr(sigma), nat.ptr(rgb),
+                                                           nat.ptr(ts), nat.ptr(g), N, S, nat.ptr(dz_t), nat.stream()),
+                      "nerf_mlp_backward_tc_fused")
+    else:
+        dsig, drgb = composite_backward(sigma, rgb, ts, g_ray)
+        with nat.timed_kernel("mlp_tc_bwd_kernel", M):
+            nat.check(nat.lib().nerf_mlp_backward_tc(nat.ptr(model.packed_weights_t()), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb),
+                                                     N, S, nat.ptr(dz_t), nat.stream()), "nerf_mlp_backward_tc")
     params = model.ordered_params()
     direct = accumulate_into_grad and all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == F32 for p in params)
     if direct:

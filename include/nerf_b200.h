@@ -150,6 +150,11 @@ NERF_API size_t nerf_packed_t_bytes(void);
 NERF_API int nerf_pack_weights_t(const float* const* params20_host, void* packed_t, void* stream);
 NERF_API int nerf_mlp_backward_tc(const void* packed_t, const void* masks, const float* dsigma_pre, const float* drgb_pre,
                          int64_t N, int S, void* dz_out, void* stream);
+/* The same dgrad chain with the compositing backward (nerf_composite_backward) INSIDE the kernel - what the training step launches:
+ * the producer warps turn g_ray [N,3] = dL/d(ray colour) and the forward's saved sigma [N,S], rgb [N,S,3], ts [N,S] into the head
+ * gradients of the 256 samples of each tile pair in shared memory; dz_out is bit-identical to the two-call sequence. S <= 1024. */
+NERF_API int nerf_mlp_backward_tc_fused(const void* packed_t, const void* masks, const float* sigma, const float* rgb, const float* ts,
+                                        const float* g_ray, int64_t N, int S, void* dz_out, void* stream);
 /* ---- weight / bias gradients of one network on the tensor cores: dW_l += dz_l^T . (input of layer l), db_l += sum dz_l.
  * acts, dz: the tiled chunk-major training tensors written by nerf_mlp_forward_tc_train / nerf_mlp_backward_tc;
  * o, d, ts as in the forward (PE(x) / PE(dir) operands are recomputed).  grads20_host: HOST array of 20 device pointers

@@ -236,6 +236,36 @@ def test_graphed_train_step():
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("N,S", [(700, 67), (4096, 64), (1024, 192), (1, 64), (37, 1), (5, 1024), (301, 192)])
+def test_dgrad_with_compositing_backward_inside_is_bit_identical(N, S):
+    """nerf_mlp_backward_tc_fused (the compositing backward in the dgrad kernel's producer warps) against nerf_composite_backward +
+    nerf_mlp_backward_tc: the same per-ray routine, so the dz tensor - every layer's pre-activation gradient and the heads block -
+    must be BIT-identical, for rays that straddle tile pairs (S = 67, 192), many rays per pair (S = 1, 64) and rays longer than a
+    pair (S = 1024)."""
+    import _native as nat
+    import training
+    torch.manual_seed(3)
+    net = make_net(4, "dense")
+    o = torch.randn(N, 3, device=DEV) * 0.3
+    d = F.normalize(torch.randn(N, 3, device=DEV), dim=1) * 1.05
+    ts = (2.0 + 4.0 * torch.sort(torch.rand(N, S, 1, device=DEV), dim=1).values).contiguous()
+    model = net.fine_network
+    sigma, rgb, (acts, masks) = training.mlp_forward_train(model, o, d, ts)
+    g_ray = torch.randn(N, 3, device=DEV) / N
+    M = N * S
+    lib = nat.lib()
+    dsig, drgb = training.composite_backward(sigma, rgb, ts, g_ray)
+    a = torch.zeros((training.padded_rows(M) * training.DZ,), device=DEV, dtype=torch.bfloat16)
+    b = torch.zeros_like(a)
+    packed_t = model.packed_weights_t()
+    nat.check(lib.nerf_mlp_backward_tc(nat.ptr(packed_t), nat.ptr(masks), nat.ptr(dsig), nat.ptr(drgb), N, S, nat.ptr(a), nat.stream()), "dgrad")
+    nat.check(lib.nerf_mlp_backward_tc_fused(nat.ptr(packed_t), nat.ptr(masks), nat.ptr(sigma), nat.ptr(rgb), nat.ptr(ts), nat.ptr(g_ray), N, S,
+                                             nat.ptr(b), nat.stream()), "dgrad fused")
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    assert float(a.float().abs().max()) > 0
+
+
 def test_flat_adam_matches_torch_adam():
     """optim.FlatAdam (one hand-written kernel over flat buffers, csrc/adam.cu) against torch.optim.Adam on the same
     gradients for 25 steps with a decaying learning rate, then a state_dict round trip into a fresh optimiser (the
