@@ -273,7 +273,7 @@ class GraphedTrainStep:
     def close(self):
         """Destroy the captured graph (and release its private memory pool).  REQUIRED before torch.distributed's process group is
         destroyed when the step contains NCCL work: tearing a communicator down while a live CUDA graph still references its
-        kernels hangs (measured: tools/scratch/nccl_graph_teardown.py).  The object holds a reference cycle (the captured body
+        kernels hangs (measured: tools/probe_nccl_graph_teardown.py).  The object holds a reference cycle (the captured body
         closes over it), so dropping the last reference is not enough."""
         if self.graph is not None:
             self.graph.reset()
