@@ -181,12 +181,18 @@ mlp_tc_bwd3_kernel(const uint8_t* __restrict__ packed_t, const uint32_t* __restr
                 }
                 umma::mbar_wait_u32(bars + 8u * (t3::kBarPexEmpty + t), (it & 1u) ^ 1u);
                 uint8_t* tile_smem = smem + b3::kOffDr + t * 32768;
-#pragma unroll 1
+                // sign words of r's four 32-feature groups 56 .. 59 (r = activations 1792..1919), requested together: the chunk loop
+                // below used to wait for one (L1 / L2 latency) per chunk, and the producers' time per pair bounds the kernel once the
+                // compositing backward runs here too
+                uint32_t mw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+                if (store) {
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) mw[gq] = __ldg(masks32 + ((row >> 7) * (2 * pk::kMaskWords) + 56 + gq) * 128 + (row & 127));
+                }
+#pragma unroll 4
                 for (int c = 0; c < 16; ++c) {                    // chunk c = features 8c .. 8c+7 of r (rgb_fn.0's ReLU output)
-                    // sign bits written by the forward kernel: 32-bit half (c >> 2) & 1 of block 28 + (c >> 3)
-                    // sign word of r's 32-feature group 56 + (c >> 2) (r = activations 1792..1919); this chunk = pairs 4(c&3)..+3
-                    uint32_t mb = 0xFFFFFFFFu;
-                    if (store) mb = masks32[((row >> 7) * (2 * pk::kMaskWords) + 56 + (c >> 2)) * 128 + (row & 127)];
+                    // this chunk = pairs 4(c&3)..+3 of group c >> 2
+                    uint32_t mb = mw[c >> 2];
                     mb <<= (c & 3) * 4;
                     uint32_t v[4];
 #pragma unroll
