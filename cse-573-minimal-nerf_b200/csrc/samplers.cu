@@ -11,6 +11,7 @@
 // 128-byte row loads, the serial chain broadcast through shuffles), one thread per element otherwise.
 #include "common.cuh"
 #include "composite_scan.cuh"
+#include "fine_sampler.cuh"
 
 namespace nerf {
 
@@ -392,12 +393,6 @@ fine_sample_kernel(const float* __restrict__ o, const float* __restrict__ d, con
 // in registers: element e = 32 j + lane lives in register j of that lane, so compare distances >= 32 are register-to-register
 // and distances < 32 are one __shfl_xor each.  Sorting values only - equal depths are interchangeable - so the result is the
 // same multiset order torch.sort produces.
-__device__ __forceinline__ void cmpx(float& a, float& b, bool up) {
-    const float lo = fminf(a, b), hi = fmaxf(a, b);
-    a = up ? lo : hi;
-    b = up ? hi : lo;
-}
-
 __global__ void __launch_bounds__(kThreads)
 merge_sort256_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ ts_a, int A,
                      const float* __restrict__ ts_b, int B, int64_t N, float* __restrict__ ts_sorted,
@@ -469,137 +464,24 @@ merge_sort256_kernel(const float* __restrict__ o, const float* __restrict__ d, c
 // array is unique, so the result is bit-identical to sorting all C + F values (tests/test_gpu_fused_composite.py, incl. rays
 // whose cdf is NaN).  Rays whose coarse depths are NOT sorted (a caller's own depths), a NaN depth, or F > 128 take the
 // general path: the 256-wide network of merge_sort256_kernel over the concatenation.
-__device__ __forceinline__ void bitonic_stage(float (&v)[8], int nreg, int k, int dist, int lane) {
-    if (dist >= 32) {
-        const int dj = dist >> 5;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < nreg && (j & dj) == 0) {
-                const bool up = (((32 * j + lane) & k) == 0);
-                cmpx(v[j], v[j | dj], up);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < nreg) {
-                const int el = 32 * j + lane;
-                const float other = __shfl_xor_sync(kFull, v[j], dist);
-                const bool up = ((el & k) == 0);
-                const bool lower = ((lane & dist) == 0);
-                v[j] = (up == lower) ? fminf(v[j], other) : fmaxf(v[j], other);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kThreads, 8)          // 32 registers: 64 resident warps per SM (the kernel is a latency chain per ray)
+__global__ void __launch_bounds__(kThreads, 8)          // 32 registers: 64 resident warps per SM (a per-ray latency chain)
 fine_sample_merge_kernel(const float* __restrict__ w, const float* __restrict__ ts, const float* __restrict__ eps,
                          const float* __restrict__ u, const float* __restrict__ q_base, int64_t N, int C, int F,
                          float near_, float far_, float* __restrict__ ts_sorted) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float* cdf = smem + (size_t)wib * (2 * C + 2 + 128 + 256);
-    float* bounds = cdf + C;
-    float* fsorted = bounds + C + 2;           // rank merge: the sorted fine depths ...
-    float* merged = fsorted + 128;             // ... and the merged row, written back coalesced
+    float* scratch = smem + (size_t)wib * fine_sampler_floats(C);
     const int64_t warps = (int64_t)gridDim.x * kWarpsPerBlock;
-    const float Ff = (float)F;
-    const int S = C + F;
     for (int64_t n = blockIdx.x * (int64_t)kWarpsPerBlock + wib; n < N; n += warps) {
-        float running = 0.f;                                                      // nerf_helpers.py:137, sequential order
-        for (int base = 0; base < C; base += kWarp) {
-            const int i = base + lane;
-            const float x = (i < C) ? w[n * C + i] : 0.f;
-            const float excl = chunk_exclusive_scan(x, running, lane);
-            if (i < C) {
-                cdf[i] = __fadd_rn(excl, x);
-                bounds[i + 1] = ts[n * C + i];                                  // nerf_helpers.py:149
-            }
+        for (int i = lane; i < C; i += kWarp) {
+            scratch[i] = w[n * C + i];                                           // raw weights -> cdf slots
+            scratch[C + 1 + i] = ts[n * C + i];                                  // coarse depths -> bounds[1 .. C] (nerf_helpers.py:149)
         }
-        if (lane == 0) { bounds[0] = near_; bounds[C + 1] = far_; }
         __syncwarp();
-        const float total = cdf[C - 1];
-        __syncwarp();
-        for (int i = lane; i < C; i += kWarp) cdf[i] = __fdiv_rn(cdf[i], total);   // nerf_helpers.py:138
-        __syncwarp();
-        const float e = __fdiv_rn(eps[n], Ff);                                      // nerf_helpers.py:139
-        float v[8];
-        bool plain = true;                                                           // no NaN among this lane's values
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const int j = 32 * jj + lane;                                             // element index in cat([fine, coarse])
-            float t = __int_as_float(0x7f800000);
-            if (j < F) {
-                const float q = __fadd_rn(__ldg(q_base + j), e);                     // nerf_helpers.py:142
-                int lo = 0, hi = C;                                                   // torch.searchsorted, right=False
-                while (lo < hi) {
-                    const int mid = lo + ((hi - lo) >> 1);
-                    if (!(cdf[mid] >= q)) lo = mid + 1; else hi = mid;
-                }
-                const float b0 = bounds[lo], b1 = bounds[lo + 1];
-                t = __fadd_rn(b0, __fmul_rn(__fsub_rn(b1, b0), u[n * F + j]));       // nerf_helpers.py:154
-                plain = plain && (t == t);
-            }
-            v[jj] = t;
-        }
-        bool run_sorted = F <= 128 && C <= 128;
-        for (int i = lane; i + 1 < C; i += kWarp) run_sorted = run_sorted && (bounds[i + 2] >= bounds[i + 1]);   // false on NaN too
-        if (__all_sync(kFull, run_sorted && plain)) {
-            // ---- 128-wide network over the fine depths (registers 0..3; entries >= F are +inf), then the rank merge
-#pragma unroll
-            for (int k = 2; k <= 128; k <<= 1) {
-#pragma unroll
-                for (int dist = k >> 1; dist >= 1; dist >>= 1) bitonic_stage(v, 4, k, dist, lane);
-            }
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) fsorted[32 * jj + lane] = v[jj];
-            __syncwarp();
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int el = 32 * jj + lane;
-                if (el < F) {
-                    const float t = v[jj];
-                    int lo = 0, hi = C;                                               // coarse depths below t
-                    while (lo < hi) {
-                        const int mid = lo + ((hi - lo) >> 1);
-                        if (bounds[mid + 1] < t) lo = mid + 1; else hi = mid;
-                    }
-                    merged[el + lo] = t;
-                }
-            }
-            for (int i = lane; i < C; i += kWarp) {
-                const float tc = bounds[i + 1];
-                int lo = 0, hi = F;                                                   // fine depths not above tc
-                while (lo < hi) {
-                    const int mid = lo + ((hi - lo) >> 1);
-                    if (fsorted[mid] <= tc) lo = mid + 1; else hi = mid;
-                }
-                merged[i + lo] = tc;
-            }
-            __syncwarp();
-            for (int el = lane; el < S; el += kWarp) ts_sorted[n * S + el] = merged[el];
-            __syncwarp();
-            continue;
-        }
-        // ---- general path: the coarse depths join the fine ones (nerf_model.py:117: fine first, then coarse), 256-wide network
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const int j = 32 * jj + lane;
-            if (j >= F && j < S) v[jj] = bounds[j - F + 1];
-        }
-#pragma unroll
-        for (int k = 2; k <= 256; k <<= 1) {
-#pragma unroll
-            for (int dist = k >> 1; dist >= 1; dist >>= 1) bitonic_stage(v, 8, k, dist, lane);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int el = 32 * j + lane;
-            if (el < S) ts_sorted[n * S + el] = v[j];
-        }
+        fine_sample_merge_ray<true>(scratch, C, F, near_, far_, eps[n], u + n * F, q_base, ts_sorted + n * (C + F), lane);
     }
 }
+
 
 // General path (A + B <= 1024): one warp per ray, enumeration sort in shared memory: rank(e) = #{j : v_j < v_e or (v_j == v_e and j < e)}.
 // Dynamic shared memory per warp: vals[S] then sorted[S].
@@ -642,6 +524,7 @@ merge_sort_kernel(const float* __restrict__ o, const float* __restrict__ d, cons
         __syncwarp();
     }
 }
+
 
 
 // ------------------------------------------------------------------------------ compositing backward
@@ -795,7 +678,7 @@ extern "C" int nerf_fine_sample_merge(const float* w, const float* ts, const flo
     NERF_REQUIRE(N >= 0 && C > 0 && F > 0 && C + F <= 256, "nerf_fine_sample_merge: bad size N=%lld C=%d F=%d (C + F <= 256)", (long long)N, C, F);
     if (N == 0) return 0;
     NERF_REQUIRE(w && ts && eps && u && q_base && ts_sorted, "nerf_fine_sample_merge: null pointer");
-    const size_t smem = (size_t)kWarpsPerBlock * (2 * C + 2 + 128 + 256) * sizeof(float);
+    const size_t smem = (size_t)kWarpsPerBlock * fine_sampler_floats(C) * sizeof(float);
     fine_sample_merge_kernel<<<grid_for(N, kWarpsPerBlock), kThreads, smem, (cudaStream_t)stream>>>(
         w, ts, eps, u, q_base, N, C, F, near_, far_, ts_sorted);
     return check_launch("nerf_fine_sample_merge");

@@ -23,8 +23,8 @@ _grid_cache = {}
 
 
 def _strata(near, far, C, dev):
-    """`torch.arange(near, far, step)` (nerf_helpers.py:50-51) evaluated on the CPU in fp32 - the way the parity oracle (the
-    reference run on CPU) evaluates it - and cached on the device.  Upstream passes `device=device`, i.e. a CUDA arange when a GPU is
+    """`torch.arange(near, far, step)` (nerf_helpers.py:50-51) evaluated on the CPU in fp32 - the way the reference evaluates it
+    when it runs on the CPU, which is where the parity vectors were recorded - and cached on the device.  Upstream passes `device=device`, i.e. a CUDA arange when a GPU is
     present; the two can differ by 1 ulp when `step` is not exactly representable (the default 2..6 / 64 gives step = 2^-4: exact)."""
     key = ("t", float(near), float(far), int(C), str(dev))
     if key not in _grid_cache:
