@@ -1,7 +1,8 @@
 // fine_sampler.cuh - K3 + K4 for ONE ray by one warp: inverse-CDF fine depths (nerf_helpers.py:106-156) merged with the coarse
-// depths into one sorted row (nerf_model.py:116-120).  Shared by the stand-alone launch (samplers.cu,
-// fine_sample_merge_kernel) and by the coarse network's fused kernel (mlp_tc3.cu), whose compositing warps call it for every
-// ray they have just composited - same code, same arithmetic, bit-identical depths.
+// depths into one sorted row (nerf_model.py:116-120); the body of fine_sample_merge_kernel (samplers.cu).  NETWORK = false is the
+// form that was tried INSIDE the coarse network's kernel (its compositing warps calling it for every ray they had just
+// composited: bit-identical, but the producer warps became the coarse kernel's bottleneck - 32.7 ms against 27.6 + 1.6 ms per
+// 640 000 rays, profiles/r02_notes.md - so the sampler stays its own launch).
 #pragma once
 #include "composite_scan.cuh"
 

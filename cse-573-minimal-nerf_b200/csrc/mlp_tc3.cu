@@ -33,7 +33,6 @@
 #include <type_traits>
 #include "mlp_tc3_common.cuh"
 #include "composite_scan.cuh"
-#include "fine_sampler.cuh"
 
 namespace nerf {
 
@@ -200,15 +199,6 @@ struct FusedComposite {
     const float* t_base;
     float step;
     float* ts_gen;
-    // K3 + K4 inside the kernel as well (coarse network, with u_c): right after a ray has been composited the same warp draws its
-    // fine depths from the weights it has just formed and merges them with the coarse ones (fine_sample_merge_ray, the routine of
-    // the stand-alone launch: bit-identical sorted depths) - ts_sorted [N, S + F]
-    const float* eps;
-    const float* u_f;
-    const float* q_base;
-    int F;
-    float near_f, far_f;
-    float* ts_sorted;
 };
 
 __device__ __forceinline__ float ld_coherent(const float* p) {      // depths written earlier by another warp of this CTA
@@ -239,7 +229,6 @@ __device__ __forceinline__ void composite_groups(const FusedComposite& fc, const
             const uint32_t grow0 = lt0 * t3::kTileM + (uint32_t)(j * S);                // CTA-local row of the ray's first sample
             float running = 0.f;       // sum_{j<i} -sigma_j delta_j, nerf_helpers.py:86-89
             float cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f, st_sq = 0.f, st_nz = 0.f;
-            float* fine_scratch = (float*)(smem + t3::kOffFine) + w * t3::kFineFloats;     // (fc.ts_sorted only)
             float t_n = ld_coherent(tp + lane);                                          // S is a multiple of 32
             for (int base = 0; base < S; base += kWarp) {
                 const int i = base + lane;
@@ -257,7 +246,6 @@ __device__ __forceinline__ void composite_groups(const FusedComposite& fc, const
                 const float trans = expf(excl);                                          // nerf_helpers.py:89
                 const float wgt = __fmul_rn(__fsub_rn(1.0f, expf(x)), trans);            // nerf_helpers.py:90
                 if (wp) wp[i] = wgt;
-                if (fc.ts_sorted) { fine_scratch[i] = wgt; fine_scratch[S + 1 + i] = t; }   // raw weights | coarse depths
                 cr = fmaf(wgt, v.y, cr); cg = fmaf(wgt, v.z, cg); cb = fmaf(wgt, v.w, cb);   // nerf_helpers.py:103
                 dsum = fmaf(wgt, t, dsum); asum += wgt;
                 st_sq = fmaf(s, s, st_sq); st_nz += (s != 0.f) ? 1.f : 0.f;
@@ -270,11 +258,6 @@ __device__ __forceinline__ void composite_groups(const FusedComposite& fc, const
                 if (fc.depth) fc.depth[n] = dsum;
                 if (fc.acc) fc.acc[n] = asum;
                 stat[0] += st_sq; stat[1] += st_nz;
-            }
-            if (fc.ts_sorted) {        // inverse-CDF fine depths + merge for this ray (nerf_model.py:114-120), while its weights are here
-                __syncwarp();
-                fine_sample_merge_ray<false>(fine_scratch, S, fc.F, fc.near_f, fc.far_f, __ldg(fc.eps + n), fc.u_f + n * fc.F, fc.q_base,
-                                             fc.ts_sorted + n * (S + fc.F), lane);
             }
         }
         __syncwarp();
@@ -708,12 +691,6 @@ int launch_mlp_tc3(const void* packed, const float* o, const float* d, const flo
         }
         fc.weights = comp->weights; fc.ray_rgb = comp->ray_rgb; fc.depth = comp->depth; fc.acc = comp->acc; fc.stats = comp->stats;
         fc.u_c = comp->u_c; fc.t_base = comp->t_base; fc.step = comp->step; fc.ts_gen = comp->ts_gen;
-        fc.eps = comp->eps; fc.u_f = comp->u_f; fc.q_base = comp->q_base; fc.F = comp->F; fc.near_f = comp->near_f; fc.far_f = comp->far_f;
-        fc.ts_sorted = comp->ts_sorted;
-        if (fc.ts_sorted && !(fc.u_c && fc.eps && fc.u_f && fc.q_base && S <= t3::kFineMaxC && fc.F >= 1 && fc.F <= 128)) {
-            set_error("nerf_mlp_composite_tc_strata: the fine sampler inside the kernel needs the stratified-depth form, S <= 64 and 1 <= F <= 128");
-            return NERF_E_ARG;
-        }
         fc.N = total / S;
         fc.num_groups = (fc.N + fc.group_rays - 1) / fc.group_rays;
         // at least two tiles per CTA where possible, so that both halves of a pair do useful work
@@ -824,7 +801,7 @@ extern "C" int nerf_mlp_composite_tc(const void* packed, const float* o, const f
     NERF_REQUIRE(nerf_mlp_composite_tc_supported(S),
                  "nerf_mlp_composite_tc: S = %d is not supported (needs S %% 32 == 0 and a ray group of at most 6 tiles); "
                  "use nerf_mlp_forward_tc + nerf_composite", S);
-    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0.f, nullptr};
+    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4, nullptr, nullptr, 0.f, nullptr};
     return launch_mlp_tc3(packed, o, d, ts, nullptr, N * S, S, sigma, rgb, act_out, mask_out, stream, nullptr, &comp);
 }
 
@@ -834,8 +811,7 @@ extern "C" int nerf_mlp_composite_tc(const void* packed, const float* o, const f
 extern "C" int nerf_mlp_composite_tc_strata(const void* packed, const float* o, const float* d, const float* u, const float* t_base,
                                             float step, int64_t N, int S, float* ts_out, float* sigma, float* rgb, void* act_out,
                                             void* mask_out, float* weights, float* ray_rgb, float* depth, float* acc, float* stats4,
-                                            const float* eps, const float* u_f, const float* q_base, int F, float near_f, float far_f,
-                                            float* ts_sorted, void* stream) {
+                                            void* stream) {
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_mlp_composite_tc_strata: bad size N=%lld S=%d", (long long)N, S);
     if (N == 0) return 0;
     NERF_REQUIRE(packed && o && d && u && t_base && ts_out && ray_rgb, "nerf_mlp_composite_tc_strata: null pointer");
@@ -845,6 +821,6 @@ extern "C" int nerf_mlp_composite_tc_strata(const void* packed, const float* o, 
     NERF_REQUIRE(((uintptr_t)packed & 127) == 0, "nerf_mlp_composite_tc_strata: packed buffer must be 128-byte aligned");
     NERF_REQUIRE(!act_out || ((uintptr_t)act_out & 15) == 0, "nerf_mlp_composite_tc_strata: act_out must be 16-byte aligned");
     NERF_REQUIRE(nerf_mlp_composite_tc_supported(S), "nerf_mlp_composite_tc_strata: S = %d is not supported", S);
-    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4, u, t_base, step, ts_out, eps, u_f, q_base, F, near_f, far_f, ts_sorted};
+    const CompositeOutputs comp{weights, ray_rgb, depth, acc, stats4, u, t_base, step, ts_out};
     return launch_mlp_tc3(packed, o, d, nullptr, nullptr, N * S, S, sigma, rgb, act_out, mask_out, stream, nullptr, &comp);
 }

@@ -32,12 +32,7 @@ constexpr uint32_t kBarFull = 0, kBarEmpty = 8, kBarDFull = 16, kBarDFree = 18, 
                    kNumBars = 50;
 constexpr uint32_t kOffTmemHolder = kOffBars + kNumBars * 8;
 constexpr uint32_t kOffDetail = kOffTmemHolder + 16;                                 // PROFILE builds: 96 x int64
-// coarse network with the fine sampler inside (mlp_tc3.cu): per producer warp, the scratch of fine_sample_merge_ray for C <= 64
-// (cdf [64] | bounds [66] | sorted fine depths [128]; the merged row is scattered straight to global: ~4 KB is all that is left)
-constexpr int kFineMaxC = 64;
-constexpr uint32_t kFineFloats = 2 * kFineMaxC + 2 + 128;
-constexpr uint32_t kOffFine = kOffDetail + 96 * 8;
-constexpr uint32_t kSmemBytes = kOffFine + kPEWarps * kFineFloats * 4 + 1024;
+constexpr uint32_t kSmemBytes = kOffDetail + 96 * 8 + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 // setmaxnreg moves registers inside the CTA's own pool (768 threads x 80 at launch): what the two small warpgroups give

@@ -18,8 +18,6 @@ constexpr float k2PiLo = -1.7484555e-7f;
 struct CompositeOutputs {
     float* weights; float* ray_rgb; float* depth; float* acc; float* stats;
     const float* u_c; const float* t_base; float step; float* ts_gen;      // non-null u_c: stratified depths formed in the kernel
-    // non-null ts_sorted (needs u_c, S <= 128, F <= 128): the fine sampler + merge runs in the kernel too
-    const float* eps; const float* u_f; const float* q_base; int F; float near_f; float far_f; float* ts_sorted;
 };
 
 struct StageRef { uint32_t offset, bytes; };

@@ -143,18 +143,14 @@ class NeRFModel(nn.Module):
         return self.uses_tensor_cores() and bool(nat.lib().nerf_mlp_composite_tc_supported(int(S)))
 
     @nat.device_guard
-    def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False, stats=None, out=None, strata=None,
-                    fine=None):
+    def render_rays(self, o_rays, d_rays, ts, want_weights=True, keep_samples=False, save=False, stats=None, out=None, strata=None):
         """Network + alpha compositing in ONE kernel (nerf_mlp_composite_tc): the per-sample sigma / rgb stay on the SM
         unless `keep_samples` (or `save`, the training form, which also stores activations + ReLU sign words).
         Returns the same dict as nerf_helpers.composite plus 'sigma', 'rgb_samples', 'saved' (None when not kept).
         `stats`: optional ZEROED [4] fp32 buffer for the density statistics (one is allocated otherwise); `out`: optional
         contiguous [N,3] fp32 tensor the ray colours are written into (e.g. a slice of the frame buffer).
         `strata` = (u [N,S], t_base [S], step) with ts=None: the stratified depths of generate_coarse_samples are formed inside
-        the kernel as well (returned as 'ts', bit-identical to nerf_coarse_sample).
-        `fine` = (eps [N,1], u_f [N,F,1], F, near, far) together with `strata` (S <= 64, F <= 128): the inverse-CDF fine depths and
-        their merge with the coarse ones (nerf_model.py:114-120) are formed inside the kernel too, by the warp that has just
-        composited the ray (returned as 'ts_sorted' [N, S+F, 1], bit-identical to nerf_helpers.fine_depths_sorted)."""
+        the kernel as well (returned as 'ts', bit-identical to nerf_coarse_sample)."""
         if strata is not None:
             u, t_base, step = strata
             u = nat.dev(u, "u")
@@ -182,30 +178,19 @@ class NeRFModel(nn.Module):
         if stats is None:
             stats = torch.zeros((4,), device=dv, dtype=torch.float32)
         packed = self.packed_weights()
-        ts_sorted = eps = u_f = q_base = None
-        F_, near_f, far_f = 0, 0.0, 0.0
-        if fine is not None:
-            if strata is None:
-                raise ValueError("render_rays: `fine` needs `strata` (the kernel's own, sorted, stratified depths)")
-            eps, u_f, F_, near_f, far_f = fine
-            eps, u_f = nat.dev(eps, "eps"), nat.dev(u_f, "u_f")
-            q_base = nerf_helpers._queries(F_, dv)
-            ts_sorted = torch.empty((N, S + F_, 1), device=dv, dtype=torch.float32)
         with nat.timed_kernel("mlp_tc_kernel(train)" if save else "mlp_tc_kernel", N * S):
             if strata is not None:
                 nat.check(nat.lib().nerf_mlp_composite_tc_strata(nat.ptr(packed), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(u), nat.ptr(t_base),
                                                                  float(step), N, S, nat.ptr(ts), nat.ptr(sigma), nat.ptr(rgb), nat.ptr(acts),
                                                                  nat.ptr(masks), nat.ptr(w), nat.ptr(col), nat.ptr(depth), nat.ptr(acc),
-                                                                 nat.ptr(stats), nat.ptr(eps), nat.ptr(u_f), nat.ptr(q_base), int(F_),
-                                                                 float(near_f), float(far_f), nat.ptr(ts_sorted), nat.stream()),
-                          "nerf_mlp_composite_tc_strata")
+                                                                 nat.ptr(stats), nat.stream()), "nerf_mlp_composite_tc_strata")
             else:
                 nat.check(nat.lib().nerf_mlp_composite_tc(nat.ptr(packed), nat.ptr(o_rays), nat.ptr(d_rays), nat.ptr(ts), N, S,
                                                           nat.ptr(sigma), nat.ptr(rgb), nat.ptr(acts), nat.ptr(masks),
                                                           nat.ptr(w), nat.ptr(col), nat.ptr(depth), nat.ptr(acc), nat.ptr(stats),
                                                           nat.stream()), "nerf_mlp_composite_tc")
         return {"weights": w, "rgb": col, "depth": depth, "acc": acc, "stats": stats[:2], "norm": stats[2],
-                "sigma": sigma, "rgb_samples": rgb, "saved": (acts, masks) if save else None, "ts": ts, "ts_sorted": ts_sorted}
+                "sigma": sigma, "rgb_samples": rgb, "saved": (acts, masks) if save else None, "ts": ts}
 
 
 class NeRFNetwork(LightningModule):

@@ -102,7 +102,6 @@ def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray, accumulate_into_grad=
 
 
 FUSE_STRATA = True          # K1 (stratified depths) inside the coarse network's kernel as well
-FUSE_FINE_SAMPLER = True    # ... and K3 + K4 (inverse-CDF fine depths + merge): the coarse half of the forward is ONE launch (C <= 64, F <= 128)
 FUSE_COMPOSITE = True       # network + compositing in one kernel where the sample counts allow it (64 / 128 / 192 / 256)
 
 
@@ -138,11 +137,8 @@ def forward_pass(net, o, d, rand, save, keep_samples=False, fine_out=None):
         stats8 = _zeroed_stats8(dv)                              # density statistics of both networks
         if FUSE_STRATA:                                          # ... and the stratified depths are formed in that kernel too
             t_base, step = nerf_helpers._strata(net.near, net.far, C, dv)
-            # near / far are NOT forwarded to the fine sampler upstream (nerf_model.py:114-115): its 2.0 / 6.0 defaults apply
-            in_kernel_sampler = FUSE_FINE_SAMPLER and C <= 64 and Fn <= 128
             c = net.coarse_network.render_rays(o, d, None, want_weights=True, keep_samples=keep_samples, save=save, stats=stats8[:4],
-                                               strata=(nat.dev(u_c, "u_c").reshape(N, C), t_base, step),
-                                               fine=(eps, u_f, Fn, 2.0, 6.0) if in_kernel_sampler else None)
+                                               strata=(nat.dev(u_c, "u_c").reshape(N, C), t_base, step))
             c_ts = c["ts"]
         else:
             c_ts = net._coarse_ts(o, d, u_c)
@@ -157,9 +153,7 @@ def forward_pass(net, o, d, rand, save, keep_samples=False, fine_out=None):
             c_acts = None
         c = nerf_helpers.composite(c_sigma, c_rgb, c_ts)
     # near / far are NOT forwarded upstream (nerf_model.py:114-115): the sampler's 2.0 / 6.0 defaults apply
-    if fused and c.get("ts_sorted") is not None:
-        ts = c["ts_sorted"]                                     # formed inside the coarse kernel
-    elif C + Fn <= 256:       # fine depths + merge sort in one launch
+    if C + Fn <= 256:       # fine depths + merge sort in one launch
         ts = nerf_helpers.fine_depths_sorted(c["weights"], c_ts, Fn, rand=(eps, u_f))
     else:
         _, f_ts = nerf_helpers.inverse_transform_sampling(o, d, c["weights"], c_ts, Fn, rand=(eps, u_f))

@@ -184,14 +184,8 @@ NERF_API int nerf_mlp_composite_tc(const void* packed, const float* o, const flo
  * too.  u [N,S] uniforms, t_base [S] = the reference's torch.arange(near, far, step) on the device, ts_out [N,S] receives the depths
  * t = t_base[i] + u * step (bit-identical to nerf_coarse_sample); everything else as nerf_mlp_composite_tc. */
 NERF_API int nerf_mlp_composite_tc_strata(const void* packed, const float* o, const float* d, const float* u, const float* t_base, float step,
-                                          int64_t N, int S, float* ts_out, float* sigma, float* rgb, void* act_out, void* mask_out,
-                                          float* weights, float* ray_rgb, float* depth, float* acc, float* stats4,
-                                          const float* eps, const float* u_f, const float* q_base, int F, float near_f, float far_f,
-                                          float* ts_sorted, void* stream);
-/* ts_sorted != NULL (needs S <= 64, 1 <= F <= 128): K3 + K4 run inside the kernel too - the warp that has just composited a coarse
- * ray draws its F fine depths from the weights it formed (eps [N], u_f [N,F], q_base [F], near_f / far_f as nerf_fine_sample_merge)
- * and merges them with the coarse depths: ts_sorted [N, S + F], bit-identical to nerf_fine_sample_merge on the kernel's own weights /
- * depths.  The whole coarse half of NeRFNetwork.forward (nerf_model.py:103-120) is then ONE launch.  NULL: eps .. far_f are ignored. */
+                                 int64_t N, int S, float* ts_out, float* sigma, float* rgb, void* act_out, void* mask_out,
+                                 float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream);
 
 /* Both weight images (nerf_pack_weights + nerf_pack_weights_t) of both networks in ONE launch - what a training step needs
  * after the optimiser has changed the parameters.  params40_host: the 40 tensors of NeRFNetwork's state_dict order (coarse

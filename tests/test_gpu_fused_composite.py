@@ -199,54 +199,6 @@ def test_fine_depths_sorted_matches_sampler_plus_merge(N, C, F):
         assert bits_equal(got, ref)
 
 
-@pytest.mark.parametrize("N,kind,F", [(4096, "dense", 128), (301, "dense", 128), (2, "dense", 128), (1, "dense", 128), (515, "init", 128),
-                                      (130, "dense", 37), (64, "dense", 1)])
-def test_fine_sampler_inside_the_coarse_kernel_is_bit_identical(N, kind, F):
-    """nerf_mlp_composite_tc_strata with ts_sorted: the warp that has composited a coarse ray also draws its fine depths and merges
-    them (fine_sample_merge_ray, the routine of the stand-alone launch).  Against nerf_fine_sample_merge on the kernel's own weights and
-    depths: bit-identical sorted rows - including rays whose weights are all zero (NaN cdf; the random-init network) - and every other
-    output of the kernel unchanged."""
-    import nerf_helpers as h
-    net = make_net(3 if kind == "init" else 4, kind)
-    m = net.coarse_network
-    C = 64
-    o, d, _ = rays(N, 32, 5 + N)
-    g = torch.Generator(device=DEV).manual_seed(N + F)
-    u_c = torch.rand(N, C, device=DEV, generator=g)
-    eps, u_f = torch.rand(N, 1, device=DEV, generator=g), torch.rand(N, F, 1, device=DEV, generator=g)
-    u_f[::3, ::5] = 0.0
-    t_base, step = h._strata(2.0, 6.0, C, torch.device(DEV, torch.cuda.current_device()))
-    plain = m.render_rays(o, d, None, want_weights=True, strata=(u_c, t_base, step))
-    fused = m.render_rays(o, d, None, want_weights=True, strata=(u_c, t_base, step), fine=(eps, u_f, F, 2.0, 6.0))
-    ref = h.fine_depths_sorted(plain["weights"], plain["ts"], F, rand=(eps, u_f))
-    torch.cuda.synchronize()
-    for key in ("weights", "rgb", "depth", "acc", "ts"):
-        assert bits_equal(fused[key], plain[key]), key
-    assert fused["ts_sorted"].shape == (N, C + F, 1) and bits_equal(fused["ts_sorted"], ref)
-    if kind == "init":
-        assert float(plain["weights"].abs().max()) == 0.0          # every ray dead: the NaN-cdf rows
-
-
-def test_network_forward_identical_with_in_kernel_sampler(golden):
-    """NeRFNetwork.forward with the coarse half as ONE launch (FUSE_FINE_SAMPLER) against the three-launch path: bit-identical
-    colours, depths and - in training - saved tensors' consumers (the gradients up to the atomics' order)."""
-    import training
-    g = golden["network"]
-    o, d = T(g["o"], DEV), T(g["d"], DEV)
-    outs = []
-    try:
-        for flag in (True, False):
-            training.FUSE_FINE_SAMPLER = flag
-            net = make_net(4, "dense")
-            with torch.no_grad():
-                out = net.forward(o, d, rand=rand_triple(540, 64, device=DEV))
-            outs.append((out["fine_rgb_rays"].clone(), out["coarse_rgb_rays"].clone(), net.last["ts"].clone(), net.last["depth"].clone()))
-    finally:
-        training.FUSE_FINE_SAMPLER = True
-    for a, b in zip(*outs):
-        assert bits_equal(a, b)
-
-
 def test_full_frame_is_independent_of_chunking_and_sharding():
     """BASELINE configs[1] size (800 x 800 = 640 000 rays, 64 + 128 samples): with the uniforms fixed per ray, the image must not
     depend on how the rays are cut into chunks (4096 as the reference, an odd 4095, 12 345, all 640 000 at once) or into per-GPU slabs - every ray is
