@@ -63,7 +63,7 @@ def test_forward_bf16_dense(golden):
     torch.cuda.synchronize()
     for key in ("coarse_rgb_rays", "fine_rgb_rays"):
         diff = (out[key].cpu() - T(g[f"{key}_dense"])).abs()
-        psnr = 10 * np.log10(1.0 / max(float((diff ** 2).mean()), 1e-20))
+        psnr = 10 * np.log10(1.0 / max(float((diff.detach() ** 2).mean()), 1e-20))
         print(f"{key}: max {diff.max():.3e} mean {diff.mean():.3e} PSNR-vs-reference {psnr:.1f} dB")
         assert diff.mean() < 5e-4 and diff.max() < 5e-3 and psnr > 60.0          # the stated bf16 contract
     assert out["fine_rgb_rays"].shape == (64, 3)
