@@ -144,3 +144,25 @@ def test_non_default_encodings_are_refused_up_front(scene, tmp_path):
     import train_nerf
     with pytest.raises(RuntimeError, match="differentiable path exists"):
         train_nerf.main(["-n", "odd", "--gpu", "-s", "2", "-rd", str(tmp_path), "-r", "64", "-p", "6", "-d", "2", "full", "-b", str(scene)])
+
+
+def test_resume_continues_the_step_count_in_the_replayed_graph(scene, tmp_path):
+    """train_nerf.py -l CKPT with enough steps left for the CUDA-graph path: the optimiser's step count (host and device copies -
+    Adam's bias corrections are evaluated on the device in the replayed step) continues from the checkpoint, the per-epoch LR decay
+    of configure_optimizers reaches the captured kernel, and the resumed run keeps training."""
+    import train_nerf
+    first = train_nerf.main(["-n", "a", "--gpu", "-s", "9", "-rd", str(tmp_path), "-r", "512", "full", "-b", str(scene), "-cr", "0"])
+    assert first.global_step == 9 and first.optimizer._step == 9 and int(first.optimizer.dev_step) == 9
+    ckpt = first.last_checkpoint
+    blob = torch.load(str(ckpt), map_location="cpu", weights_only=False)
+    assert blob["global_step"] == 9 and float(blob["optimizer_states"][0]["state"][0]["step"]) == 9.0
+    run = train_nerf.main(["-n", "b", "--gpu", "-s", "30", "-rd", str(tmp_path), "-r", "512", "-l", str(ckpt), "full", "-b", str(scene), "-cr", "0"])
+    opt = run.optimizer
+    assert run.global_step == 30 and opt._step == 30 and int(opt.dev_step) == 30
+    gamma = (5e-5 / 5e-4) ** (1 / 1200)
+    epochs_done = run.current_epoch                                   # 3 images per epoch: 10 epochs for 30 steps
+    assert epochs_done == 10
+    assert abs(opt.param_groups[0]["lr"] - 5e-4 * gamma ** epochs_done) < 1e-12
+    assert abs(float(opt.dev_state[0]) - 5e-4 * gamma ** (epochs_done - 1)) < 1e-9     # the lr the last replayed step used
+    moved = (opt.flat_params.cpu() - torch.cat([v.flatten() for v in blob["state_dict"].values()])[: opt.flat_params.numel()].float()).abs().max()
+    assert float(moved) > 1e-4
