@@ -4,7 +4,6 @@ There is no CPU implementation behind this module: loading fails loudly when the
 built, and every wrapper rejects non-CUDA tensors.
 """
 import ctypes
-import os
 import subprocess
 from pathlib import Path
 

@@ -13,7 +13,6 @@ the Adam kernel (`FlatAdam.grad_scale`), so every rank takes the same step from 
 on rank 0 only, with the frame rendered locally (no collective depends on per-rank control flow).
 """
 import json
-import os
 import time
 from pathlib import Path
 
