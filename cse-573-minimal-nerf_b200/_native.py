@@ -50,6 +50,8 @@ _PROTOTYPES = {
     "nerf_mlp_composite_tc_supported": (_int, [_int]),
     "nerf_mlp_composite_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerf_mlp_composite_tc_strata": (_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nerf_render_workspace_bytes": (ctypes.c_size_t, [_i64, _int, _int]),
+    "nerf_render_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _int, _int, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerf_adam_step_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "nerf_adam_step": (_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i64, _f32, _vp]),
 }

@@ -124,6 +124,49 @@ def _zeroed_stats8(dv):
     return out
 
 
+RENDER_ONE_CALL = True      # inference passes go through nerf_render_forward (the three launches queued by ONE call of the C ABI)
+
+
+def _render_one_call(net, o, d, rand, fine_out):
+    """NeRFNetwork.forward for rendering as one call of the C ABI (csrc/render.cu): returns what forward_pass returns; the
+    intermediates (coarse depths / weights, merged depths) are views of the call's workspace."""
+    N, C, Fn = o.shape[0], net.coarse_samples, net.fine_samples
+    dv = o.device
+    u_c, eps, u_f = (nat.dev(t, "rand") for t in rand)
+    lib = nat.lib()
+    ws = torch.empty((lib.nerf_render_workspace_bytes(N, C, Fn),), device=dv, dtype=torch.uint8)
+    al = lambda b: (b + 255) & ~255
+    off, views = 0, []
+    for shape in ((N, C, 1), (N, C, 1), (N, C + Fn, 1), (N,), (N,)):
+        n = 4
+        for k in shape:
+            n *= k
+        views.append(ws[off:off + n].view(torch.float32).view(shape))
+        off += al(n)
+    c_ts, c_w, ts, c_depth, c_acc = views
+    c_rgb = torch.empty((N, 3), device=dv, dtype=F32)
+    f_rgb = fine_out if fine_out is not None else torch.empty((N, 3), device=dv, dtype=F32)
+    if f_rgb.shape != (N, 3) or f_rgb.dtype != F32 or not f_rgb.is_contiguous() or f_rgb.device != dv:
+        raise ValueError("forward: `fine_out` must be a contiguous [N,3] fp32 tensor on the rays' device")
+    depth = torch.empty((N,), device=dv, dtype=F32)
+    acc = torch.empty((N,), device=dv, dtype=F32)
+    stats8 = _zeroed_stats8(dv)
+    t_base, step = nerf_helpers._strata(net.near, net.far, C, dv)
+    q_base = nerf_helpers._queries(Fn, dv)
+    if True:
+        # near / far are NOT forwarded to the fine sampler upstream (nerf_model.py:114-115): its 2.0 / 6.0 defaults apply
+        nat.check(lib.nerf_render_forward(nat.ptr(net.coarse_network.packed_weights()), nat.ptr(net.fine_network.packed_weights()),
+                                          nat.ptr(o), nat.ptr(d), nat.ptr(u_c), nat.ptr(t_base), float(step), nat.ptr(eps), nat.ptr(u_f),
+                                          nat.ptr(q_base), N, C, Fn, 2.0, 6.0, nat.ptr(c_rgb), nat.ptr(f_rgb), nat.ptr(depth), nat.ptr(acc),
+                                          nat.ptr(stats8), nat.ptr(ws), nat.stream()), "nerf_render_forward")
+        nat.launches += 2                      # three kernels of ours behind the one call
+    c = {"weights": c_w, "rgb": c_rgb, "depth": c_depth, "acc": c_acc, "stats": stats8[:2], "norm": stats8[2], "ts": c_ts}
+    f = {"weights": None, "rgb": f_rgb, "depth": depth, "acc": acc, "stats": stats8[4:6], "norm": stats8[6]}
+    aux = {"c": c, "f": f, "c_ts": c_ts, "ts": ts, "c_sigma": None, "c_rgb": None, "f_sigma": None, "f_rgb": None,
+           "c_acts": None, "f_acts": None}
+    return c_rgb, f_rgb, aux
+
+
 def forward_pass(net, o, d, rand, save, keep_samples=False, fine_out=None):
     """Shared by inference and training: returns (coarse_rgb, fine_rgb, aux dict).  With the fused kernel the per-sample
     sigma / rgb of an inference pass are only materialised when `keep_samples` (aux['c_sigma'] ... are None otherwise)."""
@@ -133,6 +176,9 @@ def forward_pass(net, o, d, rand, save, keep_samples=False, fine_out=None):
         rand = (torch.rand((N, C), device=dv), torch.rand((N, 1), device=dv), torch.rand((N, Fn, 1), device=dv))
     u_c, eps, u_f = rand
     fused = FUSE_COMPOSITE and net.coarse_network.can_composite(C) and net.fine_network.can_composite(C + Fn)
+    if (fused and FUSE_STRATA and RENDER_ONE_CALL and not save and not keep_samples and C + Fn <= 256
+            and nat.kernel_events is None):        # (per-kernel event timing, bench.py's roofline, needs the launches one by one)
+        return _render_one_call(net, o, d, rand, fine_out)
     if fused:       # network + compositing in one kernel; render keeps no per-sample outputs at all
         stats8 = _zeroed_stats8(dv)                              # density statistics of both networks
         if FUSE_STRATA:                                          # ... and the stratified depths are formed in that kernel too

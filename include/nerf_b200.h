@@ -187,6 +187,19 @@ NERF_API int nerf_mlp_composite_tc_strata(const void* packed, const float* o, co
                                  int64_t N, int S, float* ts_out, float* sigma, float* rgb, void* act_out, void* mask_out,
                                  float* weights, float* ray_rgb, float* depth, float* acc, float* stats4, void* stream);
 
+/* ---- H9 in one call: NeRFNetwork.forward (nerf_model.py:89-132) for rendering - coarse kernel, fine sampler + merge, fine kernel
+ * queued back to back on `stream`.  u_c [N,C], eps [N], u_f [N,F]: the three uniform draws of the reference (nerf_helpers.py:52,139,154);
+ * t_base [C] / step: the strata (as nerf_coarse_sample), q_base [F] the query grid (as nerf_fine_sample); near_f / far_f: the fine
+ * sampler's bounds (upstream never forwards them: 2.0 / 6.0).  coarse_rgb, fine_rgb [N,3]; depth, acc [N] (fine network, nullable);
+ * stats8 (nullable, zeroed by the caller): the density statistics of the coarse [0..4) and fine [4..8) network as nerf_composite's
+ * stats.  workspace: nerf_render_workspace_bytes(N, C, F) bytes, 256-byte aligned, contents undefined afterwards.  C and C + F must
+ * be shapes nerf_mlp_composite_tc supports, C + F <= 256.  Same results as the three calls it makes. */
+NERF_API size_t nerf_render_workspace_bytes(int64_t N, int C, int F);
+NERF_API int nerf_render_forward(const void* packed_coarse, const void* packed_fine, const float* o, const float* d, const float* u_c,
+                                 const float* t_base, float step, const float* eps, const float* u_f, const float* q_base, int64_t N,
+                                 int C, int F, float near_f, float far_f, float* coarse_rgb, float* fine_rgb, float* depth, float* acc,
+                                 float* stats8, void* workspace, void* stream);
+
 /* Both weight images (nerf_pack_weights + nerf_pack_weights_t) of both networks in ONE launch - what a training step needs
  * after the optimiser has changed the parameters.  params40_host: the 40 tensors of NeRFNetwork's state_dict order (coarse
  * network's 20, then the fine network's 20). */

@@ -199,6 +199,31 @@ def test_fine_depths_sorted_matches_sampler_plus_merge(N, C, F):
         assert bits_equal(got, ref)
 
 
+@pytest.mark.parametrize("N", [1, 2, 301, 4096, 20000])
+def test_render_forward_one_call_matches_three_calls(N):
+    """nerf_render_forward (coarse kernel, sampler, fine kernel queued by ONE call of the C ABI, intermediates in a workspace)
+    against the same three launches issued by the Python host: every output bit-identical, statistics included."""
+    import training
+    net = make_net(5, "dense")
+    o, d, _ = rays(N, 32, 9 + N)
+    rand = rand_triple(700 + N, N, device=DEV)
+    outs = []
+    try:
+        for flag in (True, False):
+            training.RENDER_ONE_CALL = flag
+            with torch.no_grad():
+                out = net.forward(o, d, rand=rand)
+            torch.cuda.synchronize()
+            outs.append([out["fine_rgb_rays"].clone(), out["coarse_rgb_rays"].clone(), net.last["ts"].clone(), net.last["coarse_ts"].clone(),
+                         net.last["coarse_weights"].clone(), net.last["depth"].clone(), net.last["acc"].clone(),
+                         torch.stack([net.logged[k].clone() for k in ("coarse_density_non_zeros", "fine_density_non_zeros")])])
+    finally:
+        training.RENDER_ONE_CALL = True
+    for a, b in zip(outs[0][:-1], outs[1][:-1]):
+        assert bits_equal(a, b)
+    torch.testing.assert_close(outs[0][-1], outs[1][-1])
+
+
 def test_full_frame_is_independent_of_chunking_and_sharding():
     """BASELINE configs[1] size (800 x 800 = 640 000 rays, 64 + 128 samples): with the uniforms fixed per ray, the image must not
     depend on how the rays are cut into chunks (4096 as the reference, an odd 4095, 12 345, all 640 000 at once) or into per-GPU slabs - every ray is
