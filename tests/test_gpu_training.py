@@ -304,6 +304,80 @@ def test_flat_adam_matches_torch_adam():
         torch.testing.assert_close(pa.detach(), pb.detach(), rtol=5e-6, atol=1e-7, msg=lambda m: f"{name} after resume: {m}")
 
 
+def test_graph_safe_adam_matches_the_host_scalar_form():
+    """nerf_adam_step_dev (lr / betas / eps / grad_scale / step count in device memory, bias corrections evaluated on the device:
+    what the replayed CUDA graph runs) against nerf_adam_step (host scalars) and torch.optim.Adam: 30 steps with a decaying
+    learning rate and grad_scale = 1/4 (data parallel), parameters equal to 2e-6 relative."""
+    import copy
+    import optim
+    torch.manual_seed(5)
+    net_a = make_net(4, "dense")
+    net_b, net_c = copy.deepcopy(net_a), copy.deepcopy(net_a)
+    opt_a = optim.FlatAdam(net_a.parameters(), lr=5e-4)
+    opt_b = optim.FlatAdam(net_b.parameters(), lr=5e-4)
+    opt_c = torch.optim.Adam(net_c.parameters(), lr=5e-4)
+    opt_a.graph_safe = True
+    opt_a.grad_scale = opt_b.grad_scale = 0.25
+    opt_a.sync_device_state(); opt_a.set_device_step()
+    gen = torch.Generator(device=DEV).manual_seed(12)
+    for step in range(30):
+        lr = 5e-4 * 0.93 ** step
+        for o_ in (opt_a, opt_b, opt_c):
+            o_.param_groups[0]["lr"] = lr
+        for pa, pb, pc in zip(net_a.parameters(), net_b.parameters(), net_c.parameters()):
+            g = torch.randn(pa.shape, device=DEV, generator=gen) * (10.0 ** float(torch.randint(-6, 1, (1,)).item()))
+            pa.grad.copy_(g); pb.grad.copy_(g); pc.grad = g * 0.25
+        opt_a.step(); opt_b.step(); opt_c.step()
+    assert opt_a._step == 30 and int(opt_a.dev_step) == 30
+    for (name, pa), pb, pc in zip(net_a.named_parameters(), net_b.parameters(), net_c.parameters()):
+        torch.testing.assert_close(pa.detach(), pb.detach(), rtol=2e-6, atol=1e-7, msg=lambda m: f"{name} (device vs host scalars): {m}")
+        torch.testing.assert_close(pa.detach(), pc.detach(), rtol=5e-6, atol=1e-7, msg=lambda m: f"{name} (vs torch.optim.Adam): {m}")
+
+
+def test_batch_rays_matches_the_dataset_item_path(tmp_path):
+    """nerf_batch_rays (image index read from DEVICE memory; the batch producer inside the replayed step) against the per-item path
+    of SyntheticDataset.__getitem__ (nerf_raygen for the pixel list + colour gather): rays bit-identical, colours = fl32(u8 / 255)
+    with the division in double precision as numpy's `imread(...) / 255` upstream (dataloader.py:148)."""
+    import dataloader
+    synthetic.write_blender_scene(tmp_path, n_train=3, n_val=1, n_test=1)
+    ds = dataloader.SyntheticDataset(tmp_path, "train", 777, cropping=False)
+    images, poses = ds.stacked()
+    assert images.shape == (3, 800, 800, 3) and images.dtype == torch.uint8 and poses.shape == (3, 4, 4)
+    g = torch.Generator(device=DEV).manual_seed(8)
+    xs = torch.randint(0, 800, (777,), device=DEV, generator=g)
+    ys = torch.randint(0, 800, (777,), device=DEV, generator=g)
+    idx = torch.zeros((), device=DEV, dtype=torch.int64)
+    for k in (2, 0, 1):
+        idx.fill_(k)
+        o, d, rgb = dataloader.batch_rays(poses, idx, images, ds.focal, xs, ys)
+        o_ref, d_ref = dataloader.get_rays_at(800, 800, ds.focal, torch.tensor(ds.frames[k]["transform_matrix"], dtype=torch.float32), xs, ys)
+        assert torch.equal(o, o_ref) and torch.equal(d, d_ref)
+        want = torch.from_numpy((ds.image_u8(k)[ys, xs].cpu().numpy().astype(np.float64) / 255).astype(np.float32))
+        assert torch.equal(rgb.cpu(), want)
+
+
+def test_gradients_are_linear_in_the_upstream_gradient():
+    """Full batch size (4096 rays, both sample counts): doubling dL/d(ray colour) doubles every parameter gradient - the compositing
+    backward, the dgrad chain (bf16 dz: a factor 2 is exact) and wgrad are linear for fixed ReLU masks; what is left is the order of
+    the fp32 atomics (1e-6)."""
+    import training
+    torch.manual_seed(6)
+    net = make_net(0, "init")
+    N = 4096
+    o = torch.randn(N, 3, device=DEV) * 0.2 + torch.tensor([0.0, 0.0, 4.0], device=DEV)
+    d = F.normalize(-o + 0.4 * torch.randn(N, 3, device=DEV), dim=1)
+    for model, S in ((net.coarse_network, 64), (net.fine_network, 192)):
+        ts = (2.0 + 4.0 * torch.sort(torch.rand(N, S, 1, device=DEV), dim=1).values).contiguous()
+        sigma, rgb, acts = training.mlp_forward_train(model, o, d, ts)
+        g_ray = torch.randn(N, 3, device=DEV) / N
+        g1 = training.mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray)
+        g2 = training.mlp_backward(model, o, d, ts, sigma, rgb, acts, 2.0 * g_ray)
+        torch.cuda.synchronize()
+        for name, a, b in zip([n for n, _ in model.named_parameters()], g1, g2):
+            rel = ((b.double() - 2.0 * a.double()).norm() / (2.0 * a.double().norm()).clamp(min=1e-30)).item()
+            assert rel < 1e-5, f"{name} (S = {S}): relative deviation from linearity {rel:.2e}"
+
+
 def test_repack_all_matches_individual_packs():
     """nerf_pack_weights_all (the optimiser's post-step hook: four images, one launch) writes exactly what the per-image packers
     write, and the cached images are picked up by the next forward / backward."""
