@@ -484,21 +484,23 @@ def main():
         return t0.elapsed_time(t1), wall * 1e3
 
     def e2e_run(sharded):
+        """(mean, median, per-step list) of max(device time, wall time) per step, each the max over ranks."""
         e2e_step(0, sharded)
         e2e = [e2e_step(k, sharded) for k in range(args.steps)]
-        t = torch.tensor([float(np.mean([max(a, b) for a, b in e2e]))], device=dev, dtype=torch.float64)
+        t = torch.tensor([max(a, b) for a, b in e2e], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-    e_ms = e2e_run(False)
+        per_step = [float(x) for x in t.tolist()]
+        return float(np.mean(per_step)), float(np.median(per_step)), per_step
+    e_ms, e_med, e_steps = e2e_run(False)
     e2e_value = nrays * world / (e_ms * 1e-3)
     strong = None
     if world > 1:
-        s_ms = e2e_run(True)
+        s_ms, s_med, s_steps = e2e_run(True)
         strong = {"what": f"ONE {H}x{W} frame, rays sharded over {world} GPUs through nerf_helpers.view_reconstruction (host rays in, "
                           "uint8 all-gather, host image out; BASELINE.json configs[4] per frame)",
                   "ms_per_frame": s_ms, "rays_per_s": nrays / (s_ms * 1e-3), "speedup_vs_one_rank_e2e": e_ms / s_ms, "n_gpus": world,
-                  "scaling": "strong"}
+                  "ms_per_frame_median": s_med, "ms_steps": s_steps, "scaling": "strong"}
 
     train = None if args.no_train else bench_train(args, rank, world, dev)
 
@@ -508,7 +510,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(host_o.numel() * 4 * 2),
-                    "d2h_bytes_per_step": int(H * W * 3), "ms_per_step": e_ms,
+                    "d2h_bytes_per_step": int(H * W * 3), "ms_per_step": e_ms, "ms_per_step_median": e_med, "ms_steps": e_steps,
                     "call": "nerf_helpers.view_reconstruction(model, o.to(device), d.to(device), N=4096) -> host uint8 image"},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks.summary(), "train": train,
         }
