@@ -64,7 +64,8 @@ __device__ __forceinline__ void composite_backward_ray(const float* __restrict__
     const float g0 = g_ray[n * 3], g1 = g_ray[n * 3 + 1], g2 = g_ray[n * 3 + 2];
     const float* sg = sigma + n * S;
     const float* tp = ts + n * S;
-    // pass 0 (forward): running sum of -sigma*delta at every chunk start, in the forward kernel's order
+    // pass 0 (forward): running sum of -sigma*delta at every chunk start, with the fused forward's own 5-step shuffle scan (the
+    // transmittances are then the ones the forward composited with; the sequential 32-step form cost 6x the instructions)
     float chunk_start = 0.f, running = 0.f;
     for (int c = 0; c < chunks; ++c) {
         if (lane == c) chunk_start = running;
@@ -76,7 +77,7 @@ __device__ __forceinline__ void composite_backward_ray(const float* __restrict__
         if (lane == 31 && i + 1 < S) tn = tp[i + 1];
         const float dl = (i == S - 1) ? 1e10f : __fsub_rn(tn, t);
         const float x = in ? __fmul_rn(__fmul_rn(-1.0f, s), dl) : 0.f;
-        (void)chunk_exclusive_scan(x, running, lane);
+        (void)chunk_exclusive_scan_tree(x, running, lane);
     }
     // pass 1 (backward over chunks): suffix sums of q_j = w_j (c_j . g) taken directly, so that the last sample,
     // whose interval is 1e10 wide, sees an exactly-zero suffix (total - prefix would leave a rounding residue)
@@ -91,7 +92,7 @@ __device__ __forceinline__ void composite_backward_ray(const float* __restrict__
         if (lane == 31 && i + 1 < S) tn = tp[i + 1];
         const float dl = (i == S - 1) ? 1e10f : __fsub_rn(tn, t);
         const float x = in ? __fmul_rn(__fmul_rn(-1.0f, s), dl) : 0.f;
-        const float excl = chunk_exclusive_scan(x, run, lane);
+        const float excl = chunk_exclusive_scan_tree(x, run, lane);
         const float trans = expf(excl), e = expf(x);
         const float w = in ? __fmul_rn(__fsub_rn(1.0f, e), trans) : 0.f;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
