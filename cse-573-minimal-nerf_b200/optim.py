@@ -155,3 +155,5 @@ class FlatAdam(torch.optim.Optimizer):
                 self._step = int(float(st.get("step", self._step)))
             off += k
         self._bind_state()
+        self.set_device_step()                     # graph-safe form: the device copies follow the loaded state
+        self._dev_key = None
