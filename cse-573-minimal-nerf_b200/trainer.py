@@ -142,7 +142,9 @@ class Trainer:
                     "state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}, "callbacks": {},
                     "optimizer_states": [optimizer.state_dict()],
                     "lr_schedulers": [scheduler.state_dict()] if scheduler is not None else []}, str(path))
-        self.last_checkpoint = path
+        previous, self.last_checkpoint = self.last_checkpoint, path
+        if previous is not None and previous != path and Path(previous).exists():
+            Path(previous).unlink()            # Lightning's default ModelCheckpoint keeps the latest file only (save_top_k = 1)
         return path
 
     def fit(self, model, datamodule=None, train_dataloaders=None, val_dataloaders=None):
