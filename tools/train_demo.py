@@ -15,8 +15,12 @@ ap.add_argument("--crop-epochs", type=int, default=20)
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", "0"))
 work = Path(tempfile.gettempdir()) / "nerf_b200_train_demo"
+ready = work / f"scene_ready_{args.views}_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
 if rank == 0:
     synthetic.write_blender_scene(work / "scene", n_train=args.views, n_val=1, n_test=3)
+    ready.touch()
+while not ready.exists():                  # the other ranks: the scene is written once, by rank 0 (no process group exists yet)
+    time.sleep(0.2)
 torch.manual_seed(0)
 t0 = time.time()
 run = train_nerf.main(["-n", "demo", "--gpu", "-s", str(args.steps), "-rd", str(work / "exp"), "-r", "4096", "full", "-b", str(work / "scene"),
