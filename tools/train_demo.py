@@ -27,10 +27,18 @@ run = train_nerf.main(["-n", "demo", "--gpu", "-s", str(args.steps), "-rd", str(
                        "-cr", str(args.crop_epochs)])
 torch.cuda.synchronize()
 train_s = time.time() - t0
+import multi_gpu
+import torch.distributed as dist
 if rank == 0:
-    psnr, ssim = score.calculate_scores(run.last_checkpoint, work / "scene", 4096)
+    # rank 0 alone scores: view_reconstruction must not shard the frames over ranks that are not rendering (an all-gather nobody
+    # else joins would hang - measured the hard way)
+    with multi_gpu.local_only():
+        psnr, ssim = score.calculate_scores(run.last_checkpoint, work / "scene", 4096)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     print(json.dumps({"what": "train_nerf.py full on the analytic three-sphere scene (800x800, Blender layout), then score.py on its test split",
                       "train_views": args.views, "steps": run.global_step, "rays_per_step": 4096 * world, "n_gpus": world, "train_wall_s": train_s,
                       "ms_per_step_wall": train_s / max(run.global_step, 1) * 1e3, "final_train_loss": float(run.metrics().get("train_loss", float("nan"))),
                       "test_psnr_db": psnr, "test_ssim": ssim, "checkpoint": run.last_checkpoint.name}))
+if dist.is_available() and dist.is_initialized():
+    dist.barrier()
+    dist.destroy_process_group()
