@@ -39,7 +39,28 @@ def _worker(rank, ws, port, results):
         ok_train = bool(torch.allclose(flat.flat, sum(gathered) / ws)) and all(
             p.grad.data_ptr() >= flat.flat.data_ptr() for p in model.parameters())
         ok_views = bool(torch.equal(torch.cat([p.grad.flatten() for p in model.parameters()]), flat.flat))
-        results[rank] = (ok_render, ok_train, ok_views)
+        # --- the product's form (optim.FlatAdam): the optimiser owns the flat gradient buffer and applies 1 / world itself
+        # (grad_scale), so the reduced buffer holds the SUM; a first slice may be reduced early (the coarse network's gradients)
+        class FlatOpt:
+            def __init__(self, n):
+                self.flat_grads, self.grad_scale = torch.zeros(n), 1.0
+        opt = FlatOpt(10)
+        params = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(6))]
+        folded = FlatGradients(params, opt)
+        ok_fold = folded.flat is opt.flat_grads and opt.grad_scale == 1.0 / ws and folded.folded
+        folded.zero()
+        opt.flat_grads += torch.arange(10, dtype=torch.float32) * (rank + 1)
+        mine = opt.flat_grads.clone()
+        folded.reduce_async(4)                        # the first 4 values are final: their reduction starts now
+        folded.all_reduce_mean()                      # the rest, wait for both, NO rescale
+        total = sum((torch.arange(10, dtype=torch.float32) * (r + 1)) for r in range(ws))
+        ok_fold = ok_fold and bool(torch.equal(opt.flat_grads, total)) and folded._pending == []
+        ok_fold = ok_fold and bool(torch.allclose(folded.norm(), (total / ws).norm()))
+        # local_only(): inside it the render helpers see a single process (rank-0-only validation frames)
+        with multi_gpu.local_only():
+            alone = multi_gpu.world() == (0, 1) and bool(torch.equal(multi_gpu.sharded_render(render_rays, o, d), ref))
+        ok_fold = ok_fold and alone and multi_gpu.world() == (rank, ws)
+        results[rank] = (ok_render, ok_train, ok_views and ok_fold)
     finally:
         dist.destroy_process_group()
 
