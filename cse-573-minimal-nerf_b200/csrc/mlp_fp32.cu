@@ -2,7 +2,7 @@
 //
 // This is the tight-parity / any-shape path (arbitrary position_dim, direction_dim, N, S): it evaluates
 // nerf_model.py:362-389 with fp32 FMAs and accurate sincosf, and is what the tensor-core kernel
-// (mlp_tc.cu) is cross-checked against on the device.  It is not the throughput path.
+// (mlp_tc3.cu) is cross-checked against on the device.  It is not the throughput path.
 #include "common.cuh"
 
 namespace nerf {

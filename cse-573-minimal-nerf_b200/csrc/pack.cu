@@ -1,5 +1,5 @@
 // pack.cu - K5: fp32 nn.Linear parameters (state_dict order) -> the bf16 swizzled stage image + fp32 biases
-// that mlp_tc.cu streams with bulk copies (layout in pack_layout.cuh).
+// that mlp_tc3.cu streams with bulk copies (layout in pack_layout.cuh).
 #include "common.cuh"
 #include "pack_layout.cuh"
 #include "umma.cuh"

@@ -1,5 +1,5 @@
 // pack_layout.cuh - layout of one network's packed weights and the per-tile step/stage schedule shared by
-// the packer (pack.cu) and the fused tensor-core kernel (mlp_tc.cu).
+// the packer (pack.cu) and the fused tensor-core kernels (mlp_tc3.cu, mlp_tc_bwd3.cu, wgrad_tc.cu).
 //
 // One NeRFModel (nerf_model.py:331-360, position_dim 10, direction_dim 4) is evaluated per 128-sample tile
 // as 17 "steps", each one accumulator region (<=128 fp32 columns of TMEM) produced by a run of K=64 weight
@@ -104,7 +104,7 @@ constexpr Layout kLayout = make_layout();
 static_assert(kLayout.weight_bytes == 57u * kStageBytesFull + 6u * kStageBytesSmall, "stage accounting");
 
 
-// ---- backward (dgrad) image: B = W^T stages in the order mlp_tc_bwd.cu consumes them, then two fp32 constant blocks
+// ---- backward (dgrad) image: B = W^T stages in the order mlp_tc_bwd3.cu consumes them, then two fp32 constant blocks
 //   steps 0,1   rgb_fn.0 dgrad   d feat[:, 128h:128h+128] = dr[128 x K=128] . W8[:, 128h:...]      2 stages per half
 //   steps 2..13 feature_fn.4, feature_fn.2, feature_fn.0 (h part), mlp.6, mlp.4, mlp.2              4 stages per half
 constexpr int kStagesT = 52;

@@ -135,10 +135,9 @@ NERF_API int nerf_mlp_forward_tc(const void* packed, const float* o, const float
  * feature_fn.0, feature_fn.2, feature_fn.4 at feature 256*k; rgb_fn.0 at 1792).  act_out: ceil(N*S/128)*128 rows x 1920
  * features, TILED CHUNK-MAJOR: element (row, f) at ((row/128 * 240 + f/8) * 128 + row%128) * 8 + f%8. */
 /* mask_out: ceil(N*S/128)*128 * 30 * 8 bytes of ReLU sign bits (one bit per sample and hidden feature), all the dgrad kernel
- * needs from the activations.  The encoding is private to the forward / dgrad kernel pair that is active: the default two-tile
- * kernels write one 32-bit word per (sample, 32-feature group) at word ((row/128)*60 + f/32)*128 + row%128, bit 15-j / 31-j =
- * [pre-activation of feature 32*(f/32) + 2j / 2j+1 is negative]; the diagnostic one-tile kernels (NERF_TC_ONE_TILE=1) write 64-bit
- * words, word ((row/128)*30 + f/64)*128 + row%128, bit i = [act(row, 64*(f/64)+i) > 0].  Treat it as opaque. */
+ * needs from the activations.  The encoding is private to the forward / dgrad kernel pair: one 32-bit word per (sample, 32-feature
+ * group) at word ((row/128)*60 + f/32)*128 + row%128, bit 15-j / 31-j = [pre-activation of feature 32*(f/32) + 2j / 2j+1 is negative].
+ * Treat it as opaque. */
 NERF_API int nerf_mlp_forward_tc_train(const void* packed, const float* o, const float* d, const float* ts,
                               int64_t N, int S, float* sigma, float* rgb, void* act_out, void* mask_out, void* stream);
 /* ---- backward of H8 (dgrad chain) on the tensor cores.  packed_t = nerf_pack_weights_t image (W^T stages, bf16).

@@ -59,7 +59,7 @@ fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p] * 4
 dbg = torch.zeros(148 * 16 + 128, dtype=torch.int64, device=dev)
 import os
-G = int(os.environ.get("NERF_TC_MAX_CTAS", "148"))
+G = 148
 for it in range(3):
     dbg.zero_()
     dbg[148 * 16 + 120] = int(os.environ.get('NERF_PROF_FLAGS', '0'))
