@@ -502,7 +502,16 @@ def main():
                   "ms_per_frame": s_ms, "rays_per_s": nrays / (s_ms * 1e-3), "speedup_vs_one_rank_e2e": e_ms / s_ms, "n_gpus": world,
                   "ms_per_frame_median": s_med, "ms_steps": s_steps, "scaling": "strong"}
 
-    train = None if args.no_train else bench_train(args, rank, world, dev)
+    train = None
+    if not args.no_train:
+        try:
+            train = bench_train(args, rank, world, dev)
+        except Exception as exc:                 # the render line must not be lost to a failure of the extra training section
+            if world > 1:
+                raise                            # (ranks must not diverge: under torchrun a failure stays a failure)
+            import traceback
+            traceback.print_exc()
+            train = {"metric": "rays/sec train (device-timed)", "value": None, "error": f"{type(exc).__name__}: {exc}"[:500]}
 
     if rank == 0:
         line = {
