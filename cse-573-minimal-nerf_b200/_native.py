@@ -12,7 +12,7 @@ import torch
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libnerf_b200.so"
 DEBUG_LIB_PATH = HERE.parent / "tools" / "libnerf_b200_debug.so"      # probes + cycle-counter kernel forms; tools/ and tests only
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _c_f32p = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -45,7 +45,7 @@ _PROTOTYPES = {
     "nerf_pack_weights_t": (_int, [_vp, _vp, _vp]),
     "nerf_mlp_backward_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "nerf_mlp_backward_tc_fused": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
-    "nerf_wgrad_tc": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    "nerf_wgrad_tc": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _int, _vp]),
     "nerf_mlp_forward_tc_points": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "nerf_mlp_composite_tc_supported": (_int, [_int]),
     "nerf_mlp_composite_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -104,7 +104,7 @@ __device__ long long g_wgrad_cycles[2 * 160];
 
 __global__ void __launch_bounds__(wg::kThreads, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __restrict__ dz, const float* __restrict__ o_rays,
-                const float* __restrict__ d_rays, const float* __restrict__ ts, int64_t total, int S, Grads G) {
+                const float* __restrict__ d_rays, const float* __restrict__ ts, int64_t total, int S, Grads G, const bool one_cta_per_job) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + wg::kOffBars);
@@ -123,10 +123,13 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ acts, const __nv_bfloat16* __r
 
     // which job, and which share of its tiles, this CTA owns
     int job_idx = 0, first = blockIdx.x;
-    while (job_idx < wg::kNumJobs && first >= wg::c_jobs[job_idx].ctas) { first -= wg::c_jobs[job_idx].ctas; ++job_idx; }
+    // deterministic form: ONE CTA per job (grid = 9) walks all tiles in order, so every gradient element receives exactly one
+    // atomic add and the result is bit-reproducible (a parity-debugging mode: ~16x slower)
+    if (one_cta_per_job) { job_idx = blockIdx.x; first = 0; }
+    else while (job_idx < wg::kNumJobs && first >= wg::c_jobs[job_idx].ctas) { first -= wg::c_jobs[job_idx].ctas; ++job_idx; }
     if (job_idx >= wg::kNumJobs) return;                 // spare CTAs
     const wg::Job job = wg::c_jobs[job_idx];
-    const int stride = job.ctas, nA = job.nA;
+    const int stride = one_cta_per_job ? 1 : job.ctas, nA = job.nA;
     const int b_cols = job.b_cols16 * 16;
     const bool has_pe = job.pe != wg::PE_NONE;
     const int region_cols = b_cols + (has_pe ? 64 : 0);  // TMEM columns per A block
@@ -418,7 +421,7 @@ extern "C" NERF_API int nerf_debug_wgrad_cycles(long long* host_out320) {
 #endif
 
 extern "C" int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
-                             float* const* grads20_host, void* stream) {
+                             float* const* grads20_host, int deterministic, void* stream) {
     NERF_REQUIRE(N >= 0 && S > 0, "nerf_wgrad_tc: bad size");
     if (N == 0) return 0;
     NERF_REQUIRE(acts && dz && o && d && ts && grads20_host, "nerf_wgrad_tc: null pointer");
@@ -434,7 +437,7 @@ extern "C" int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, c
         if (e != cudaSuccess) { set_error("nerf_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
         attrs_done(attr_mask);
     }
-    wgrad_tc_kernel<<<wg::kGridCtas, wg::kThreads, wg::kSmemBytes, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)acts, (const __nv_bfloat16*)dz, o, d, ts, N * S, S, G);
+    wgrad_tc_kernel<<<deterministic ? wg::kNumJobs : wg::kGridCtas, wg::kThreads, wg::kSmemBytes, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)acts, (const __nv_bfloat16*)dz, o, d, ts, N * S, S, G, deterministic != 0);
     return check_launch("nerf_wgrad_tc");
 }

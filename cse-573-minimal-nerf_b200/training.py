@@ -60,6 +60,8 @@ def composite_backward(sigma, rgb, ts, g_ray):
 
 
 FUSE_COMPOSITE_BACKWARD = True     # the compositing backward inside the dgrad kernel's producer warps (nerf_mlp_backward_tc_fused)
+DETERMINISTIC_WGRAD = False        # True: one CTA per wgrad job instead of split-K + atomics - bit-reproducible gradients, ~16x slower
+                                   # weight-gradient kernel; a parity-debugging mode
 
 
 def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray, accumulate_into_grad=False):
@@ -96,7 +98,8 @@ def mlp_backward(model, o, d, ts, sigma, rgb, acts, g_ray, accumulate_into_grad=
             off += p.numel()
     arr = (ctypes.c_void_p * 20)(*[g.data_ptr() for g in grads])
     with nat.timed_kernel("wgrad_tc_kernel", M):
-        nat.check(nat.lib().nerf_wgrad_tc(nat.ptr(acts), nat.ptr(dz_t), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, arr, nat.stream()),
+        nat.check(nat.lib().nerf_wgrad_tc(nat.ptr(acts), nat.ptr(dz_t), nat.ptr(o), nat.ptr(d), nat.ptr(ts), N, S, arr,
+                                          1 if DETERMINISTIC_WGRAD else 0, nat.stream()),
                   "nerf_wgrad_tc")
     return [None] * 20 if direct else grads
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NERF_ABI_VERSION 2
+#define NERF_ABI_VERSION 3
 
 /* libnerf_b200.so is built with -fvisibility=hidden: the functions declared here are its whole dynamic symbol table
  * (tests/test_abi.py compares `nm -D` with this header). */
@@ -159,8 +159,11 @@ NERF_API int nerf_mlp_backward_tc_fused(const void* packed_t, const void* masks,
  * o, d, ts as in the forward (PE(x) / PE(dir) operands are recomputed).  grads20_host: HOST array of 20 device pointers
  * (state_dict order, fp32, nn.Linear layout), ACCUMULATED into with atomics - zero them first. */
 NERF_API int nerf_wgrad_tc(const void* acts, const void* dz, const float* o, const float* d, const float* ts, int64_t N, int S,
-                  float* const* grads20_host, void* stream);
-/* Same kernel with explicit sample points [N,S,3] (the NeRFModel.forward(samples, direc) call surface). */
+                           float* const* grads20_host, int deterministic, void* stream);
+/* deterministic = 0: 148 CTAs split every job's tiles (split-K) and add their partial sums with fp32 atomics - the order of those
+ * adds, hence the last bits of the gradients, varies from run to run (relative spread ~1e-7).  deterministic != 0: one CTA per job
+ * walks all tiles in order and every gradient element receives exactly one add - bit-reproducible, ~16x slower; for parity debugging. */
+/* nerf_mlp_forward_tc with explicit sample points [N,S,3] (the NeRFModel.forward(samples, direc) call surface). */
 NERF_API int nerf_mlp_forward_tc_points(const void* packed, const float* samples, const float* d,
                                int64_t N, int S, float* sigma, float* rgb, void* stream);
 

@@ -27,7 +27,7 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), f"{name} declared in include/nerf_b200.h but not exported"
     import _native
     assert declared == set(_native.exported_symbols())
-    assert lib.nerf_abi_version() == 2
+    assert lib.nerf_abi_version() == 3
     assert lib.nerf_packed_bytes() == 57 * 16384 + 6 * 2048 + 1928 * 4
 
 

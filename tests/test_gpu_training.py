@@ -105,6 +105,35 @@ def test_gradient_run_to_run_spread_is_atomics_noise(golden):
     assert worst < 1e-5
 
 
+def test_deterministic_wgrad_is_bit_reproducible_and_agrees_with_split_k(golden, monkeypatch):
+    """training.DETERMINISTIC_WGRAD: one CTA per wgrad job, one add per gradient element.  Three backward passes over the same
+    batch give bit-identical gradients, and they agree with the default split-K form to 1e-3 (relative 2-norm per parameter: the
+    single CTA's fp32 accumulators in TMEM run over every tile of the batch, a longer summation chain than a split-K share's)."""
+    import training
+    g = golden["network"]
+    net = make_net(4, "dense")
+    o, d, target = T(g["o"], DEV), T(g["d"], DEV), T(g["target"], DEV)
+
+    def grads():
+        net.zero_grad(set_to_none=True)
+        pred = net.forward(o, d, rand=rand_triple(540, 64, device=DEV))
+        (F.mse_loss(pred["coarse_rgb_rays"], target) + F.mse_loss(pred["fine_rgb_rays"], target)).backward()
+        return [p.grad.clone() for p in net.parameters()]
+
+    split_k = grads()
+    monkeypatch.setattr(training, "DETERMINISTIC_WGRAD", True)
+    runs = [grads() for _ in range(3)]
+    for other in runs[1:]:
+        for (name, _), a, b in zip(net.named_parameters(), runs[0], other):
+            assert torch.equal(a, b), name
+    worst = 0.0
+    for (name, _), a, b in zip(net.named_parameters(), runs[0], split_k):
+        rel = float((a.double() - b.double()).norm() / a.double().norm().clamp(min=1e-30))
+        worst = max(worst, rel)
+        assert rel < 1e-3, (name, rel)
+    print(f"deterministic vs split-K wgrad: worst relative gradient difference {worst:.2e}")
+
+
 def test_forward_only_networks_fail_backward_with_the_reason():
     """precision='fp32' / other encoding sizes run the forward-only exact kernel: forward works with gradients enabled, the
     backward raises a RuntimeError that says why; a training run refuses them up front (train_nerf.py -p / -d)."""
