@@ -13,7 +13,8 @@ algorithms are restated below with numpy + scipy.ndimage (which is what skimage 
           per-channel values.
 
 Parity status: UNPINNED against skimage itself (not installable offline); pinned only by the known answers in
-tests/test_oracle_golden.py (identical images -> 1, constant offset -> closed form, PSNR of a unit error = 20 log10 255).
+tests/test_oracle_golden.py (identical images -> 1, constant offset -> closed form, PSNR of a unit error = 20 log10 255) and by two
+implementations that share no code with this file (OpenCV's cv2.PSNR; a brute-force per-window evaluation of the SSIM definition).
 """
 import numpy as np
 from scipy.ndimage import uniform_filter

@@ -3,6 +3,7 @@ unmodified reference, plus the known-answer values of the reference's own unit t
 import hashlib
 
 import numpy as np
+import pytest
 import torch
 
 import synthetic
@@ -170,6 +171,33 @@ def test_score_oracle_known_answers():
     noisy = np.clip(a.astype(np.int16) + rng.integers(-3, 4, size=a.shape), 0, 255).astype(np.uint8)
     other = rng.integers(0, 256, size=a.shape, dtype=np.uint8)
     assert S.structural_similarity(a, noisy) > 0.98 > 0.2 > S.structural_similarity(a, other)
+
+
+def test_score_oracle_against_independent_implementations():
+    """Two cross-checks that do not share code with oracle/score_oracle.py (still not skimage itself: the oracle stays "parity
+    unpinned" in the tier's sense).  PSNR against OpenCV's `cv2.PSNR` (R = 255, all channels pooled - the same definition skimage
+    uses for uint8 input).  SSIM against a brute-force evaluation of its definition: every fully-inside 7x7 window, means and SAMPLE
+    (ddof = 1) variances / covariance from `np.var` / `np.cov`, S averaged over windows then over channels."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import score_oracle as S
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, size=(23, 31, 3), dtype=np.uint8)
+    b = np.clip(a.astype(np.int16) + rng.integers(-20, 21, size=a.shape), 0, 255).astype(np.uint8)
+    assert abs(S.peak_signal_noise_ratio(a, b) - cv2.PSNR(a, b)) < 1e-9
+
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    per_channel = []
+    for c in range(3):
+        x, y = a[..., c].astype(np.float64), b[..., c].astype(np.float64)
+        vals = []
+        for i in range(x.shape[0] - 6):
+            for j in range(x.shape[1] - 6):
+                wx, wy = x[i:i + 7, j:j + 7].ravel(), y[i:i + 7, j:j + 7].ravel()
+                ux, uy = wx.mean(), wy.mean()
+                vx, vy, vxy = wx.var(ddof=1), wy.var(ddof=1), np.cov(wx, wy, ddof=1)[0, 1]
+                vals.append(((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2)))
+        per_channel.append(np.mean(vals))
+    assert abs(S.structural_similarity(a, b) - np.mean(per_channel)) < 1e-10
 
 
 def test_oracle_training_path_matches_reference_trajectory(golden):
