@@ -31,6 +31,33 @@ def test_header_symbols_exported(lib):
     assert lib.nerf_packed_bytes() == 57 * 16384 + 6 * 2048 + 1928 * 4
 
 
+def test_ctypes_prototypes_match_the_header():
+    """Every declaration of include/nerf_b200.h has a ctypes prototype in _native._PROTOTYPES with the same number of arguments
+    and a matching kind per argument (pointer / 64-bit integer / int / float): a signature edited on one side only would
+    otherwise corrupt the call silently."""
+    import _native
+    header = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "nerf_b200.h").read_text(), flags=re.S)
+    decls = re.findall(r"NERF_API\s+[\w\s\*]+?\b(nerf_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+    assert len(decls) == len(_native._PROTOTYPES)
+
+    def kind_of_c(arg):
+        arg = " ".join(arg.split())
+        if "*" in arg:
+            return "pointer"
+        return {"int64_t": "i64", "int": "int", "float": "float", "size_t": "size"}[arg.rsplit(" ", 1)[0].replace("const ", "")]
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) == "P":
+            return "pointer"
+        return {ctypes.c_int64: "i64", ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_size_t: "size"}[t]
+
+    for name, args in decls:
+        args = args.strip()
+        c_kinds = [] if args in ("", "void") else [kind_of_c(a) for a in args.split(",")]
+        proto = _native._PROTOTYPES[name][1]
+        assert [kind_of_ctypes(t) for t in proto] == c_kinds, name
+
+
 def test_dynamic_symbol_table_is_exactly_the_header(lib):
     """The product library is built with -fvisibility=hidden: `nm -D` must list the functions of include/nerf_b200.h and
     nothing else of ours (no nerf_debug_* probes, no internal C++ symbols); the probes live in tools/libnerf_b200_debug.so."""
