@@ -314,13 +314,22 @@ def bench_train(args, rank, world, dev):
         e = per.setdefault(name, {"ms": 0.0, "samples": 0})
         e["ms"] += a.elapsed_time(b) / 4
         e["samples"] += units // 4
+    # DRAM bytes per kernel from the committed ncu --set full capture of the same step shape (two launches per kernel and step:
+    # coarse + fine network - summed, like the algorithmic bytes beside them)
+    dram, dram_src = {}, None
+    for tf_ in sorted((ROOT / "profiles").glob("r*_train_traffic.json"), reverse=True):
+        rec = json.loads(tf_.read_text())
+        if rec.get("rays_per_step") == n and rec.get("coarse_samples") == COARSE and rec.get("fine_samples") == COARSE + FINE:
+            dram = {k: sum(v["dram_bytes_per_launch"]) for k, v in rec["kernels"].items()}
+            dram_src = f"profiles/{tf_.name}: {rec.get('what', '')}"
+            break
     kernels = []
     for name, e in per.items():
         gb = e["samples"] * TRAIN_BYTES.get(name, 0) / 1e9
         tf = e["samples"] * TRAIN_FLOPS.get(name, 0) / 1e12
         sec = e["ms"] * 1e-3
         kernels.append({"kernel": name, "ms_per_step": e["ms"], "algorithmic_gb": gb, "hbm_gbs": gb / sec, "hbm_frac": gb / sec / pk["hbm_gbs"],
-                        "tflops": tf / sec, "tensor_frac_of_sustained": tf / sec / pk["tflops_sustained"]})
+                        "tflops": tf / sec, "tensor_frac_of_sustained": tf / sec / pk["tflops_sustained"], "traffic": dram.get(name)})
     torch.cuda.synchronize()
     stepper.close()                               # destroys the CUDA graph (and the NCCL work captured in it) before the process group goes
     kms = sum(k["ms_per_step"] for k in kernels)
@@ -332,7 +341,7 @@ def bench_train(args, rank, world, dev):
         roofline_train = {"bound": "hbm" if hbm_bound else "tensor", "kernel": dom["kernel"],
                           "achieved": dom["hbm_gbs"] if hbm_bound else dom["tflops"], "peak": pk["hbm_gbs"] if hbm_bound else pk["tflops_sustained"],
                           "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": dom["hbm_frac"] if hbm_bound else dom["tensor_frac_of_sustained"],
-                          "traffic": None, "kernels": kernels, "kernel_ms_per_step": kms, "kernel_share_of_step": kms / eager_ms,
+                          "traffic": dom.get("traffic"), "traffic_source": dram_src, "kernels": kernels, "kernel_ms_per_step": kms, "kernel_share_of_step": kms / eager_ms,
                           "measured_in": "4 launch-by-launch steps queued behind a device-side delay (kernels back to back), CUDA events per kernel",
                           "launch_by_launch_step_ms": eager_ms, "kernel_ms_over_replayed_step": kms / ms,
                           "step_algorithmic_tflops": tfl, "step_frac_of_sustained_peak": tfl / pk["tflops_sustained"],
